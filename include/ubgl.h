@@ -1,0 +1,194 @@
+/* ubgl.h -- C ABI of the B200-native fluid-step hot path (libubgl.so).
+ *
+ * Drop-in boundary for te42kyfo/ubootgl's `Simulation` / `MG` solver classes:
+ * the repo's own C++ mirror of those classes (ubootgl_b200/host/) and any
+ * other binding (ctypes in ubootgl_b200/capi.py) call only what is declared
+ * here.  Plain C types, opaque handles, `int` status: 0 = ok, negative = error
+ * (UBGL_E_*), text via ubgl_last_error().  No exceptions cross the boundary.
+ *
+ * Conventions (all from the reference, file:line under te42kyfo/ubootgl):
+ *  - host grids are UNPADDED row-major fp32, idx = y*width + x (db2dgrid.hpp:19);
+ *    staggered sizes: vx (W-1)xH, vy Wx(H-1), cell fields WxH
+ *    (simulation.hpp:22-29).  The library re-pitches them on the device.
+ *  - a handle is used by one host thread at a time and owns its own CUDA stream;
+ *    host pointers are caller-owned and only touched during the call.
+ *  - there is NO CPU fallback: every entry point that computes fails with
+ *    UBGL_E_CUDA when no sm_100 device is usable.
+ */
+#ifndef UBGL_H
+#define UBGL_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UBGL_VERSION 100
+
+/* status codes */
+#define UBGL_OK 0
+#define UBGL_E_ARG (-1)    /* bad argument (null handle, size, field id, ...) */
+#define UBGL_E_CUDA (-2)   /* CUDA runtime error, see ubgl_last_error() */
+#define UBGL_E_STATE (-3)  /* call not valid in the handle's current state */
+#define UBGL_E_NOMEM (-4)
+
+/* field ids -- the public data members of Simulation (simulation.hpp:128-132) */
+enum ubgl_field {
+  UBGL_FLAG = 0,        /* Simulation::flag            W x H     */
+  UBGL_VX = 1,          /* Simulation::vx front buffer (W-1) x H */
+  UBGL_VY = 2,          /* Simulation::vy front buffer W x (H-1) */
+  UBGL_VXB = 3,         /* Simulation::vx back buffer  (db2dgrid.hpp:103) */
+  UBGL_VYB = 4,         /* Simulation::vy back buffer  */
+  UBGL_P = 5,           /* Simulation::p               W x H */
+  UBGL_F = 6,           /* Simulation::f (divergence rhs) */
+  UBGL_VX_ACCUM = 7,    /* Simulation::vx_accum        */
+  UBGL_VY_ACCUM = 8,    /* Simulation::vy_accum        */
+  UBGL_R = 9,           /* residual field of the last ubgl_sim_residual() */
+  UBGL_VX_CURRENT = 10, /* Simulation::vx_current      */
+  UBGL_VY_CURRENT = 11, /* Simulation::vy_current      */
+  UBGL_NUM_FIELDS = 12
+};
+
+/* Simulation::BC (simulation.hpp:69), same numeric order */
+enum ubgl_bc {
+  UBGL_BC_INFLOW = 0,
+  UBGL_BC_OUTFLOW = 1,
+  UBGL_BC_OUTFLOW_ZERO_PRESSURE = 2,
+  UBGL_BC_NOSLIP = 3
+};
+
+/* stages of Simulation::step (simulation.cpp:356-374) for stage-level parity */
+enum ubgl_stage {
+  UBGL_ST_ACCUM = 0,   /* applyAccumulatedVelocity  simulation.cpp:376-396 */
+  UBGL_ST_DIFFUSE = 1, /* diffuse                   simulation.cpp:104-162 */
+  UBGL_ST_ADVECT = 2,  /* advect                    simulation.cpp:241-354 */
+  UBGL_ST_SETVBCS = 3, /* setVBCs                   simulation.cpp:80-102  */
+  UBGL_ST_PROJECT = 4, /* project                   simulation.cpp:164-208 */
+  UBGL_ST_SAVE = 5     /* saveCurrentVelocityFields simulation.cpp:16-19   */
+};
+
+/* tunables (ubgl_sim_set_option / ubgl_mg_set_option) */
+enum ubgl_option {
+  UBGL_OPT_VCYCLES = 0,  /* V-cycles per project(); default 2 (simulation.cpp:189-190) */
+  UBGL_OPT_FUSED = 1,    /* 1 (default): fused / temporally blocked kernels;
+                            0: one plain kernel per reference stage (same results) */
+  UBGL_OPT_GRAPH = 2,    /* 1 (default): replay the step as a captured CUDA graph */
+  UBGL_OPT_TIMING = 3    /* 1: record per-stage CUDA events (ubgl_sim_stage_ms) */
+};
+
+typedef struct ubgl_sim ubgl_sim_t; /* device-resident Simulation state */
+typedef struct ubgl_mg ubgl_mg_t;   /* device-resident stand-alone MG   */
+
+/* ---- library -------------------------------------------------------------- */
+int ubgl_version(void);
+const char *ubgl_last_error(void); /* thread-local text of the last failure */
+int ubgl_device_count(void);       /* usable CUDA devices, 0 if none */
+
+/* ---- class Simulation (simulation.hpp:18-141) ----------------------------- */
+/* Simulation(flag, pwidth, mu) simulation.hpp:32-67: copies flag, BCs
+ * W=INFLOW E=OUTFLOW_ZERO_PRESSURE N,S=NOSLIP, vx(0,y)=1 on both buffers,
+ * builds the MG flag pyramid, h = pwidth/(W-1).  Requires W,H >= 8. */
+int ubgl_sim_create(const float *flag, int W, int H, float pwidth, float mu,
+                    int device, ubgl_sim_t **out);
+int ubgl_sim_destroy(ubgl_sim_t *sim);
+int ubgl_sim_set_option(ubgl_sim_t *sim, int option, int value);
+/* members bcWest/bcEast/bcNorth/bcSouth (simulation.hpp:124) */
+int ubgl_sim_set_bc(ubgl_sim_t *sim, int west, int east, int north, int south);
+/* whole-field H->D / D->H of one public member; host layout as the reference */
+int ubgl_sim_upload(ubgl_sim_t *sim, int field, const float *host);
+int ubgl_sim_download(ubgl_sim_t *sim, int field, float *host);
+/* memcpy(sim.flag.data(), ...) + sim.mg.updateFields(sim.flag)
+ * (ubootgl_app.cpp:111-112, pressure_solver.hpp:34-57) */
+int ubgl_sim_update_flag(ubgl_sim_t *sim, const float *flag);
+/* coarse flag mask of MG level `level` (flagcs[level]); sizes via
+ * ubgl_sim_mg_level_size.  Bit-exact with the reference. */
+int ubgl_sim_mg_levels(ubgl_sim_t *sim);
+int ubgl_sim_mg_level_size(ubgl_sim_t *sim, int level, int *w, int *h);
+int ubgl_sim_mg_get_flagc(ubgl_sim_t *sim, int level, float *host);
+/* member `sinks` (simulation.hpp:140): xyz triples in physical coordinates as
+ * pushed by explosion.cpp:33; stamped into f, decayed and erased inside
+ * project exactly as simulation.cpp:173-187.  get returns the survivors. */
+int ubgl_sim_set_sinks(ubgl_sim_t *sim, const float *xyz, int n);
+int ubgl_sim_get_sinks(ubgl_sim_t *sim, float *xyz, int cap, int *n);
+/* Simulation::step(dt) (simulation.cpp:356-374) on the device-resident state.
+ * Asynchronous on the handle's stream; ubgl_sim_sync() or a download waits. */
+int ubgl_sim_step(ubgl_sim_t *sim, float dt);
+/* One stage of step() (enum ubgl_stage), for parity tests. */
+int ubgl_sim_stage(ubgl_sim_t *sim, int stage, float dt);
+/* step() as the reference's callers see it, with HOST mirrors: uploads flag
+ * (if non-null; rebuilds the pyramid), vx_accum/vy_accum (if non-null; the
+ * host arrays are zeroed like simulation.cpp:384,392), runs step(dt), then
+ * downloads vx, vy, p, vx_current, vy_current (each if non-null). */
+typedef struct ubgl_host_mirrors {
+  const float *flag;   /* in, optional */
+  float *vx_accum;     /* in (then zeroed), optional */
+  float *vy_accum;     /* in (then zeroed), optional */
+  float *vx, *vy, *p;  /* out, optional */
+  float *vx_current;   /* out, optional */
+  float *vy_current;   /* out, optional */
+} ubgl_host_mirrors;
+int ubgl_sim_step_host(ubgl_sim_t *sim, float dt, const ubgl_host_mirrors *m);
+int ubgl_sim_sync(ubgl_sim_t *sim);
+/* calculateResidualField(p, f, flag, r, h) (pressure_solver.cpp:91-116) on the
+ * resident p/f/flag; r readable as field UBGL_R. */
+int ubgl_sim_residual(ubgl_sim_t *sim, float *l2);
+/* MG::solve(p, f, flag, h, true) on the resident fields, `cycles` times */
+int ubgl_sim_mg_solve(ubgl_sim_t *sim, int cycles);
+/* device address + pitch (in floats) of a resident field, for zero-copy
+ * producers/consumers (tracers, interop, benchmark input generation). */
+int ubgl_sim_device_ptr(ubgl_sim_t *sim, int field, void **dptr, int *pitch);
+/* per-stage device time of the last step when UBGL_OPT_TIMING=1 */
+int ubgl_sim_stage_ms(ubgl_sim_t *sim, int stage, float *ms);
+/* number of kernels this handle launched so far (graph replays included) */
+long long ubgl_sim_launch_count(ubgl_sim_t *sim);
+/* the CUDA stream (cudaStream_t) the handle launches on */
+void *ubgl_sim_stream(ubgl_sim_t *sim);
+
+/* ---- class MG (pressure_solver.hpp:13-76) ---------------------------------- */
+/* MG(int w, int h): level pyramid by integer halving while w>3 && h>3, all
+ * coarse flags 1.0 (pressure_solver.hpp:16-31).  Requires >= 2 levels. */
+int ubgl_mg_create(int W, int H, int device, ubgl_mg_t **out);
+int ubgl_mg_destroy(ubgl_mg_t *mg);
+int ubgl_mg_set_option(ubgl_mg_t *mg, int option, int value);
+int ubgl_mg_levels(ubgl_mg_t *mg);
+int ubgl_mg_level_size(ubgl_mg_t *mg, int level, int *w, int *h);
+/* MG::updateFields(flag) (pressure_solver.hpp:34-57) */
+int ubgl_mg_update_fields(ubgl_mg_t *mg, const float *flag);
+int ubgl_mg_get_flagc(ubgl_mg_t *mg, int level, float *host);
+/* MG::solve(p, f, flag, h, zeroGradientBC) with host grids
+ * (pressure_solver.hpp:59-62): uploads p, f, flag, runs one V-cycle, downloads p.
+ * As in the reference, level 0 uses the caller's flag and levels >= 1 the
+ * pyramid from the last updateFields. */
+int ubgl_mg_solve_host(ubgl_mg_t *mg, float *p, const float *f,
+                       const float *flag, float h, int zero_gradient_bc);
+/* resident variant: upload once, cycle many times, download */
+int ubgl_mg_upload(ubgl_mg_t *mg, const float *p, const float *f,
+                   const float *flag); /* each optional */
+int ubgl_mg_download_p(ubgl_mg_t *mg, float *p);
+int ubgl_mg_solve(ubgl_mg_t *mg, float h, int zero_gradient_bc, int cycles);
+int ubgl_mg_residual(ubgl_mg_t *mg, float h, float *l2);
+int ubgl_mg_sync(ubgl_mg_t *mg);
+long long ubgl_mg_launch_count(ubgl_mg_t *mg);
+void *ubgl_mg_stream(ubgl_mg_t *mg);
+
+/* ---- pressure_solver.cpp free functions, host grids in/out ---------------- */
+/* rbgs(p,f,flag,h,alpha) x sweeps, canonical red-black order
+ * (pressure_solver.cpp:35-72; the pipelined path :73-87 is not reproduced) */
+int ubgl_rbgs(float *p, const float *f, const float *flag, int w, int h,
+              float hh, float alpha, int sweeps);
+/* calculateResidualField (pressure_solver.cpp:91-116) */
+int ubgl_residual(const float *p, const float *f, const float *flag, float *r,
+                  int w, int h, float hh, float *l2);
+/* restrict (pressure_solver.cpp:118-132); rc is (w/2) x (h/2), border 0 */
+int ubgl_restrict(const float *r, int w, int h, float *rc);
+/* prolongate (pressure_solver.cpp:134-172); e is w x h, ec/flagc (w/2)x(h/2) */
+int ubgl_prolongate(float *e, int w, int h, const float *ec, const float *flagc,
+                    const float *flag);
+/* correct (pressure_solver.cpp:174-181) */
+int ubgl_correct(float *p, const float *e, int w, int h);
+/* setZeroGradientBC (pressure_solver.cpp:183-192) */
+int ubgl_zero_gradient_bc(float *p, int w, int h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UBGL_H */

@@ -1,0 +1,3 @@
+// TEST INFRASTRUCTURE ONLY (oracle build shim): forwards to the minimal glm.hpp stand-in.
+#pragma once
+#include "../glm.hpp"

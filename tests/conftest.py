@@ -1,0 +1,42 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def port():
+    """The plain-C restatement (oracle/ubgl_oracle.c), built on demand."""
+    from oracle import bind
+    if not bind.have_port():
+        bind.build(ref=False)
+    return bind.Port()
+
+
+@pytest.fixture(scope="session")
+def ref():
+    """The unmodified reference TUs (oracle/_ref); skipped when not built/shipped."""
+    from oracle import bind
+    if not bind.have_ref():
+        if os.path.exists("/root/reference/simulation.cpp"):
+            bind.build(ref=True)
+        else:
+            pytest.skip("oracle/_ref not available on this box")
+    return bind.Ref()
+
+
+@pytest.fixture(scope="session")
+def ubgl():
+    """The product: ctypes face of libubgl.so.  GPU tests call through this."""
+    import ubootgl_b200
+    if ubootgl_b200.lib.ubgl_device_count() < 1:
+        pytest.fail("GPU test selected but libubgl sees no CUDA device")
+    return ubootgl_b200

@@ -1,0 +1,148 @@
+"""GPU parity: every stage of Simulation::step and whole steps (libubgl.so
+through the C ABI) against the CPU oracle on identical seeded inputs."""
+import numpy as np
+import pytest
+
+from oracle import bind as ob
+from tests import cases
+from tests.cases import rel_l2
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+# widths chosen to hit every "last 0-7 columns untouched" residue (W mod 8) and
+# the flat-index wrap of the vy loop (W = 2 mod 8, e.g. 1090)
+SIZES = [(24, 16), (41, 33), (66, 50), (70, 40), (71, 40), (72, 41), (73, 40), (74, 44),
+         (75, 40), (76, 40), (77, 40), (130, 97), (258, 131)]
+FIELDS = [ob.VX, ob.VY, ob.VXB, ob.VYB, ob.P, ob.F, ob.VX_ACCUM, ob.VY_ACCUM]
+
+
+def make_pair(ubgl, port, W, H, seed):
+    c = cases.sim_case(W, H, seed)
+    G = ubgl.Simulation(c["flag"])
+    O = port.Sim(c["flag"])
+    for s in (G, O):
+        s.set(ob.VX, c["vx"])
+        s.set(ob.VY, c["vy"])
+        s.set(ob.VXB, c["vx"][::-1].copy())  # distinct junk in the back buffers
+        s.set(ob.VYB, c["vy"][::-1].copy())
+        s.set(ob.VX_ACCUM, c["vx_accum"])
+        s.set(ob.VY_ACCUM, c["vy_accum"])
+        s.set(ob.P, c["p"])
+    return G, O, c
+
+
+def sync_from_oracle(G, O):
+    for f in FIELDS:
+        G.set(f, O.get(f))
+
+
+def check(G, O, fields, tol=TOL, what=""):
+    for f in fields:
+        a, b = G.get(f), O.get(f)
+        assert a.shape == b.shape
+        assert rel_l2(a, b) <= tol, (what, f, rel_l2(a, b))
+
+
+@pytest.mark.parametrize("W,H", SIZES)
+def test_stages(ubgl, port, W, H):
+    G, O, c = make_pair(ubgl, port, W, H, seed=W * 100 + H)
+    dt = float(O.dx)  # CFL ~ 1
+    G.stage(ob.ST_SETVBCS, dt); O.stage(ob.ST_SETVBCS, dt)
+    check(G, O, [ob.VX, ob.VY, ob.VXB, ob.VYB], 0.0, "setVBCs")
+    G.stage(ob.ST_ACCUM, dt); O.stage(ob.ST_ACCUM, dt)
+    check(G, O, [ob.VX, ob.VY, ob.VX_ACCUM, ob.VY_ACCUM], 1e-7, "accum")
+    sync_from_oracle(G, O)
+    G.stage(ob.ST_DIFFUSE, dt); O.stage(ob.ST_DIFFUSE, dt)
+    check(G, O, [ob.VX, ob.VY, ob.VXB, ob.VYB], TOL, "diffuse")
+    sync_from_oracle(G, O)
+    G.stage(ob.ST_ADVECT, dt); O.stage(ob.ST_ADVECT, dt)
+    check(G, O, [ob.VX, ob.VY, ob.VXB, ob.VYB], TOL, "advect")
+    # untouched entries (skipped octets, last columns) are bit-identical copies
+    gx, ox = G.get(ob.VX), O.get(ob.VX)
+    stale = ox == c["vx"][::-1] if False else None
+    sync_from_oracle(G, O)
+    G.stage(ob.ST_SETVBCS, dt); O.stage(ob.ST_SETVBCS, dt)
+    check(G, O, [ob.VX, ob.VY, ob.VXB, ob.VYB], 0.0, "setVBCs2")
+    G.stage(ob.ST_PROJECT, dt); O.stage(ob.ST_PROJECT, dt)
+    check(G, O, [ob.F], TOL, "divergence")
+    check(G, O, [ob.P, ob.VX, ob.VY], 2e-5, "project")
+    sync_from_oracle(G, O)
+    G.stage(ob.ST_SAVE, dt); O.stage(ob.ST_SAVE, dt)
+    check(G, O, [ob.VX_CURRENT, ob.VY_CURRENT], 0.0, "save")
+
+
+@pytest.mark.parametrize("W,H", [(70, 40), (74, 44), (130, 97)])
+def test_advect_quirks_bit_exact(ubgl, port, W, H):
+    """Faces the reference never advects (whole-octet skip, last 0-7 columns)
+    must keep the back-buffer content bit for bit."""
+    G, O, c = make_pair(ubgl, port, W, H, seed=11)
+    dt = float(O.dx)
+    backx, backy = O.get(ob.VXB), O.get(ob.VYB)
+    G.stage(ob.ST_ADVECT, dt); O.stage(ob.ST_ADVECT, dt)
+    gx, ox, gy, oy = G.get(ob.VX), O.get(ob.VX), G.get(ob.VY), O.get(ob.VY)
+    sx = (ox.view(np.uint32) == backx.view(np.uint32))
+    sy = (oy.view(np.uint32) == backy.view(np.uint32))
+    assert sx.sum() > 0 and sy.sum() > 0
+    assert (gx.view(np.uint32)[sx] == backx.view(np.uint32)[sx]).all()
+    assert (gy.view(np.uint32)[sy] == backy.view(np.uint32)[sy]).all()
+    # and the GPU leaves exactly the same set untouched (up to value coincidences)
+    tx = (gx.view(np.uint32) == backx.view(np.uint32))
+    assert abs(int(tx.sum()) - int(sx.sum())) <= 2
+
+
+@pytest.mark.parametrize("bcs", [(0, 2, 3, 3), (3, 3, 3, 3), (0, 1, 3, 3), (1, 2, 0, 3), (2, 0, 1, 1)])
+def test_boundary_condition_kinds(ubgl, port, bcs):
+    G, O, c = make_pair(ubgl, port, 66, 50, seed=9)
+    G.set_bc(*bcs); O.set_bc(*bcs)
+    dt = float(O.dx)
+    G.stage(ob.ST_SETVBCS, dt); O.stage(ob.ST_SETVBCS, dt)
+    check(G, O, [ob.VX, ob.VY, ob.VXB, ob.VYB], 0.0, "setVBCs")
+    G.step(dt); O.step(dt)
+    check(G, O, [ob.VX, ob.VY, ob.P], 5e-5, "step")
+
+
+@pytest.mark.parametrize("W,H", [(70, 40), (130, 97), (258, 131), (1090, 436)])
+def test_steps_with_sinks(ubgl, port, W, H):
+    G, O, c = make_pair(ubgl, port, W, H, seed=W + H)
+    for s in (G, O):
+        s.add_sink(0.4, 0.4 * H / W, 120.0)
+        s.add_sink(0.401, 0.4 * H / W, 60.0)   # overlapping stamp: list order wins
+        s.add_sink(0.001, 0.001, 50.0)         # inside the 3-cell border: skipped, never decays
+    dt = 0.001
+    for k in range(3):
+        G.step(dt); O.step(dt)
+        tol = 3e-5 * (k + 1)
+        check(G, O, [ob.VX, ob.VY, ob.P, ob.VX_CURRENT, ob.VY_CURRENT], tol, f"step {k}")
+        assert np.allclose(G.sinks(), O.sinks(), rtol=1e-6, atol=0)
+        assert (G.get(ob.VX_ACCUM) == O.get(ob.VX_ACCUM)).all()
+
+
+def test_step_host_mirrors(ubgl, port):
+    """The e2e entry point: host accumulators in (and zeroed), fields out."""
+    W, H = 130, 97
+    G, O, c = make_pair(ubgl, port, W, H, seed=1)
+    dt = 0.001
+    ax, ay = c["vx_accum"].copy(), c["vy_accum"].copy()
+    out = {k: np.empty(s, np.float32) for k, s in
+           dict(vx=(H, W - 1), vy=(H - 1, W), p=(H, W), vx_current=(H, W - 1),
+                vy_current=(H - 1, W)).items()}
+    G.step_host(dt, flag=c["flag"], vx_accum=ax, vy_accum=ay, **out)
+    O.step(dt)
+    assert rel_l2(out["vx"], O.get(ob.VX)) <= 3e-5
+    assert rel_l2(out["vy"], O.get(ob.VY)) <= 3e-5
+    assert rel_l2(out["p"], O.get(ob.P)) <= 3e-5
+    assert (out["vx_current"] == out["vx"]).all() and (out["vy_current"] == out["vy"]).all()
+    assert (ax == O.get(ob.VX_ACCUM)).all() and (ay == O.get(ob.VY_ACCUM)).all()
+
+
+def test_flag_update_rebuilds_pyramid(ubgl, port):
+    W, H = 130, 97
+    G, O, c = make_pair(ubgl, port, W, H, seed=2)
+    flag2 = c["flag"].copy()
+    flag2[40:60, 50:80] = 0
+    G.update_flag(flag2); O.update_flag(flag2)
+    assert G.mg_levels() == O.mg_levels()
+    for l in range(G.mg_levels()):
+        assert (G.mg_flagc(l) == O.mg_flagc(l)).all()
+    G.step(0.001); O.step(0.001)
+    check(G, O, [ob.VX, ob.VY, ob.P], 3e-5, "step after flag edit")

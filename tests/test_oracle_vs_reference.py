@@ -1,0 +1,94 @@
+"""CPU: the C restatement against the UNMODIFIED reference translation units
+(oracle/_ref) on seeded random inputs and awkward sizes.  Skipped where
+oracle/_ref could not be built or shipped."""
+import numpy as np
+import pytest
+
+from oracle import bind as ob
+from tests import cases
+from tests.cases import rel_l2
+
+TOL = 1e-5
+
+
+@pytest.mark.parametrize("W,H", [(8, 8), (9, 17), (33, 20), (64, 64), (131, 77), (257, 130)])
+def test_operators(port, ref, W, H):
+    flag, p, f = cases.random_fields(W, H, seed=W * 1000 + H)
+    ref.canonical_threads(H)
+    assert rel_l2(port.rbgs(p, f, flag, 0.01, 1.0, 3), ref.rbgs(p, f, flag, 0.01, 1.0, 3)) <= TOL
+    assert rel_l2(port.rbgs(p, f, flag, 0.01, 0.6, 1), ref.rbgs(p, f, flag, 0.01, 0.6, 1)) <= TOL
+    (r1, n1), (r2, n2) = port.residual(p, f, flag, 0.01), ref.residual(p, f, flag, 0.01)
+    assert rel_l2(r1, r2) <= TOL and abs(n1 - n2) <= 1e-5 * n2
+    assert rel_l2(port.restrict(r2), ref.restrict(r2)) <= TOL
+    rng = np.random.default_rng(W)
+    flagc = (rng.random((H // 2, W // 2)) > 0.3).astype(np.float32)
+    ec = rng.standard_normal((H // 2, W // 2)).astype(np.float32)
+    e1, e2 = port.prolongate(ec, flagc, flag), ref.prolongate(ec, flagc, flag)
+    assert rel_l2(e1, e2) <= TOL and ((e1 == 0) == (e2 == 0)).all()
+    assert (port.correct(p, e2) == ref.correct(p, e2)).all()
+    assert (port.zero_gradient_bc(p) == ref.zero_gradient_bc(p)).all()
+
+
+@pytest.mark.parametrize("W,H", [(8, 8), (16, 9), (131, 77), (545, 218), (1025, 1025)])
+def test_pyramid_and_vcycle(port, ref, W, H):
+    flag, g = cases.channel_flag(W, H, seed=W + H, ndiscs=12, radius=max(2.0, H / 12.0),
+                                 closed_box=True)
+    a, b = ref.MG(W, H), port.MG(W, H)
+    a.update_fields(flag)
+    b.update_fields(flag)
+    assert a.levels() == b.levels() == len(ob.mg_level_sizes(W, H))
+    for l in range(a.levels()):
+        assert (a.flagc(l) == b.flagc(l)).all()
+    if W * H > 300000:
+        return
+    f = cases.dipole_rhs(flag, g, n=16)
+    hh = np.float32(0.8 / (W - 1))
+    ref.canonical_threads(H)
+    p0 = np.zeros((H, W), np.float32)
+    a.set(p0, f, flag)
+    b.set(p0, f, flag)
+    for _ in range(3):
+        a.solve(hh, True)
+        b.solve(hh, True)
+        assert rel_l2(b.get_p(), a.get_p()) <= 2e-5
+        ra, rb = a.residual(hh), b.residual(hh)
+        assert abs(ra - rb) <= 0.01 * max(ra, 1e-30)
+
+
+@pytest.mark.parametrize("W,H", [(24, 16), (70, 40), (71, 41), (72, 40), (73, 44), (74, 44),
+                                 (75, 40), (76, 40), (77, 40), (130, 97)])
+def test_step_stages(port, ref, W, H):
+    c = cases.sim_case(W, H, seed=W * 100 + H)
+    A, B = ref.Sim(c["flag"]), port.Sim(c["flag"])
+    for s in (A, B):
+        s.set(ob.VX, c["vx"]); s.set(ob.VY, c["vy"])
+        s.set(ob.VXB, c["vx"][::-1].copy()); s.set(ob.VYB, c["vy"][::-1].copy())
+        s.set(ob.VX_ACCUM, c["vx_accum"]); s.set(ob.VY_ACCUM, c["vy_accum"])
+        s.set(ob.P, c["p"])
+        s.add_sink(0.4, 0.4 * H / W, 120.0)
+        s.add_sink(0.0, 0.0, 10.0)
+    ref.canonical_threads(H)
+    dt = float(A.dx)
+    fields = [ob.VX, ob.VY, ob.VXB, ob.VYB, ob.P, ob.F, ob.VX_ACCUM, ob.VY_ACCUM]
+    for st in (ob.ST_ACCUM, ob.ST_DIFFUSE, ob.ST_ADVECT, ob.ST_SETVBCS, ob.ST_PROJECT,
+               ob.ST_SETVBCS, ob.ST_SAVE):
+        A.stage(st, dt)
+        B.stage(st, dt)
+        for f in fields + [ob.VX_CURRENT, ob.VY_CURRENT]:
+            tol = 2e-5 if st == ob.ST_PROJECT else TOL
+            assert rel_l2(B.get(f), A.get(f)) <= tol, (st, f)
+        for f in fields:  # restart the next stage from identical state
+            B.set(f, A.get(f))
+        assert np.allclose(A.sinks(), B.sinks(), rtol=1e-6)
+
+
+@pytest.mark.parametrize("bcs", [(0, 2, 3, 3), (3, 3, 3, 3), (0, 1, 3, 3), (1, 2, 0, 3), (2, 0, 1, 1)])
+def test_bc_kinds(port, ref, bcs):
+    c = cases.sim_case(66, 50, seed=9)
+    A, B = ref.Sim(c["flag"]), port.Sim(c["flag"])
+    for s in (A, B):
+        s.set(ob.VX, c["vx"]); s.set(ob.VY, c["vy"]); s.set_bc(*bcs)
+    ref.canonical_threads(50)
+    A.step(0.002); B.step(0.002)
+    for f in (ob.VX, ob.VY, ob.P, ob.VXB, ob.VYB):
+        assert rel_l2(B.get(f), A.get(f)) <= 3e-5, f

@@ -1,0 +1,350 @@
+"""ctypes binding of include/ubgl.h, shaped like the reference's classes.
+
+``Simulation`` mirrors simulation.hpp:18-141 (step, setVBCs..., public grids as
+get/set of numpy arrays), ``MG`` mirrors pressure_solver.hpp:13-76.  Every call
+goes through libubgl.so; there is no Python or CPU implementation behind it.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "_lib", "libubgl.so")
+
+FLAG, VX, VY, VXB, VYB, P, F, VX_ACCUM, VY_ACCUM, R, VX_CURRENT, VY_CURRENT = range(12)
+ST_ACCUM, ST_DIFFUSE, ST_ADVECT, ST_SETVBCS, ST_PROJECT, ST_SAVE = range(6)
+BC_INFLOW, BC_OUTFLOW, BC_OUTFLOW_ZERO_PRESSURE, BC_NOSLIP = range(4)
+OPT_VCYCLES, OPT_FUSED, OPT_GRAPH, OPT_TIMING = range(4)
+
+FP = C.POINTER(C.c_float)
+IP = C.POINTER(C.c_int)
+
+
+class UbglError(RuntimeError):
+    pass
+
+
+class HostMirrors(C.Structure):
+    _fields_ = [("flag", FP), ("vx_accum", FP), ("vy_accum", FP), ("vx", FP), ("vy", FP),
+                ("p", FP), ("vx_current", FP), ("vy_current", FP)]
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise UbglError(
+            f"{LIB_PATH} is missing: build it with `make -C ubootgl_b200` "
+            "(python -c 'import __graft_entry__ as g; g.build()'). There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    v, i, f, ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
+    VP = C.POINTER(C.c_void_p)
+    sig = {
+        "ubgl_version": (i, []),
+        "ubgl_last_error": (C.c_char_p, []),
+        "ubgl_device_count": (i, []),
+        "ubgl_sim_create": (i, [FP, i, i, f, f, i, VP]),
+        "ubgl_sim_destroy": (i, [v]),
+        "ubgl_sim_set_option": (i, [v, i, i]),
+        "ubgl_sim_set_bc": (i, [v, i, i, i, i]),
+        "ubgl_sim_upload": (i, [v, i, FP]),
+        "ubgl_sim_download": (i, [v, i, FP]),
+        "ubgl_sim_update_flag": (i, [v, FP]),
+        "ubgl_sim_mg_levels": (i, [v]),
+        "ubgl_sim_mg_level_size": (i, [v, i, IP, IP]),
+        "ubgl_sim_mg_get_flagc": (i, [v, i, FP]),
+        "ubgl_sim_set_sinks": (i, [v, FP, i]),
+        "ubgl_sim_get_sinks": (i, [v, FP, i, IP]),
+        "ubgl_sim_step": (i, [v, f]),
+        "ubgl_sim_stage": (i, [v, i, f]),
+        "ubgl_sim_step_host": (i, [v, f, C.POINTER(HostMirrors)]),
+        "ubgl_sim_sync": (i, [v]),
+        "ubgl_sim_residual": (i, [v, FP]),
+        "ubgl_sim_mg_solve": (i, [v, i]),
+        "ubgl_sim_device_ptr": (i, [v, i, VP, IP]),
+        "ubgl_sim_stage_ms": (i, [v, i, FP]),
+        "ubgl_sim_launch_count": (ll, [v]),
+        "ubgl_sim_stream": (v, [v]),
+        "ubgl_mg_create": (i, [i, i, i, VP]),
+        "ubgl_mg_destroy": (i, [v]),
+        "ubgl_mg_set_option": (i, [v, i, i]),
+        "ubgl_mg_levels": (i, [v]),
+        "ubgl_mg_level_size": (i, [v, i, IP, IP]),
+        "ubgl_mg_update_fields": (i, [v, FP]),
+        "ubgl_mg_get_flagc": (i, [v, i, FP]),
+        "ubgl_mg_solve_host": (i, [v, FP, FP, FP, f, i]),
+        "ubgl_mg_upload": (i, [v, FP, FP, FP]),
+        "ubgl_mg_download_p": (i, [v, FP]),
+        "ubgl_mg_solve": (i, [v, f, i, i]),
+        "ubgl_mg_residual": (i, [v, f, FP]),
+        "ubgl_mg_sync": (i, [v]),
+        "ubgl_mg_launch_count": (ll, [v]),
+        "ubgl_mg_stream": (v, [v]),
+        "ubgl_rbgs": (i, [FP, FP, FP, i, i, f, f, i]),
+        "ubgl_residual": (i, [FP, FP, FP, FP, i, i, f, FP]),
+        "ubgl_restrict": (i, [FP, i, i, FP]),
+        "ubgl_prolongate": (i, [FP, i, i, FP, FP, FP]),
+        "ubgl_correct": (i, [FP, FP, i, i]),
+        "ubgl_zero_gradient_bc": (i, [FP, i, i]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    L._ubgl_sig = sig
+    return L
+
+
+lib = _load()
+SYMBOLS = sorted(lib._ubgl_sig)
+
+
+def _ck(rc):
+    if rc != 0:
+        raise UbglError(f"libubgl error {rc}: {lib.ubgl_last_error().decode()}")
+
+
+def _fp(a):
+    assert a.dtype == np.float32 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(FP)
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def field_shape(field, w, h):
+    if field in (VX, VXB, VX_ACCUM, VX_CURRENT):
+        return (h, w - 1)
+    if field in (VY, VYB, VY_ACCUM, VY_CURRENT):
+        return (h - 1, w)
+    return (h, w)
+
+
+class Simulation:
+    """Simulation(flag, pwidth, mu) -- simulation.hpp:32-67, state on the GPU."""
+
+    def __init__(self, flag, pwidth=0.8, mu=0.001, device=0):
+        flag = _f32(flag)
+        self.height, self.width = flag.shape
+        self.pwidth, self.mu = pwidth, mu
+        self.h = np.float32(pwidth) / (np.float32(self.width) - np.float32(1.0))
+        self._h = C.c_void_p()
+        _ck(lib.ubgl_sim_create(_fp(flag), self.width, self.height, pwidth, mu, device,
+                                C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.ubgl_sim_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- public members as arrays ----
+    def get(self, field):
+        a = np.empty(field_shape(field, self.width, self.height), np.float32)
+        _ck(lib.ubgl_sim_download(self._h, field, _fp(a)))
+        return a
+
+    def set(self, field, a):
+        a = _f32(a)
+        if a.shape != field_shape(field, self.width, self.height):
+            raise UbglError(f"field {field}: shape {a.shape} does not match the grid")
+        _ck(lib.ubgl_sim_upload(self._h, field, _fp(a)))
+
+    def update_flag(self, flag):
+        """memcpy into sim.flag + mg.updateFields (ubootgl_app.cpp:111-112)."""
+        flag = _f32(flag)
+        if flag.shape != (self.height, self.width):
+            raise UbglError("flag shape does not match the grid")
+        _ck(lib.ubgl_sim_update_flag(self._h, _fp(flag)))
+
+    def set_bc(self, west, east, north, south):
+        _ck(lib.ubgl_sim_set_bc(self._h, west, east, north, south))
+
+    def set_option(self, opt, val):
+        _ck(lib.ubgl_sim_set_option(self._h, opt, int(val)))
+
+    def set_sinks(self, xyz):
+        xyz = _f32(np.asarray(xyz, np.float32).reshape(-1, 3))
+        _ck(lib.ubgl_sim_set_sinks(self._h, _fp(xyz), len(xyz)))
+
+    def add_sink(self, x, y, z):
+        s = self.sinks()
+        self.set_sinks(np.concatenate([s, np.array([[x, y, z]], np.float32)]))
+
+    def sinks(self):
+        n = C.c_int()
+        _ck(lib.ubgl_sim_get_sinks(self._h, None, 0, C.byref(n)))
+        a = np.zeros((n.value, 3), np.float32)
+        if n.value:
+            _ck(lib.ubgl_sim_get_sinks(self._h, _fp(a), n.value, C.byref(n)))
+        return a
+
+    # ---- methods ----
+    def step(self, dt):
+        _ck(lib.ubgl_sim_step(self._h, dt))
+
+    def stage(self, stage, dt):
+        _ck(lib.ubgl_sim_stage(self._h, stage, dt))
+
+    def step_host(self, dt, flag=None, vx_accum=None, vy_accum=None, vx=None, vy=None, p=None,
+                  vx_current=None, vy_current=None):
+        m = HostMirrors()
+        for name, a in (("flag", flag), ("vx_accum", vx_accum), ("vy_accum", vy_accum),
+                        ("vx", vx), ("vy", vy), ("p", p), ("vx_current", vx_current),
+                        ("vy_current", vy_current)):
+            setattr(m, name, _fp(a) if a is not None else None)
+        _ck(lib.ubgl_sim_step_host(self._h, dt, C.byref(m)))
+
+    def sync(self):
+        _ck(lib.ubgl_sim_sync(self._h))
+
+    def residual(self):
+        l2 = C.c_float()
+        _ck(lib.ubgl_sim_residual(self._h, C.byref(l2)))
+        return l2.value
+
+    def mg_solve(self, cycles=1):
+        _ck(lib.ubgl_sim_mg_solve(self._h, cycles))
+
+    def mg_levels(self):
+        return lib.ubgl_sim_mg_levels(self._h)
+
+    def mg_flagc(self, level):
+        w, h = C.c_int(), C.c_int()
+        _ck(lib.ubgl_sim_mg_level_size(self._h, level, C.byref(w), C.byref(h)))
+        a = np.empty((h.value, w.value), np.float32)
+        _ck(lib.ubgl_sim_mg_get_flagc(self._h, level, _fp(a)))
+        return a
+
+    def device_ptr(self, field):
+        p, pitch = C.c_void_p(), C.c_int()
+        _ck(lib.ubgl_sim_device_ptr(self._h, field, C.byref(p), C.byref(pitch)))
+        return p.value, pitch.value
+
+    def stage_ms(self, stage):
+        ms = C.c_float()
+        _ck(lib.ubgl_sim_stage_ms(self._h, stage, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self):
+        return lib.ubgl_sim_launch_count(self._h)
+
+    def stream(self):
+        return lib.ubgl_sim_stream(self._h)
+
+
+class MG:
+    """MG(width, height) -- pressure_solver.hpp:16-31, state on the GPU."""
+
+    def __init__(self, width, height, device=0):
+        self.width, self.height = width, height
+        self._h = C.c_void_p()
+        _ck(lib.ubgl_mg_create(width, height, device, C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.ubgl_mg_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_option(self, opt, val):
+        _ck(lib.ubgl_mg_set_option(self._h, opt, int(val)))
+
+    def levels(self):
+        return lib.ubgl_mg_levels(self._h)
+
+    def update_fields(self, flag):
+        _ck(lib.ubgl_mg_update_fields(self._h, _fp(_f32(flag))))
+
+    def flagc(self, level):
+        w, h = C.c_int(), C.c_int()
+        _ck(lib.ubgl_mg_level_size(self._h, level, C.byref(w), C.byref(h)))
+        a = np.empty((h.value, w.value), np.float32)
+        _ck(lib.ubgl_mg_get_flagc(self._h, level, _fp(a)))
+        return a
+
+    def solve_host(self, p, f, flag, hh, zero_gradient_bc=False):
+        """MG::solve(p, f, flag, h, zeroGradientBC): p is updated in place."""
+        assert p.dtype == np.float32 and p.flags["C_CONTIGUOUS"]
+        _ck(lib.ubgl_mg_solve_host(self._h, _fp(p), _fp(_f32(f)), _fp(_f32(flag)), hh,
+                                   int(zero_gradient_bc)))
+
+    def set(self, p=None, f=None, flag=None):
+        args = [_fp(_f32(a)) if a is not None else None for a in (p, f, flag)]
+        _ck(lib.ubgl_mg_upload(self._h, *args))
+
+    def get_p(self):
+        a = np.empty((self.height, self.width), np.float32)
+        _ck(lib.ubgl_mg_download_p(self._h, _fp(a)))
+        return a
+
+    def solve(self, hh, zero_gradient_bc=False, cycles=1):
+        _ck(lib.ubgl_mg_solve(self._h, hh, int(zero_gradient_bc), cycles))
+
+    def residual(self, hh):
+        l2 = C.c_float()
+        _ck(lib.ubgl_mg_residual(self._h, hh, C.byref(l2)))
+        return l2.value
+
+    def sync(self):
+        _ck(lib.ubgl_mg_sync(self._h))
+
+    def launch_count(self):
+        return lib.ubgl_mg_launch_count(self._h)
+
+
+# ---- pressure_solver.cpp free functions -------------------------------------
+def rbgs(p, f, flag, hh, alpha=1.0, sweeps=1):
+    p = _f32(p).copy()
+    H, W = p.shape
+    _ck(lib.ubgl_rbgs(_fp(p), _fp(_f32(f)), _fp(_f32(flag)), W, H, hh, alpha, sweeps))
+    return p
+
+
+def residual(p, f, flag, hh):
+    p = _f32(p)
+    H, W = p.shape
+    r = np.zeros_like(p)
+    l2 = C.c_float()
+    _ck(lib.ubgl_residual(_fp(p), _fp(_f32(f)), _fp(_f32(flag)), _fp(r), W, H, hh, C.byref(l2)))
+    return r, l2.value
+
+
+def restrict(r):
+    r = _f32(r)
+    H, W = r.shape
+    rc = np.zeros((H // 2, W // 2), np.float32)
+    _ck(lib.ubgl_restrict(_fp(r), W, H, _fp(rc)))
+    return rc
+
+
+def prolongate(ec, flagc, flag):
+    flag = _f32(flag)
+    H, W = flag.shape
+    e = np.full((H, W), 7.0, np.float32)
+    _ck(lib.ubgl_prolongate(_fp(e), W, H, _fp(_f32(ec)), _fp(_f32(flagc)), _fp(flag)))
+    return e
+
+
+def correct(p, e):
+    p = _f32(p).copy()
+    H, W = p.shape
+    _ck(lib.ubgl_correct(_fp(p), _fp(_f32(e)), W, H))
+    return p
+
+
+def zero_gradient_bc(p):
+    p = _f32(p).copy()
+    H, W = p.shape
+    _ck(lib.ubgl_zero_gradient_bc(_fp(p), W, H))
+    return p

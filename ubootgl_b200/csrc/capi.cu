@@ -1,0 +1,556 @@
+// capi.cu -- the extern "C" boundary declared in include/ubgl.h.  Everything
+// behind it is C++/CUDA; nothing but plain C types and opaque handles crosses.
+#include "../../include/ubgl.h"
+#include "mg.cuh"
+#include "sim.cuh"
+#include <cstring>
+#include <memory>
+#include <new>
+#include <vector>
+
+namespace ubgl {
+static thread_local std::string g_err;
+void set_error(const std::string &m) { g_err = m; }
+const char *get_error() { return g_err.c_str(); }
+} // namespace ubgl
+
+using namespace ubgl;
+
+struct ubgl_sim {
+  std::unique_ptr<DeviceSim> s;
+};
+
+struct ubgl_mg {
+  int W = 0, H = 0, device = 0;
+  cudaStream_t stream = nullptr;
+  LaunchCounter lc;
+  std::unique_ptr<DeviceMG> mg;
+  Grid p, f, flag;
+  ~ubgl_mg() {
+    cudaSetDevice(device);
+    if (stream) cudaStreamSynchronize(stream);
+    mg.reset();
+    free_grid(p);
+    free_grid(f);
+    free_grid(flag);
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+
+#define UBGL_TRY try {
+#define UBGL_CATCH                                                             \
+  }                                                                            \
+  catch (const CudaError &e) {                                                 \
+    char buf[512];                                                             \
+    snprintf(buf, sizeof buf, "CUDA error %d (%s) at %s:%d", (int)e.code,      \
+             cudaGetErrorString(e.code), e.file, e.line);                      \
+    set_error(buf);                                                            \
+    cudaGetLastError();                                                        \
+    return e.code == cudaErrorMemoryAllocation ? UBGL_E_NOMEM : UBGL_E_CUDA;   \
+  }                                                                            \
+  catch (const ArgError &e) {                                                  \
+    set_error(e.msg);                                                          \
+    return UBGL_E_ARG;                                                         \
+  }                                                                            \
+  catch (const std::bad_alloc &) {                                             \
+    set_error("host allocation failed");                                       \
+    return UBGL_E_NOMEM;                                                       \
+  }                                                                            \
+  catch (...) {                                                                \
+    set_error("unknown internal error");                                       \
+    return UBGL_E_STATE;                                                       \
+  }                                                                            \
+  return UBGL_OK;
+
+#define NEED(ptr, what) UBGL_REQUIRE((ptr) != nullptr, what " must not be null")
+
+static void require_device(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) throw CudaError{e, __FILE__, __LINE__};
+  UBGL_REQUIRE(device >= 0 && device < n, "no such CUDA device (libubgl has no CPU fallback)");
+  UBGL_CUDA(cudaSetDevice(device));
+}
+
+extern "C" {
+
+int ubgl_version(void) { return UBGL_VERSION; }
+const char *ubgl_last_error(void) { return get_error(); }
+int ubgl_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+// ---- Simulation -------------------------------------------------------------
+int ubgl_sim_create(const float *flag, int W, int H, float pwidth, float mu, int device,
+                    ubgl_sim_t **out) {
+  UBGL_TRY
+  NEED(out, "out");
+  *out = nullptr;
+  NEED(flag, "flag");
+  require_device(device);
+  std::unique_ptr<ubgl_sim> h(new ubgl_sim);
+  h->s.reset(new DeviceSim(flag, W, H, pwidth, mu, device));
+  *out = h.release();
+  UBGL_CATCH
+}
+
+int ubgl_sim_destroy(ubgl_sim_t *sim) {
+  UBGL_TRY
+  delete sim;
+  UBGL_CATCH
+}
+
+#define SIM(sim)                                                               \
+  NEED(sim, "sim");                                                            \
+  DeviceSim &S = *(sim)->s;                                                    \
+  UBGL_CUDA(cudaSetDevice(S.device));
+
+int ubgl_sim_set_option(ubgl_sim_t *sim, int option, int value) {
+  UBGL_TRY
+  SIM(sim);
+  switch (option) {
+  case UBGL_OPT_VCYCLES:
+    UBGL_REQUIRE(value >= 0, "vcycles must be >= 0");
+    S.vcycles = value;
+    break;
+  case UBGL_OPT_FUSED: S.fused = value != 0; S.mg->fused = value != 0; break;
+  case UBGL_OPT_GRAPH: S.use_graph = value != 0; break;
+  case UBGL_OPT_TIMING: S.timing = value != 0; break;
+  default: throw ArgError{"unknown option"};
+  }
+  UBGL_CATCH
+}
+
+int ubgl_sim_set_bc(ubgl_sim_t *sim, int west, int east, int north, int south) {
+  UBGL_TRY
+  SIM(sim);
+  auto ok = [](int b) { return b >= 0 && b <= 3; };
+  UBGL_REQUIRE(ok(west) && ok(east) && ok(north) && ok(south), "bad BC id");
+  S.bcW = west; S.bcE = east; S.bcN = north; S.bcS = south;
+  UBGL_CATCH
+}
+
+int ubgl_sim_upload(ubgl_sim_t *sim, int field, const float *host) {
+  UBGL_TRY
+  SIM(sim);
+  UBGL_REQUIRE(field >= 0 && field < UBGL_NUM_FIELDS, "bad field id");
+  S.upload(field, host);
+  UBGL_CATCH
+}
+
+int ubgl_sim_download(ubgl_sim_t *sim, int field, float *host) {
+  UBGL_TRY
+  SIM(sim);
+  UBGL_REQUIRE(field >= 0 && field < UBGL_NUM_FIELDS, "bad field id");
+  S.download(field, host);
+  UBGL_CATCH
+}
+
+int ubgl_sim_update_flag(ubgl_sim_t *sim, const float *flag) {
+  UBGL_TRY
+  SIM(sim);
+  S.update_flag(flag);
+  UBGL_CATCH
+}
+
+int ubgl_sim_mg_levels(ubgl_sim_t *sim) { return sim ? sim->s->mg->levels() : UBGL_E_ARG; }
+
+int ubgl_sim_mg_level_size(ubgl_sim_t *sim, int level, int *w, int *h) {
+  UBGL_TRY
+  SIM(sim);
+  UBGL_REQUIRE(level >= 0 && level < S.mg->levels(), "bad level");
+  NEED(w, "w");
+  NEED(h, "h");
+  *w = S.mg->level(level).w;
+  *h = S.mg->level(level).h;
+  UBGL_CATCH
+}
+
+int ubgl_sim_mg_get_flagc(ubgl_sim_t *sim, int level, float *host) {
+  UBGL_TRY
+  SIM(sim);
+  UBGL_REQUIRE(level >= 0 && level < S.mg->levels(), "bad level");
+  NEED(host, "host");
+  const MGLevel &L = S.mg->level(level);
+  download_grid(L.flagc, host, L.w, L.h, S.stream);
+  S.sync();
+  UBGL_CATCH
+}
+
+int ubgl_sim_set_sinks(ubgl_sim_t *sim, const float *xyz, int n) {
+  UBGL_TRY
+  SIM(sim);
+  UBGL_REQUIRE(n >= 0 && (n == 0 || xyz), "bad sink list");
+  S.sinks.resize(n);
+  for (int i = 0; i < n; i++) S.sinks[i] = Sink{xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
+  UBGL_CATCH
+}
+
+int ubgl_sim_get_sinks(ubgl_sim_t *sim, float *xyz, int cap, int *n) {
+  UBGL_TRY
+  SIM(sim);
+  NEED(n, "n");
+  *n = (int)S.sinks.size();
+  for (int i = 0; i < *n && i < cap && xyz; i++) {
+    xyz[3 * i] = S.sinks[i].x;
+    xyz[3 * i + 1] = S.sinks[i].y;
+    xyz[3 * i + 2] = S.sinks[i].z;
+  }
+  UBGL_CATCH
+}
+
+int ubgl_sim_step(ubgl_sim_t *sim, float dt) {
+  UBGL_TRY
+  SIM(sim);
+  S.step(dt);
+  UBGL_CATCH
+}
+
+int ubgl_sim_stage(ubgl_sim_t *sim, int stage, float dt) {
+  UBGL_TRY
+  SIM(sim);
+  S.stage(stage, dt);
+  UBGL_CATCH
+}
+
+int ubgl_sim_step_host(ubgl_sim_t *sim, float dt, const ubgl_host_mirrors *m) {
+  UBGL_TRY
+  SIM(sim);
+  NEED(m, "mirrors");
+  if (m->flag) {
+    Grid g = S.field(F_FLAG);
+    upload_grid(g, m->flag, g.w, g.h, S.stream);
+    S.mg->update_fields(g);
+  }
+  if (m->vx_accum) {
+    Grid g = S.field(F_VX_ACCUM);
+    upload_grid(g, m->vx_accum, g.w, g.h, S.stream);
+  }
+  if (m->vy_accum) {
+    Grid g = S.field(F_VY_ACCUM);
+    upload_grid(g, m->vy_accum, g.w, g.h, S.stream);
+  }
+  if (m->vx_accum || m->vy_accum) {
+    // the reference zeroes the interior of the accumulators while applying
+    // them (simulation.cpp:384,392); the host mirrors follow once the upload
+    // has consumed them.
+    S.sync();
+    if (m->vx_accum)
+      for (int y = 1; y < S.H - 1; y++)
+        std::memset(m->vx_accum + (size_t)y * (S.W - 1) + 1, 0, sizeof(float) * (S.W - 3));
+    if (m->vy_accum)
+      for (int y = 1; y < S.H - 2; y++)
+        std::memset(m->vy_accum + (size_t)y * S.W + 1, 0, sizeof(float) * (S.W - 2));
+  }
+  S.step(dt);
+  struct { int id; float *dst; } outs[] = {{F_VX, m->vx}, {F_VY, m->vy}, {F_P, m->p},
+                                           {F_VX_CURRENT, m->vx_current},
+                                           {F_VY_CURRENT, m->vy_current}};
+  for (auto &o : outs)
+    if (o.dst) {
+      Grid g = S.field(o.id);
+      download_grid(g, o.dst, g.w, g.h, S.stream);
+    }
+  S.sync();
+  UBGL_CATCH
+}
+
+int ubgl_sim_sync(ubgl_sim_t *sim) {
+  UBGL_TRY
+  SIM(sim);
+  S.sync();
+  UBGL_CATCH
+}
+
+int ubgl_sim_residual(ubgl_sim_t *sim, float *l2) {
+  UBGL_TRY
+  SIM(sim);
+  NEED(l2, "l2");
+  *l2 = S.residual();
+  UBGL_CATCH
+}
+
+int ubgl_sim_mg_solve(ubgl_sim_t *sim, int cycles) {
+  UBGL_TRY
+  SIM(sim);
+  UBGL_REQUIRE(cycles >= 0, "cycles must be >= 0");
+  S.mg_solve(cycles);
+  UBGL_CATCH
+}
+
+int ubgl_sim_device_ptr(ubgl_sim_t *sim, int field, void **dptr, int *pitch) {
+  UBGL_TRY
+  SIM(sim);
+  NEED(dptr, "dptr");
+  UBGL_REQUIRE(field >= 0 && field < UBGL_NUM_FIELDS, "bad field id");
+  Grid g = S.field(field);
+  *dptr = g.d;
+  if (pitch) *pitch = g.pitch;
+  UBGL_CATCH
+}
+
+int ubgl_sim_stage_ms(ubgl_sim_t *sim, int stage, float *ms) {
+  UBGL_TRY
+  SIM(sim);
+  NEED(ms, "ms");
+  UBGL_REQUIRE(stage >= 0 && stage < ST_COUNT, "bad stage id");
+  *ms = S.stage_ms[stage];
+  UBGL_CATCH
+}
+
+long long ubgl_sim_launch_count(ubgl_sim_t *sim) { return sim ? sim->s->lc.n : -1; }
+void *ubgl_sim_stream(ubgl_sim_t *sim) { return sim ? (void *)sim->s->stream : nullptr; }
+
+// ---- MG ---------------------------------------------------------------------
+int ubgl_mg_create(int W, int H, int device, ubgl_mg_t **out) {
+  UBGL_TRY
+  NEED(out, "out");
+  *out = nullptr;
+  UBGL_REQUIRE(W >= 8 && H >= 8, "MG needs W,H >= 8 (two levels)");
+  require_device(device);
+  std::unique_ptr<ubgl_mg> m(new ubgl_mg);
+  m->W = W;
+  m->H = H;
+  m->device = device;
+  UBGL_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+  m->mg.reset(new DeviceMG(W, H, device, m->stream, &m->lc));
+  int pitch = m->mg->level(0).pitch;
+  m->p = alloc_grid(W, H, pitch);
+  m->f = alloc_grid(W, H, pitch);
+  m->flag = alloc_grid(W, H, pitch, false);
+  fill_grid(m->flag, 1.0f, m->stream, nullptr);
+  UBGL_CUDA(cudaStreamSynchronize(m->stream));
+  *out = m.release();
+  UBGL_CATCH
+}
+
+int ubgl_mg_destroy(ubgl_mg_t *mg) {
+  UBGL_TRY
+  delete mg;
+  UBGL_CATCH
+}
+
+#define MGH(mg)                                                                \
+  NEED(mg, "mg");                                                              \
+  ubgl_mg &M = *(mg);                                                          \
+  UBGL_CUDA(cudaSetDevice(M.device));
+
+int ubgl_mg_set_option(ubgl_mg_t *mg, int option, int value) {
+  UBGL_TRY
+  MGH(mg);
+  switch (option) {
+  case UBGL_OPT_FUSED: M.mg->fused = value != 0; break;
+  case UBGL_OPT_GRAPH: case UBGL_OPT_TIMING: case UBGL_OPT_VCYCLES: break;
+  default: throw ArgError{"unknown option"};
+  }
+  UBGL_CATCH
+}
+
+int ubgl_mg_levels(ubgl_mg_t *mg) { return mg ? mg->mg->levels() : UBGL_E_ARG; }
+
+int ubgl_mg_level_size(ubgl_mg_t *mg, int level, int *w, int *h) {
+  UBGL_TRY
+  MGH(mg);
+  UBGL_REQUIRE(level >= 0 && level < M.mg->levels(), "bad level");
+  NEED(w, "w");
+  NEED(h, "h");
+  *w = M.mg->level(level).w;
+  *h = M.mg->level(level).h;
+  UBGL_CATCH
+}
+
+int ubgl_mg_update_fields(ubgl_mg_t *mg, const float *flag) {
+  UBGL_TRY
+  MGH(mg);
+  NEED(flag, "flag");
+  upload_grid(M.flag, flag, M.W, M.H, M.stream);
+  M.mg->update_fields(M.flag);
+  UBGL_CUDA(cudaStreamSynchronize(M.stream));
+  UBGL_CATCH
+}
+
+int ubgl_mg_get_flagc(ubgl_mg_t *mg, int level, float *host) {
+  UBGL_TRY
+  MGH(mg);
+  UBGL_REQUIRE(level >= 0 && level < M.mg->levels(), "bad level");
+  NEED(host, "host");
+  const MGLevel &L = M.mg->level(level);
+  download_grid(L.flagc, host, L.w, L.h, M.stream);
+  UBGL_CUDA(cudaStreamSynchronize(M.stream));
+  UBGL_CATCH
+}
+
+int ubgl_mg_upload(ubgl_mg_t *mg, const float *p, const float *f, const float *flag) {
+  UBGL_TRY
+  MGH(mg);
+  if (p) upload_grid(M.p, p, M.W, M.H, M.stream);
+  if (f) upload_grid(M.f, f, M.W, M.H, M.stream);
+  if (flag) upload_grid(M.flag, flag, M.W, M.H, M.stream);
+  UBGL_CUDA(cudaStreamSynchronize(M.stream));
+  UBGL_CATCH
+}
+
+int ubgl_mg_download_p(ubgl_mg_t *mg, float *p) {
+  UBGL_TRY
+  MGH(mg);
+  NEED(p, "p");
+  download_grid(M.p, p, M.W, M.H, M.stream);
+  UBGL_CUDA(cudaStreamSynchronize(M.stream));
+  UBGL_CATCH
+}
+
+int ubgl_mg_solve(ubgl_mg_t *mg, float h, int zero_gradient_bc, int cycles) {
+  UBGL_TRY
+  MGH(mg);
+  UBGL_REQUIRE(cycles >= 0, "cycles must be >= 0");
+  for (int c = 0; c < cycles; c++) M.mg->solve(M.p, M.f, M.flag, h, zero_gradient_bc != 0);
+  UBGL_CATCH
+}
+
+int ubgl_mg_solve_host(ubgl_mg_t *mg, float *p, const float *f, const float *flag, float h,
+                       int zero_gradient_bc) {
+  UBGL_TRY
+  MGH(mg);
+  NEED(p, "p");
+  NEED(f, "f");
+  NEED(flag, "flag");
+  upload_grid(M.p, p, M.W, M.H, M.stream);
+  upload_grid(M.f, f, M.W, M.H, M.stream);
+  upload_grid(M.flag, flag, M.W, M.H, M.stream);
+  M.mg->solve(M.p, M.f, M.flag, h, zero_gradient_bc != 0);
+  download_grid(M.p, p, M.W, M.H, M.stream);
+  UBGL_CUDA(cudaStreamSynchronize(M.stream));
+  UBGL_CATCH
+}
+
+int ubgl_mg_residual(ubgl_mg_t *mg, float h, float *l2) {
+  UBGL_TRY
+  MGH(mg);
+  NEED(l2, "l2");
+  Grid r = alloc_grid(M.W, M.H, M.p.pitch, false);
+  try {
+    M.mg->residual(M.p, M.f, M.flag, r, h, true);
+    *l2 = M.mg->residual_norm_result();
+  } catch (...) {
+    free_grid(r);
+    throw;
+  }
+  free_grid(r);
+  UBGL_CATCH
+}
+
+int ubgl_mg_sync(ubgl_mg_t *mg) {
+  UBGL_TRY
+  MGH(mg);
+  UBGL_CUDA(cudaStreamSynchronize(M.stream));
+  UBGL_CATCH
+}
+
+long long ubgl_mg_launch_count(ubgl_mg_t *mg) { return mg ? mg->lc.n : -1; }
+void *ubgl_mg_stream(ubgl_mg_t *mg) { return mg ? (void *)mg->stream : nullptr; }
+
+// ---- free operators with host grids ------------------------------------------
+namespace {
+// small RAII scratch context for the one-shot operator calls
+struct Scratch {
+  cudaStream_t stream = nullptr;
+  LaunchCounter lc;
+  std::vector<Grid> grids;
+  std::unique_ptr<DeviceMG> mg;
+  Scratch(int w, int h) {
+    require_device(0);
+    UBGL_REQUIRE(w >= 8 && h >= 8, "operator grids need w,h >= 8");
+    UBGL_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    mg.reset(new DeviceMG(w, h, 0, stream, &lc));
+  }
+  Grid up(const float *host, int w, int h) {
+    Grid g = alloc_grid(w, h, round_up(w, 32));
+    grids.push_back(g);
+    if (host) upload_grid(g, host, w, h, stream);
+    return g;
+  }
+  void down(const Grid &g, float *host) {
+    download_grid(g, host, g.w, g.h, stream);
+    UBGL_CUDA(cudaStreamSynchronize(stream));
+  }
+  ~Scratch() {
+    if (stream) cudaStreamSynchronize(stream);
+    mg.reset();
+    for (auto &g : grids) free_grid(g);
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+} // namespace
+
+int ubgl_rbgs(float *p, const float *f, const float *flag, int w, int h, float hh, float alpha,
+              int sweeps) {
+  UBGL_TRY
+  NEED(p, "p"); NEED(f, "f"); NEED(flag, "flag");
+  Scratch sc(w, h);
+  Grid P = sc.up(p, w, h), F = sc.up(f, w, h), G = sc.up(flag, w, h);
+  for (int i = 0; i < sweeps; i++) sc.mg->rbgs(P, F, G, hh, alpha);
+  sc.down(P, p);
+  UBGL_CATCH
+}
+
+int ubgl_residual(const float *p, const float *f, const float *flag, float *r, int w, int h,
+                  float hh, float *l2) {
+  UBGL_TRY
+  NEED(p, "p"); NEED(f, "f"); NEED(flag, "flag"); NEED(r, "r");
+  Scratch sc(w, h);
+  Grid P = sc.up(p, w, h), F = sc.up(f, w, h), G = sc.up(flag, w, h), R = sc.up(nullptr, w, h);
+  sc.mg->residual(P, F, G, R, hh, true);
+  float n = sc.mg->residual_norm_result();
+  if (l2) *l2 = n;
+  sc.down(R, r);
+  UBGL_CATCH
+}
+
+int ubgl_restrict(const float *r, int w, int h, float *rc) {
+  UBGL_TRY
+  NEED(r, "r"); NEED(rc, "rc");
+  Scratch sc(w, h);
+  Grid R = sc.up(r, w, h), RC = sc.up(nullptr, w / 2, h / 2);
+  sc.mg->restrict_fw(R, RC);
+  sc.down(RC, rc);
+  UBGL_CATCH
+}
+
+int ubgl_prolongate(float *e, int w, int h, const float *ec, const float *flagc,
+                    const float *flag) {
+  UBGL_TRY
+  NEED(e, "e"); NEED(ec, "ec"); NEED(flagc, "flagc"); NEED(flag, "flag");
+  Scratch sc(w, h);
+  Grid E = sc.up(nullptr, w, h), EC = sc.up(ec, w / 2, h / 2), GC = sc.up(flagc, w / 2, h / 2),
+       G = sc.up(flag, w, h);
+  sc.mg->prolongate(E, EC, GC, G);
+  sc.down(E, e);
+  UBGL_CATCH
+}
+
+int ubgl_correct(float *p, const float *e, int w, int h) {
+  UBGL_TRY
+  NEED(p, "p"); NEED(e, "e");
+  Scratch sc(w, h);
+  Grid P = sc.up(p, w, h), E = sc.up(e, w, h);
+  sc.mg->correct(P, E);
+  sc.down(P, p);
+  UBGL_CATCH
+}
+
+int ubgl_zero_gradient_bc(float *p, int w, int h) {
+  UBGL_TRY
+  NEED(p, "p");
+  Scratch sc(w, h);
+  Grid P = sc.up(p, w, h);
+  sc.mg->zero_gradient_bc(P);
+  sc.down(P, p);
+  UBGL_CATCH
+}
+
+} // extern "C"

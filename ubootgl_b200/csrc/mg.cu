@@ -1,0 +1,359 @@
+// mg.cu -- multigrid V-cycle on the device.  Reference: pressure_solver.cpp /
+// pressure_solver.hpp of te42kyfo/ubootgl (file:line cited per kernel).
+#include "mg.cuh"
+#include "stencils.cuh"
+
+namespace ubgl {
+
+// ---------------------------------------------------------------------------
+// grid helpers
+// ---------------------------------------------------------------------------
+Grid alloc_grid(int w, int h, int pitch, bool zero) {
+  Grid g;
+  g.w = w;
+  g.h = h;
+  g.pitch = pitch;
+  UBGL_CUDA(cudaMalloc(&g.d, g.bytes()));
+  if (zero) UBGL_CUDA(cudaMemset(g.d, 0, g.bytes()));
+  return g;
+}
+void free_grid(Grid &g) {
+  if (g.d) cudaFree(g.d);
+  g.d = nullptr;
+}
+void upload_grid(const Grid &g, const float *host, int w, int h, cudaStream_t s) {
+  UBGL_CUDA(cudaMemcpy2DAsync(g.d, sizeof(float) * g.pitch, host, sizeof(float) * w,
+                              sizeof(float) * w, h, cudaMemcpyHostToDevice, s));
+}
+void download_grid(const Grid &g, float *host, int w, int h, cudaStream_t s) {
+  UBGL_CUDA(cudaMemcpy2DAsync(host, sizeof(float) * w, g.d, sizeof(float) * g.pitch,
+                              sizeof(float) * w, h, cudaMemcpyDeviceToHost, s));
+}
+
+__global__ void k_fill(float *d, size_t n, float v) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) d[i] = v;
+}
+void fill_grid(const Grid &g, float v, cudaStream_t s, LaunchCounter *lc) {
+  size_t n = (size_t)g.pitch * g.h;
+  if (v == 0.0f) {
+    UBGL_CUDA(cudaMemsetAsync(g.d, 0, n * sizeof(float), s));
+    return;
+  }
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  k_fill<<<blocks, 256, 0, s>>>(g.d, n, v);
+  UBGL_CHECK_LAUNCH();
+  if (lc) lc->n++;
+}
+
+// ---------------------------------------------------------------------------
+// plain kernels: one per reference operator
+// ---------------------------------------------------------------------------
+
+// rbgs_red_line / rbgs_black_line (pressure_solver.cpp:35-47): color 0 ("red")
+// starts each row at x = 1 + (y%2), color 1 ("black") at x = 1 + ((y+1)%2).
+__global__ void k_rbgs_half(Grid p, Grid f, Grid flag, float hh, float alpha, int color) {
+  int y = 1 + blockIdx.y * blockDim.y + threadIdx.y;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int x = 1 + ((y + color) & 1) + 2 * i;
+  if (y >= p.h - 1 || x >= p.w - 1) return;
+  size_t c = (size_t)y * p.pitch + x;
+  const float *fl = flag.d + (size_t)y * flag.pitch + x;
+  float fh2 = fh2_of(f.d[(size_t)y * f.pitch + x], hh);
+  p.d[c] = smooth_cell(p.d[c], p.d[c - 1], p.d[c + 1], p.d[c - p.pitch], p.d[c + p.pitch],
+                       fl[0], fl[-1], fl[1], fl[-flag.pitch], fl[flag.pitch], fh2, alpha);
+}
+
+// setZeroGradientBC (pressure_solver.cpp:183-192): the column loop touches only
+// y in [1,h-2] and the row loop only x in [1,w-2], so they are independent.
+__global__ void k_zero_gradient_bc(Grid p) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 1 && i < p.h - 1) {
+    p.at(0, i) = p.at(1, i);
+    p.at(p.w - 1, i) = p.at(p.w - 2, i);
+  }
+  if (i >= 1 && i < p.w - 1) {
+    p.at(i, 0) = p.at(i, 1);
+    p.at(i, p.h - 1) = p.at(i, p.h - 2);
+  }
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// calculateResidualField (pressure_solver.cpp:91-116).  Writes r on the whole
+// grid (0 on the border, as after the reference's r.fill(0.0) :218) and, if
+// partials != nullptr, one double partial sum of r^2 per block (warp-shuffle
+// reduction; summed by k_finish_norm in a fixed order => deterministic).
+__global__ void k_residual(Grid p, Grid f, Grid flag, Grid r, float ihsq, double *partials) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x;
+  int y = blockIdx.y * blockDim.y + threadIdx.y;
+  float rv = 0.0f;
+  if (x < p.w && y < p.h) {
+    if (x >= 1 && y >= 1 && x < p.w - 1 && y < p.h - 1) {
+      size_t c = (size_t)y * p.pitch + x;
+      const float *fl = flag.d + (size_t)y * flag.pitch + x;
+      rv = residual_cell(p.d[c], p.d[c - 1], p.d[c + 1], p.d[c - p.pitch], p.d[c + p.pitch],
+                         fl[0], fl[-1], fl[1], fl[-flag.pitch], fl[flag.pitch],
+                         f.d[(size_t)y * f.pitch + x], ihsq);
+    }
+    r.d[(size_t)y * r.pitch + x] = rv;
+  }
+  if (partials) {
+    __shared__ double wsum[32];
+    double s = warp_sum((double)rv * (double)rv);
+    int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    int nw = (blockDim.x * blockDim.y + 31) / 32;
+    if ((tid & 31) == 0) wsum[tid >> 5] = s;
+    __syncthreads();
+    if (tid < 32) {
+      double t = tid < nw ? wsum[tid] : 0.0;
+      t = warp_sum(t);
+      if (tid == 0) partials[blockIdx.y * gridDim.x + blockIdx.x] = t;
+    }
+  }
+}
+
+__global__ void k_finish_norm(const double *partials, int n, double *out) {
+  __shared__ double wsum[32];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += partials[i];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double t = threadIdx.x < (blockDim.x >> 5) ? wsum[threadIdx.x] : 0.0;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) *out = sqrt(t);
+  }
+}
+
+// restrict (pressure_solver.cpp:118-132) + the rc.fill(0.0) before it (:222):
+// the coarse border is written as 0.
+__global__ void k_restrict(Grid r, Grid rc) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x;
+  int y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= rc.w || y >= rc.h) return;
+  float v = 0.0f;
+  if (x >= 1 && y >= 1 && x < rc.w - 1 && y < rc.h - 1) {
+    const float *a = r.d + (size_t)(2 * y - 1) * r.pitch + 2 * x;
+    const float *b = a + r.pitch, *c = b + r.pitch;
+    v = fw9(a[-1], a[0], a[1], b[-1], b[0], b[1], c[-1], c[0], c[1]);
+  }
+  rc.d[(size_t)y * rc.pitch + x] = v;
+}
+
+// MG::updateFields level step (pressure_solver.hpp:36-55): threshold of the
+// full-weighted fine flag at 0.2 (double compare); border cells stay 1.0.
+__global__ void k_coarsen_flag(Grid fine, Grid fc) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x;
+  int y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= fc.w || y >= fc.h) return;
+  float v = 1.0f;
+  if (x >= 1 && y >= 1 && x < fc.w - 1 && y < fc.h - 1) {
+    const float *a = fine.d + (size_t)(2 * y - 1) * fine.pitch + 2 * x;
+    const float *b = a + fine.pitch, *c = b + fine.pitch;
+    float s = fw9(a[-1], a[0], a[1], b[-1], b[0], b[1], c[-1], c[0], c[1]);
+    v = ((double)s > 0.2) ? 1.0f : 0.0f;
+  }
+  fc.d[(size_t)y * fc.pitch + x] = v;
+}
+
+// prolongate (pressure_solver.cpp:134-172): e on the whole fine grid.
+__global__ void k_prolongate(Grid e, Grid ec, Grid flagc, Grid flag) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x;
+  int y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= e.w || y >= e.h) return;
+  e.d[(size_t)y * e.pitch + x] =
+      prolong_cell(ec.d, flagc.d, ec.pitch, flag.d[(size_t)y * flag.pitch + x], x, y, e.w, e.h);
+}
+
+// correct (pressure_solver.cpp:174-181)
+__global__ void k_correct(Grid p, Grid e) {
+  int x = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+  int y = 1 + blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= p.w - 1 || y >= p.h - 1) return;
+  size_t c = (size_t)y * p.pitch + x;
+  p.d[c] = __fadd_rn(p.d[c], e.d[(size_t)y * e.pitch + x]);
+}
+
+// prolongate + correct in one pass (e never materialised)
+__global__ void k_prolongate_correct(Grid p, Grid ec, Grid flagc, Grid flag) {
+  int x = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+  int y = 1 + blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= p.w - 1 || y >= p.h - 1) return;
+  size_t c = (size_t)y * p.pitch + x;
+  float e = prolong_cell(ec.d, flagc.d, ec.pitch, flag.d[(size_t)y * flag.pitch + x], x, y,
+                         p.w, p.h);
+  p.d[c] = __fadd_rn(p.d[c], e);
+}
+
+// ---------------------------------------------------------------------------
+// DeviceMG
+// ---------------------------------------------------------------------------
+static inline dim3 blk2d() { return dim3(32, 8); }
+static inline dim3 grd2d(int w, int h) { return dim3(ceil_div(w, 32), ceil_div(h, 8)); }
+
+DeviceMG::DeviceMG(int W, int H, int device_, cudaStream_t stream_, LaunchCounter *lc_)
+    : device(device_), stream(stream_), lc(lc_) {
+  // MG::MG(int,int) pressure_solver.hpp:16-31
+  int cw = W, ch = H;
+  while (cw > 3 && ch > 3) {
+    MGLevel L;
+    L.w = cw;
+    L.h = ch;
+    L.pitch = round_up(cw, 32);
+    lv.push_back(L);
+    cw /= 2;
+    ch /= 2;
+  }
+  UBGL_REQUIRE(lv.size() >= 2, "MG needs at least two levels (W,H >= 8)");
+  for (size_t l = 0; l < lv.size(); l++) {
+    MGLevel &L = lv[l];
+    L.flagc = alloc_grid(L.w, L.h, L.pitch, false);
+    fill_grid(L.flagc, 1.0f, stream, nullptr);
+    if (l >= 1 && l + 1 < lv.size()) { // level levels-1 is never visited (:203)
+      L.rc = alloc_grid(L.w, L.h, L.pitch);
+      L.ec = alloc_grid(L.w, L.h, L.pitch);
+    }
+  }
+  dim3 g = grd2d(W, H);
+  n_partials = g.x * g.y;
+  UBGL_CUDA(cudaMalloc(&d_partials, sizeof(double) * n_partials));
+  UBGL_CUDA(cudaMalloc(&d_norm, sizeof(double)));
+  UBGL_CUDA(cudaStreamSynchronize(stream));
+}
+
+DeviceMG::~DeviceMG() {
+  for (auto &L : lv) {
+    free_grid(L.flagc);
+    free_grid(L.rc);
+    free_grid(L.ec);
+    free_grid(L.r);
+  }
+  if (d_partials) cudaFree(d_partials);
+  if (d_norm) cudaFree(d_norm);
+}
+
+void DeviceMG::ensure_r(int level) {
+  MGLevel &L = lv[level];
+  if (!L.r.d) L.r = alloc_grid(L.w, L.h, L.pitch);
+}
+
+void DeviceMG::update_fields(const Grid &flag0) {
+  UBGL_REQUIRE(flag0.w == lv[0].w && flag0.h == lv[0].h, "updateFields: flag size mismatch");
+  if (flag0.d != lv[0].flagc.d)
+    UBGL_CUDA(cudaMemcpy2DAsync(lv[0].flagc.d, sizeof(float) * lv[0].pitch, flag0.d,
+                                sizeof(float) * flag0.pitch, sizeof(float) * flag0.w, flag0.h,
+                                cudaMemcpyDeviceToDevice, stream));
+  for (size_t l = 1; l < lv.size(); l++) {
+    k_coarsen_flag<<<grd2d(lv[l].w, lv[l].h), blk2d(), 0, stream>>>(lv[l - 1].flagc, lv[l].flagc);
+    UBGL_CHECK_LAUNCH();
+    lc->n++;
+  }
+}
+
+void DeviceMG::rbgs(const Grid &p, const Grid &f, const Grid &flag, float hh, float alpha) {
+  dim3 b = blk2d();
+  dim3 g(ceil_div((p.w - 2 + 1) / 2, b.x), ceil_div(p.h - 2, b.y));
+  for (int color = 0; color < 2; color++) {
+    k_rbgs_half<<<g, b, 0, stream>>>(p, f, flag, hh, alpha, color);
+    UBGL_CHECK_LAUNCH();
+    lc->n++;
+  }
+}
+
+void DeviceMG::zero_gradient_bc(const Grid &p) {
+  int n = p.w > p.h ? p.w : p.h;
+  k_zero_gradient_bc<<<ceil_div(n, 256), 256, 0, stream>>>(p);
+  UBGL_CHECK_LAUNCH();
+  lc->n++;
+}
+
+void DeviceMG::residual(const Grid &p, const Grid &f, const Grid &flag, const Grid &r, float hh,
+                        bool want_norm) {
+  dim3 g = grd2d(p.w, p.h);
+  UBGL_REQUIRE(!want_norm || (int)(g.x * g.y) <= n_partials, "residual: grid larger than MG");
+  float ihsq = 1.0f / hh / hh;
+  k_residual<<<g, blk2d(), 0, stream>>>(p, f, flag, r, ihsq, want_norm ? d_partials : nullptr);
+  UBGL_CHECK_LAUNCH();
+  lc->n++;
+  if (want_norm) {
+    k_finish_norm<<<1, 1024, 0, stream>>>(d_partials, g.x * g.y, d_norm);
+    UBGL_CHECK_LAUNCH();
+    lc->n++;
+  }
+}
+
+float DeviceMG::residual_norm_result() {
+  double v = 0.0;
+  UBGL_CUDA(cudaMemcpyAsync(&v, d_norm, sizeof(double), cudaMemcpyDeviceToHost, stream));
+  UBGL_CUDA(cudaStreamSynchronize(stream));
+  return (float)v;
+}
+
+void DeviceMG::restrict_fw(const Grid &r, const Grid &rc) {
+  k_restrict<<<grd2d(rc.w, rc.h), blk2d(), 0, stream>>>(r, rc);
+  UBGL_CHECK_LAUNCH();
+  lc->n++;
+}
+
+void DeviceMG::prolongate(const Grid &e, const Grid &ec, const Grid &flagc, const Grid &flag) {
+  k_prolongate<<<grd2d(e.w, e.h), blk2d(), 0, stream>>>(e, ec, flagc, flag);
+  UBGL_CHECK_LAUNCH();
+  lc->n++;
+}
+
+void DeviceMG::correct(const Grid &p, const Grid &e) {
+  k_correct<<<grd2d(p.w - 2, p.h - 2), blk2d(), 0, stream>>>(p, e);
+  UBGL_CHECK_LAUNCH();
+  lc->n++;
+}
+
+void DeviceMG::prolongate_correct(const Grid &p, const Grid &ec, const Grid &flagc,
+                                  const Grid &flag) {
+  k_prolongate_correct<<<grd2d(p.w - 2, p.h - 2), blk2d(), 0, stream>>>(p, ec, flagc, flag);
+  UBGL_CHECK_LAUNCH();
+  lc->n++;
+}
+
+void DeviceMG::solve(const Grid &p, const Grid &f, const Grid &flag, float hh, bool zgbc) {
+  UBGL_REQUIRE(p.w == lv[0].w && p.h == lv[0].h, "solve: grid size mismatch");
+  solve_level(p, f, flag, hh, 0, zgbc);
+}
+
+// MG::solveLevel (pressure_solver.cpp:201-248), plain path: one kernel per
+// reference operator, same order.
+void DeviceMG::solve_level(const Grid &p, const Grid &f, const Grid &flag, float hh, int level,
+                           bool zgbc) {
+  const int nl = levels();
+  if (level == nl - 2) {
+    for (int i = 0; i < 5; i++) rbgs(p, f, flag, hh, 1.0f);
+    return;
+  }
+  const bool bc = (level == 0 && zgbc);
+  for (int i = 0; i < 3; i++) {
+    rbgs(p, f, flag, hh, 1.0f);
+    if (bc) zero_gradient_bc(p);
+  }
+  MGLevel &C = lv[level + 1];
+  ensure_r(level);
+  residual(p, f, flag, lv[level].r, hh, false);
+  restrict_fw(lv[level].r, C.rc);
+  fill_grid(C.ec, 0.0f, stream, lc);
+  float hc = hh * ((float)p.w - 1.0f) / ((float)C.w - 1.0f);
+  solve_level(C.ec, C.rc, C.flagc, hc, level + 1, false);
+  prolongate_correct(p, C.ec, C.flagc, flag);
+  if (bc) zero_gradient_bc(p);
+  for (int i = 0; i < 3; i++) {
+    rbgs(p, f, flag, hh, 1.0f);
+    if (bc) zero_gradient_bc(p);
+  }
+}
+
+} // namespace ubgl

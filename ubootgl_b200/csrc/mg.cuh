@@ -1,0 +1,66 @@
+// mg.cuh -- device-resident geometric multigrid (the reference's class MG,
+// pressure_solver.hpp:13-76, and the free operators of pressure_solver.cpp).
+#pragma once
+#include "common.cuh"
+#include <vector>
+
+namespace ubgl {
+
+struct MGLevel {
+  int w = 0, h = 0, pitch = 0;
+  Grid flagc; // flagcs[l]  (level 0: copy of the flag given to updateFields)
+  Grid rc;    // rcs[l]     restricted residual = rhs of this level (l >= 1)
+  Grid ec;    // ecs[l]     error / solution of this level            (l >= 1)
+  Grid r;     // rs[l]      residual scratch, only materialised by the plain path
+};
+
+class DeviceMG {
+public:
+  DeviceMG(int W, int H, int device, cudaStream_t stream, LaunchCounter *lc);
+  ~DeviceMG();
+  DeviceMG(const DeviceMG &) = delete;
+  DeviceMG &operator=(const DeviceMG &) = delete;
+
+  int levels() const { return (int)lv.size(); }
+  const MGLevel &level(int l) const { return lv[l]; }
+
+  // MG::updateFields (pressure_solver.hpp:34-57); flag0 is a device grid.
+  void update_fields(const Grid &flag0);
+  // MG::solve -> solveLevel(.., level 0) (pressure_solver.cpp:201-248)
+  void solve(const Grid &p, const Grid &f, const Grid &flag, float hh, bool zgbc);
+
+  // individual operators (device grids), used by the plain path and the C ABI
+  void rbgs(const Grid &p, const Grid &f, const Grid &flag, float hh, float alpha);
+  void zero_gradient_bc(const Grid &p);
+  void residual(const Grid &p, const Grid &f, const Grid &flag, const Grid &r,
+                float hh, bool want_norm);
+  float residual_norm_result(); // syncs the stream
+  void restrict_fw(const Grid &r, const Grid &rc);
+  void prolongate(const Grid &e, const Grid &ec, const Grid &flagc, const Grid &flag);
+  void correct(const Grid &p, const Grid &e);
+  void prolongate_correct(const Grid &p, const Grid &ec, const Grid &flagc,
+                          const Grid &flag);
+
+  bool fused = true;
+  int device;
+  cudaStream_t stream;
+  LaunchCounter *lc;
+
+private:
+  void solve_level(const Grid &p, const Grid &f, const Grid &flag, float hh,
+                   int level, bool zgbc);
+  void ensure_r(int level);
+  std::vector<MGLevel> lv;
+  double *d_partials = nullptr; // per-block partial sums of r^2
+  double *d_norm = nullptr;
+  int n_partials = 0;
+};
+
+Grid alloc_grid(int w, int h, int pitch_floats, bool zero = true);
+void free_grid(Grid &g);
+// unpadded host <-> pitched device copies on a stream
+void upload_grid(const Grid &g, const float *host, int w, int h, cudaStream_t s);
+void download_grid(const Grid &g, float *host, int w, int h, cudaStream_t s);
+void fill_grid(const Grid &g, float v, cudaStream_t s, LaunchCounter *lc);
+
+} // namespace ubgl

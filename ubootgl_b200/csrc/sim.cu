@@ -1,0 +1,519 @@
+// sim.cu -- Simulation::step on the device.  Reference: simulation.cpp /
+// simulation.hpp / interpolators.hpp of te42kyfo/ubootgl (file:line per kernel).
+#include "sim.cuh"
+#include "stencils.cuh"
+#include <cmath>
+#include <cstring>
+
+namespace ubgl {
+
+static inline dim3 blk2d() { return dim3(32, 8); }
+static inline dim3 grd2d(int w, int h) { return dim3(ceil_div(w, 32), ceil_div(h, 8)); }
+
+// ---------------------------------------------------------------------------
+// plain kernels: one per reference stage
+// ---------------------------------------------------------------------------
+
+// applyAccumulatedVelocity (simulation.cpp:376-396), one component
+__global__ void k_apply_accum(Grid v, Grid acc) {
+  int x = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+  int y = 1 + blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= v.w - 1 || y >= v.h - 1) return;
+  size_t i = (size_t)y * v.pitch + x;
+  v.d[i] = __fadd_rn(v.d[i], acc.d[i]);
+  acc.d[i] = 0.0f;
+}
+
+// diffuse, x-velocity pass (simulation.cpp:113-129)
+__global__ void k_diffuse_vx(Grid src, Grid dst, Grid flag, float a, float den) {
+  int x = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+  int y = 1 + blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= src.w - 1 || y >= src.h - 1) return;
+  const float *v = src.d + (size_t)y * src.pitch + x;
+  const float *fl = flag.d + (size_t)y * flag.pitch + x;
+  const int vp = src.pitch, fp = flag.pitch;
+  float mE = __fmul_rn(fl[1], fl[2]);
+  float mW = __fmul_rn(fl[0], fl[-1]);
+  float fvn = __fmul_rn(fl[fp], fl[fp - 1]);
+  float fvs = __fmul_rn(fl[-fp], fl[-fp - 1]);
+  float mC = __fmul_rn(fl[0], fl[1]);
+  dst.d[(size_t)y * dst.pitch + x] =
+      diffuse_cell(v[0], v[1], mE, v[-1], mW, v[vp], fvn, v[-vp], fvs, mC, a, den);
+}
+
+// diffuse, y-velocity pass (simulation.cpp:139-155)
+__global__ void k_diffuse_vy(Grid src, Grid dst, Grid flag, float a, float den) {
+  int x = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+  int y = 1 + blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= src.w - 1 || y >= src.h - 1) return;
+  const float *v = src.d + (size_t)y * src.pitch + x;
+  const float *fl = flag.d + (size_t)y * flag.pitch + x;
+  const int vp = src.pitch, fp = flag.pitch;
+  float mS = __fmul_rn(fl[0], fl[-fp]);
+  float mN = __fmul_rn(fl[fp], fl[2 * fp]);
+  float fve = __fmul_rn(fl[1], fl[fp + 1]);
+  float fvw = __fmul_rn(fl[-1], fl[fp - 1]);
+  float mC = __fmul_rn(fl[0], fl[fp]);
+  dst.d[(size_t)y * dst.pitch + x] =
+      diffuse_cell(v[0], v[-vp], mS, v[vp], mN, v[1], fve, v[-1], fvw, mC, a, den);
+}
+
+// setVBCs (simulation.cpp:80-102): column loops, then row loops (the row loops
+// read the column results at x = 0 / w-1, and win at the corners), written to
+// the front AND back buffers.  One block; __syncthreads separates the phases.
+__global__ void k_set_vbcs(Grid xf, Grid xb, Grid yf, Grid yb, int bcW, int bcE, int bcN,
+                           int bcS) {
+  for (int y = threadIdx.x; y < xf.h; y += blockDim.x) {
+    float v = vbc_par(bcW, xf.at(1, y), xf.at(0, y));
+    xf.at(0, y) = v;
+    xb.at(0, y) = v;
+    v = vbc_par(bcE, xf.at(xf.w - 2, y), xf.at(xf.w - 1, y));
+    xf.at(xf.w - 1, y) = v;
+    xb.at(xf.w - 1, y) = v;
+  }
+  for (int y = threadIdx.x; y < yf.h; y += blockDim.x) {
+    float v = vbc_per(bcW, yf.at(1, y), yf.at(0, y));
+    yf.at(0, y) = v;
+    yb.at(0, y) = v;
+    v = vbc_per(bcE, yf.at(yf.w - 2, y), yf.at(yf.w - 1, y));
+    yf.at(yf.w - 1, y) = v;
+    yb.at(yf.w - 1, y) = v;
+  }
+  __syncthreads();
+  for (int x = threadIdx.x; x < xf.w; x += blockDim.x) {
+    float v = vbc_per(bcS, xf.at(x, 1), xf.at(x, 0));
+    xf.at(x, 0) = v;
+    xb.at(x, 0) = v;
+    v = vbc_per(bcN, xf.at(x, xf.h - 2), xf.at(x, xf.h - 1));
+    xf.at(x, xf.h - 1) = v;
+    xb.at(x, xf.h - 1) = v;
+  }
+  for (int x = threadIdx.x; x < yf.w; x += blockDim.x) {
+    float v = vbc_par(bcS, yf.at(x, 1), yf.at(x, 0));
+    yf.at(x, 0) = v;
+    yb.at(x, 0) = v;
+    v = vbc_par(bcN, yf.at(x, yf.h - 2), yf.at(x, yf.h - 1));
+    yf.at(x, yf.h - 1) = v;
+    yb.at(x, yf.h - 1) = v;
+  }
+}
+
+// bicubicSample (interpolators.hpp:92-206): clamp to [3, w-3] x [3, h-3]
+// (:94-97), truncate (:99-103), 4x4 taps at rows iy-1..iy+2 / cols ix-1..ix+2,
+// vertical Hermite per column first, then horizontal (:132-204).
+__device__ __forceinline__ float bicubic(const float *__restrict__ g, int pitch, int w, int h,
+                                         float cx, float cy) {
+  cx = fmaxf(fminf(cx, (float)w - 3.0f), 3.0f);
+  cy = fmaxf(fminf(cy, (float)h - 3.0f), 3.0f);
+  int icx = (int)cx, icy = (int)cy;
+  float stx = __fsub_rn(cx, truncf(cx)), sty = __fsub_rn(cy, truncf(cy));
+  const float *b = g + (size_t)(icy - 1) * pitch + (icx - 1);
+  float c0 = cubic_hermite(sty, __ldg(b + 0), __ldg(b + pitch + 0), __ldg(b + 2 * pitch + 0),
+                           __ldg(b + 3 * pitch + 0));
+  float c1 = cubic_hermite(sty, __ldg(b + 1), __ldg(b + pitch + 1), __ldg(b + 2 * pitch + 1),
+                           __ldg(b + 3 * pitch + 1));
+  float c2 = cubic_hermite(sty, __ldg(b + 2), __ldg(b + pitch + 2), __ldg(b + 2 * pitch + 2),
+                           __ldg(b + 3 * pitch + 2));
+  float c3 = cubic_hermite(sty, __ldg(b + 3), __ldg(b + pitch + 3), __ldg(b + 2 * pitch + 3),
+                           __ldg(b + 3 * pitch + 3));
+  return cubic_hermite(stx, c0, c1, c2, c3);
+}
+
+// advect, x-velocity faces (simulation.cpp:246-297).  blockDim.x == 32 and the
+// warp's first face is x = 1 (mod 32), so lanes 8k..8k+7 are exactly one of the
+// reference's AVX2 octets (x = 1, 9, 17, ...).  Reproduced quirks:
+//  * octets exist only while x0 < vx.width - 8 (:248) -> last columns untouched;
+//  * whole-octet skip unless some lane has flag(x-1+i,y)+flag(x+i,y) == 2 (:254);
+//  * untouched entries keep whatever the back buffer holds.
+__global__ void k_advect_vx(Grid vx, Grid vy, Grid vxb, Grid flag, float half, float full) {
+  const int lane = threadIdx.x;
+  const int xi = 1 + blockIdx.x * 32 + lane;
+  const int y = 1 + blockIdx.y * blockDim.y + threadIdx.y;
+  const bool row_ok = y < vx.h - 1;
+  const int x0 = xi - (lane & 7);
+  const bool oct_ok = row_ok && (x0 < vx.w - 8);
+  bool cond = false;
+  float f0 = 0.0f, f1 = 0.0f;
+  if (oct_ok) {
+    const float *fl = flag.d + (size_t)y * flag.pitch + xi;
+    f0 = fl[0];
+    f1 = fl[1];
+    cond = (__fadd_rn(fl[-1], f0) == 2.0f);
+  }
+  unsigned ball = __ballot_sync(0xffffffffu, cond);
+  if (!oct_ok || ((ball >> (lane & ~7)) & 0xffu) == 0) return;
+
+  float posx = __fadd_rn((float)xi, 0.5f), posy = (float)y;
+  float vx1 = vx.at(xi, y);
+  float vy1 = __fmul_rn(__fadd_rn(__fadd_rn(vy.at(xi, y), vy.at(xi, y - 1)),
+                                  __fadd_rn(vy.at(xi + 1, y), vy.at(xi + 1, y - 1))),
+                        0.25f);
+  float midx = __fmaf_rn(-vx1, half, posx), midy = __fmaf_rn(-vy1, half, posy);
+  float vx2 = bicubic(vx.d, vx.pitch, vx.w, vx.h, __fsub_rn(midx, 0.5f), midy);
+  float vy2 = bicubic(vy.d, vy.pitch, vy.w, vy.h, midx, __fsub_rn(midy, 0.5f));
+  float endx = __fmaf_rn(-vx2, full, posx), endy = __fmaf_rn(-vy2, full, posy);
+  float xvel = bicubic(vx.d, vx.pitch, vx.w, vx.h, __fsub_rn(endx, 0.5f), endy);
+  vxb.at(xi, y) = __fmul_rn(__fmul_rn(xvel, f0), f1);
+}
+
+// advect, y-velocity faces (simulation.cpp:300-347); rows 1..H-2 like the vx
+// loop (so vy's top boundary row IS written, :247).  The four vx loads at
+// (x+1, .) are FLAT in the reference (:317-325): when x+1 == vx.width they read
+// the first element of the next row; reproduced through vx_flat().
+__device__ __forceinline__ float vx_flat(const Grid &vx, int x, int y) {
+  if (x >= vx.w) {
+    x -= vx.w;
+    y += 1;
+  }
+  return vx.at(x, y);
+}
+__global__ void k_advect_vy(Grid vx, Grid vy, Grid vyb, Grid flag, int rows, float half,
+                            float full) {
+  const int lane = threadIdx.x;
+  const int xi = 1 + blockIdx.x * 32 + lane;
+  const int y = 1 + blockIdx.y * blockDim.y + threadIdx.y;
+  const bool row_ok = y < rows - 1; // rows = vx.height: y in [1, H-2]
+  const int x0 = xi - (lane & 7);
+  const bool oct_ok = row_ok && (x0 < vy.w - 8);
+  bool cond = false;
+  float f0 = 0.0f, f1 = 0.0f;
+  if (oct_ok) {
+    const float *fl = flag.d + (size_t)y * flag.pitch + xi;
+    f0 = fl[0];
+    f1 = fl[flag.pitch];
+    cond = (__fadd_rn(f0, fl[-flag.pitch]) == 2.0f);
+  }
+  unsigned ball = __ballot_sync(0xffffffffu, cond);
+  if (!oct_ok || ((ball >> (lane & ~7)) & 0xffu) == 0) return;
+
+  float posy = __fadd_rn((float)y, 0.5f), posx = (float)xi;
+  float vy1 = vy.at(xi, y);
+  float vx1 = __fmul_rn(__fadd_rn(__fadd_rn(vx.at(xi, y), vx.at(xi, y - 1)),
+                                  __fadd_rn(vx_flat(vx, xi + 1, y), vx_flat(vx, xi + 1, y - 1))),
+                        0.25f);
+  float midx = __fmaf_rn(-vx1, half, posx), midy = __fmaf_rn(-vy1, half, posy);
+  float vx2 = bicubic(vx.d, vx.pitch, vx.w, vx.h, __fsub_rn(midx, 0.5f), midy);
+  float vy2 = bicubic(vy.d, vy.pitch, vy.w, vy.h, midx, __fsub_rn(midy, 0.5f));
+  float endx = __fmaf_rn(-vx2, full, posx), endy = __fmaf_rn(-vy2, full, posy);
+  float yvel = bicubic(vy.d, vy.pitch, vy.w, vy.h, endx, __fsub_rn(endy, 0.5f));
+  vyb.at(xi, y) = __fmul_rn(__fmul_rn(yvel, f0), f1);
+}
+
+// project part 1 (simulation.cpp:166-171): f = -(1/h) div v on the interior
+__global__ void k_divergence(Grid vx, Grid vy, Grid f, float ih) {
+  int x = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+  int y = 1 + blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= f.w - 1 || y >= f.h - 1) return;
+  float d = __fsub_rn(__fadd_rn(__fsub_rn(vx.at(x, y), vx.at(x - 1, y)), vy.at(x, y)),
+                      vy.at(x, y - 1));
+  f.at(x, y) = __fmul_rn(-ih, d);
+}
+
+// sinks (simulation.cpp:173-182): 3x3 stamps, in list order (later sinks win)
+__global__ void k_stamp_sinks(Grid f, const float *sinks, int n) {
+  int dx = (int)(threadIdx.x % 3) - 1, dy = (int)(threadIdx.x / 3) - 1;
+  for (int k = 0; k < n; k++) {
+    if (threadIdx.x < 9) {
+      int ix = (int)sinks[3 * k], iy = (int)sinks[3 * k + 1];
+      f.at(ix + dx, iy + dy) = sinks[3 * k + 2];
+    }
+    __syncthreads();
+  }
+}
+
+// setPBC (simulation.cpp:36-45): columns for all y, then rows for all x.
+__global__ void k_set_pbc(Grid p, int bcW, int bcE, int bcN, int bcS) {
+  for (int y = threadIdx.x; y < p.h; y += blockDim.x) {
+    p.at(0, y) = single_pbc(bcW, p.at(1, y));
+    p.at(p.w - 1, y) = single_pbc(bcE, p.at(p.w - 2, y));
+  }
+  __syncthreads();
+  for (int x = threadIdx.x; x < p.w; x += blockDim.x) {
+    p.at(x, 0) = single_pbc(bcS, p.at(x, 1));
+    p.at(x, p.h - 1) = single_pbc(bcN, p.at(x, p.h - 2));
+  }
+}
+
+// gradient subtraction (simulation.cpp:196-207)
+__global__ void k_gradient(Grid vx, Grid vy, Grid p, Grid flag, float ih) {
+  int x = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+  int y = 1 + blockIdx.y * blockDim.y + threadIdx.y;
+  const int W = p.w, H = p.h;
+  if (x >= W - 1 || y >= H - 1) return;
+  float pc = p.at(x, y), fc = flag.at(x, y);
+  if (x < W - 2) {
+    float m = __fmul_rn(__fmul_rn(fc, flag.at(x + 1, y)), ih);
+    vx.at(x, y) = __fmaf_rn(-m, __fsub_rn(p.at(x + 1, y), pc), vx.at(x, y));
+  }
+  if (y < H - 2) {
+    float m = __fmul_rn(__fmul_rn(fc, flag.at(x, y + 1)), ih);
+    vy.at(x, y) = __fmaf_rn(-m, __fsub_rn(p.at(x, y + 1), pc), vy.at(x, y));
+  }
+}
+
+// ---------------------------------------------------------------------------
+// DeviceSim
+// ---------------------------------------------------------------------------
+DeviceSim::DeviceSim(const float *host_flag, int W_, int H_, float pwidth_, float mu_, int device_)
+    : W(W_), H(H_), pwidth(pwidth_), mu(mu_), device(device_) {
+  UBGL_REQUIRE(W >= 8 && H >= 8, "Simulation needs W,H >= 8");
+  UBGL_REQUIRE(host_flag != nullptr, "flag must not be null");
+  UBGL_CUDA(cudaSetDevice(device));
+  UBGL_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  pitch = round_up(W, 32);
+  for (int b = 0; b < 2; b++) {
+    vx[b] = alloc_grid(W - 1, H, pitch);
+    vy[b] = alloc_grid(W, H - 1, pitch);
+  }
+  vx_accum = alloc_grid(W - 1, H, pitch);
+  vy_accum = alloc_grid(W, H - 1, pitch);
+  vx_current = alloc_grid(W - 1, H, pitch);
+  vy_current = alloc_grid(W, H - 1, pitch);
+  p = alloc_grid(W, H, pitch);
+  f = alloc_grid(W, H, pitch);
+  flag = alloc_grid(W, H, pitch);
+  // Simulation(flag,pwidth,mu) simulation.hpp:32-67
+  bcS = 3; bcN = 3; bcW = 0; bcE = 2;
+  h = pwidth / ((float)W - 1.0f);
+  mg.reset(new DeviceMG(W, H, device, stream, &lc));
+  upload_grid(flag, host_flag, W, H, stream);
+  {
+    std::vector<float> col(H, 1.0f); // vx.f(0,y) = vx.b(0,y) = 1 (:58-60)
+    for (int b = 0; b < 2; b++)
+      UBGL_CUDA(cudaMemcpy2DAsync(vx[b].d, sizeof(float) * pitch, col.data(), sizeof(float),
+                                  sizeof(float), H, cudaMemcpyHostToDevice, stream));
+    UBGL_CUDA(cudaStreamSynchronize(stream));
+  }
+  mg->update_fields(flag);
+  UBGL_CUDA(cudaStreamSynchronize(stream));
+}
+
+DeviceSim::~DeviceSim() {
+  cudaSetDevice(device);
+  if (stream) cudaStreamSynchronize(stream);
+  mg.reset();
+  for (int b = 0; b < 2; b++) {
+    free_grid(vx[b]);
+    free_grid(vy[b]);
+  }
+  free_grid(vx_accum); free_grid(vy_accum); free_grid(vx_current); free_grid(vy_current);
+  free_grid(p); free_grid(f); free_grid(flag); free_grid(r);
+  if (d_sinks) cudaFree(d_sinks);
+  if (stream) cudaStreamDestroy(stream);
+}
+
+Grid DeviceSim::field(int id) {
+  switch (id) {
+  case F_FLAG: return flag;
+  case F_VX: return vx[vxf];
+  case F_VY: return vy[vyf];
+  case F_VXB: return vx[1 - vxf];
+  case F_VYB: return vy[1 - vyf];
+  case F_P: return p;
+  case F_F: return f;
+  case F_VX_ACCUM: return vx_accum;
+  case F_VY_ACCUM: return vy_accum;
+  case F_R:
+    if (!r.d) r = alloc_grid(W, H, pitch);
+    return r;
+  case F_VX_CURRENT: return vx_current;
+  case F_VY_CURRENT: return vy_current;
+  }
+  throw ArgError{"unknown field id"};
+}
+
+void DeviceSim::field_size(int id, int *w, int *hh) const {
+  switch (id) {
+  case F_VX: case F_VXB: case F_VX_ACCUM: case F_VX_CURRENT: *w = W - 1; *hh = H; return;
+  case F_VY: case F_VYB: case F_VY_ACCUM: case F_VY_CURRENT: *w = W; *hh = H - 1; return;
+  default: *w = W; *hh = H; return;
+  }
+}
+
+void DeviceSim::upload(int id, const float *host) {
+  UBGL_REQUIRE(host != nullptr, "upload: null host pointer");
+  Grid g = field(id);
+  upload_grid(g, host, g.w, g.h, stream);
+  UBGL_CUDA(cudaStreamSynchronize(stream)); // host buffer is only borrowed for the call
+}
+
+void DeviceSim::download(int id, float *host) {
+  UBGL_REQUIRE(host != nullptr, "download: null host pointer");
+  Grid g = field(id);
+  download_grid(g, host, g.w, g.h, stream);
+  UBGL_CUDA(cudaStreamSynchronize(stream));
+}
+
+void DeviceSim::update_flag(const float *host_flag) {
+  UBGL_REQUIRE(host_flag != nullptr, "update_flag: null host pointer");
+  upload_grid(flag, host_flag, W, H, stream);
+  mg->update_fields(flag);
+  UBGL_CUDA(cudaStreamSynchronize(stream));
+}
+
+void DeviceSim::sync() { UBGL_CUDA(cudaStreamSynchronize(stream)); }
+
+void DeviceSim::apply_accum() {
+  k_apply_accum<<<grd2d(W - 3, H - 2), blk2d(), 0, stream>>>(vx[vxf], vx_accum);
+  UBGL_CHECK_LAUNCH();
+  k_apply_accum<<<grd2d(W - 2, H - 3), blk2d(), 0, stream>>>(vy[vyf], vy_accum);
+  UBGL_CHECK_LAUNCH();
+  lc.n += 2;
+}
+
+void DeviceSim::set_vbcs() {
+  k_set_vbcs<<<1, 1024, 0, stream>>>(vx[vxf], vx[1 - vxf], vy[vyf], vy[1 - vyf], bcW, bcE, bcN,
+                                     bcS);
+  UBGL_CHECK_LAUNCH();
+  lc.n++;
+}
+
+void DeviceSim::diffuse() {
+  float a = dt * mu * ((float)W - 1.0f) / pwidth; // simulation.cpp:105
+  float den = 1.0f + 4.0f * a;
+  for (int i = 1; i < 3; i++) {
+    k_diffuse_vx<<<grd2d(W - 3, H - 2), blk2d(), 0, stream>>>(vx[vxf], vx[1 - vxf], flag, a, den);
+    UBGL_CHECK_LAUNCH();
+    lc.n++;
+    vxf = 1 - vxf;
+    set_vbcs();
+  }
+  for (int i = 1; i < 3; i++) {
+    k_diffuse_vy<<<grd2d(W - 2, H - 3), blk2d(), 0, stream>>>(vy[vyf], vy[1 - vyf], flag, a, den);
+    UBGL_CHECK_LAUNCH();
+    lc.n++;
+    vyf = 1 - vyf;
+    set_vbcs();
+  }
+}
+
+void DeviceSim::advect() {
+  float ih = 1.0f / h;
+  float half = 0.5f * dt * ih, full = dt * ih; // simulation.cpp:276,286
+  dim3 b(32, 8);
+  dim3 g(ceil_div(W - 2, 32), ceil_div(H - 2, 8));
+  k_advect_vx<<<g, b, 0, stream>>>(vx[vxf], vy[vyf], vx[1 - vxf], flag, half, full);
+  UBGL_CHECK_LAUNCH();
+  k_advect_vy<<<g, b, 0, stream>>>(vx[vxf], vy[vyf], vy[1 - vyf], flag, H, half, full);
+  UBGL_CHECK_LAUNCH();
+  lc.n += 2;
+  vxf = 1 - vxf;
+  vyf = 1 - vyf;
+}
+
+void DeviceSim::project() {
+  float ih = 1.0f / h;
+  k_divergence<<<grd2d(W - 2, H - 2), blk2d(), 0, stream>>>(vx[vxf], vy[vyf], f, ih);
+  UBGL_CHECK_LAUNCH();
+  lc.n++;
+
+  // sinks (simulation.cpp:173-187): grid position, border skip, decay and erase
+  // are host-side list work exactly as in the reference; only the 3x3 stamps
+  // touch device memory.
+  std::vector<float> stamps;
+  for (auto &s : sinks) {
+    float gx = s.x / h + 0.5f, gy = s.y / h + 0.5f;
+    if (gx <= 3 || gx > (float)(W - 3) || gy <= 3 || gy > (float)(H - 3)) continue;
+    stamps.push_back((float)(int)gx);
+    stamps.push_back((float)(int)gy);
+    stamps.push_back(s.z);
+    s.z = (float)((double)s.z * std::pow(0.000001, (double)(dt * 50)));
+  }
+  {
+    size_t n = 0;
+    for (size_t k = 0; k < sinks.size(); k++)
+      if (!(sinks[k].z < 0.05f)) sinks[n++] = sinks[k];
+    sinks.resize(n);
+  }
+  if (!stamps.empty()) {
+    int n = (int)stamps.size() / 3;
+    if (n > cap_sinks) {
+      if (d_sinks) UBGL_CUDA(cudaFree(d_sinks));
+      cap_sinks = n * 2;
+      UBGL_CUDA(cudaMalloc(&d_sinks, sizeof(float) * 3 * cap_sinks));
+    }
+    UBGL_CUDA(cudaMemcpyAsync(d_sinks, stamps.data(), sizeof(float) * stamps.size(),
+                              cudaMemcpyHostToDevice, stream));
+    UBGL_CUDA(cudaStreamSynchronize(stream)); // stamps is a stack-lifetime staging buffer
+    k_stamp_sinks<<<1, 32, 0, stream>>>(f, d_sinks, n);
+    UBGL_CHECK_LAUNCH();
+    lc.n++;
+  }
+
+  for (int c = 0; c < vcycles; c++) mg->solve(p, f, flag, h, true);
+
+  k_set_pbc<<<1, 1024, 0, stream>>>(p, bcW, bcE, bcN, bcS);
+  UBGL_CHECK_LAUNCH();
+  k_gradient<<<grd2d(W - 2, H - 2), blk2d(), 0, stream>>>(vx[vxf], vy[vyf], p, flag, ih);
+  UBGL_CHECK_LAUNCH();
+  lc.n += 2;
+}
+
+void DeviceSim::save_current() {
+  UBGL_CUDA(cudaMemcpyAsync(vx_current.d, vx[vxf].d, vx_current.bytes(), cudaMemcpyDeviceToDevice,
+                            stream));
+  UBGL_CUDA(cudaMemcpyAsync(vy_current.d, vy[vyf].d, vy_current.bytes(), cudaMemcpyDeviceToDevice,
+                            stream));
+}
+
+void DeviceSim::stage(int st, float dt_) {
+  dt = dt_;
+  switch (st) {
+  case ST_ACCUM: apply_accum(); break;
+  case ST_DIFFUSE: diffuse(); break;
+  case ST_ADVECT: advect(); break;
+  case ST_SETVBCS: set_vbcs(); break;
+  case ST_PROJECT: project(); break;
+  case ST_SAVE: save_current(); break;
+  default: throw ArgError{"unknown stage id"};
+  }
+}
+
+// Simulation::step (simulation.cpp:356-374)
+void DeviceSim::step(float dt_) {
+  dt = dt_;
+  cudaEvent_t ev[8];
+  if (timing)
+    for (auto &e : ev) UBGL_CUDA(cudaEventCreate(&e));
+  int k = 0;
+  auto mark = [&]() { if (timing) UBGL_CUDA(cudaEventRecord(ev[k++], stream)); };
+  mark();
+  apply_accum();
+  mark();
+  diffuse();
+  mark();
+  advect();
+  mark();
+  set_vbcs();
+  mark();
+  project();
+  mark();
+  set_vbcs();
+  mark();
+  save_current();
+  mark();
+  if (timing) {
+    UBGL_CUDA(cudaStreamSynchronize(stream));
+    float ms[7];
+    for (int i = 0; i < 7; i++) UBGL_CUDA(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
+    stage_ms[ST_ACCUM] = ms[0];
+    stage_ms[ST_DIFFUSE] = ms[1];
+    stage_ms[ST_ADVECT] = ms[2];
+    stage_ms[ST_SETVBCS] = ms[3] + ms[5];
+    stage_ms[ST_PROJECT] = ms[4];
+    stage_ms[ST_SAVE] = ms[6];
+    for (auto &e : ev) cudaEventDestroy(e);
+  }
+}
+
+float DeviceSim::residual() {
+  Grid rr = field(F_R);
+  mg->residual(p, f, flag, rr, h, true);
+  return mg->residual_norm_result();
+}
+
+void DeviceSim::mg_solve(int cycles) {
+  for (int c = 0; c < cycles; c++) mg->solve(p, f, flag, h, true);
+}
+
+} // namespace ubgl
