@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py -- fluid-step throughput (MLUP/s) of the B200-native hot path.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload NAME]
+
+A "step" is one Simulation::step (accumulate, diffuse, advect, divergence,
+2 multigrid V-cycles, gradient, save) on synthetic input.  Workloads
+(SURVEY.md section 8d / BASELINE.json configs):
+
+  channel8192  8192x8192 channel with 32 obstacles, uniform stream, dt = h
+               (configs[2]; the config BASELINE.json's target is quoted on) -- default at N=1
+  channel32768 32768x32768, same generator, row-slab decomposed (configs[3]) -- default at N>1
+  game         1090x436-like game level (configs[1]) -- L2 resident, latency bound
+  channel<S>   any other square size S
+
+Prints ONE JSON line (rank 0).  See DESIGN.md section "Measurement".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from tests import cases  # noqa: E402  (seeded synthetic generators, numpy only)
+
+VCYCLES = 2                      # simulation.cpp:189-190
+B_NONMG = 152.0                  # algorithmic B/cell of the non-MG stages
+B_VCYCLE = 186.7                 # algorithmic B/level-0-cell per V-cycle, whole pyramid
+PWIDTH, MU = 0.8, 0.001
+
+
+def bytes_per_cell(k=VCYCLES):
+    return B_NONMG + B_VCYCLE * k
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def workload_dims(name):
+    if name == "game":
+        return 1090, 436
+    if name.startswith("channel"):
+        s = int(name[len("channel"):])
+        return s, s
+    raise SystemExit(f"unknown workload {name}")
+
+
+def make_inputs(name):
+    W, H = workload_dims(name)
+    if name == "game":
+        from tests import golden_util
+        flag, _, _ = golden_util.game_level()
+        vx = np.zeros((H, W - 1), np.float32)
+        vx[:, 0] = 1.0
+        vy = np.zeros((H - 1, W), np.float32)
+        dt = 0.001
+    else:
+        flag, _ = cases.channel_flag(W, H, seed=1234)
+        vx, vy = cases.uniform_stream(flag)
+        dt = float(np.float32(PWIDTH) / np.float32(W - 1))  # dt = h, CFL ~ 1
+    return W, H, flag, vx, vy, dt
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows = []
+        self.stop = False
+        self.index = index
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.t.join(timeout=6)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 7:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference's own OpenMP+AVX2 CPU solver
+# ---------------------------------------------------------------------------
+def cpu_reference_run(name, steps, warmup, threads=None):
+    """Times Simulation::step of the unmodified reference (oracle/_ref when it
+    was built from /root/reference, else the C restatement) on the host cores."""
+    from oracle import bind as ob
+    if ob.have_ref():
+        chk, kind = ob.Ref(), "reference"
+    else:
+        if not ob.have_port():
+            ob.build(ref=False)
+        chk, kind = ob.Port(), "port"
+    nproc = chk.num_procs()
+    threads = threads or nproc
+    chk.set_threads(threads)
+    W, H, flag, vx, vy, dt = make_inputs(name)
+    sim = chk.Sim(flag, PWIDTH, MU)
+    sim.set(ob.VX, vx)
+    sim.set(ob.VY, vy)
+    for _ in range(warmup):
+        sim.step(dt)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        sim.step(dt)
+    t = time.perf_counter() - t0
+    path = "pipelined path 3 (H/T >= 100)" if H // threads >= 100 else "canonical red-black"
+    return dict(value=W * H * steps / t / 1e6, ms_per_step=t / steps * 1e3, cores=threads, kind=kind,
+                nproc=nproc, rbgs_path=path, W=W, H=H, steps=steps, warmup=warmup)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    name = args.workload or ("channel8192" if args.gpus == 1 else "channel32768")
+    sample = name
+    W, H = workload_dims(name)
+    if W * H > 8192 * 8192:
+        # a 32768^2 reference step needs ~80 GB and minutes per step: time the
+        # 8192^2 member of the same generator instead and say so
+        sample = "channel8192"
+    steps = max(1, min(args.steps, 3 if sample != "game" else args.steps))
+    warmup = max(1, min(args.warmup, 1 if sample != "game" else args.warmup))
+    r = cpu_reference_run(sample, steps, warmup)
+    line = {
+        "impl": "reference", "metric": "fluid_step_throughput", "value": r["value"], "unit": "MLUP/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+        "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": name, "grid": [W, H], "vcycles_per_step": VCYCLES,
+                   "note": "reference CPU solver (OpenMP+AVX2) on the GPU box's host cores"},
+        "cpu_baseline": {"value": r["value"], "unit": "MLUP/s", "cores": r["cores"], "kind": r["kind"],
+                         "sample": f"{sample}: {r['warmup']} warm-up + {r['steps']} timed Simulation::step, "
+                                   f"OMP threads {r['cores']} of {r['nproc']} procs, rbgs {r['rbgs_path']}"},
+        "e2e": {"value": r["value"], "unit": "MLUP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------
+def run_single_gpu(args, name):
+    import torch
+    import ubootgl_b200 as u
+    from ubootgl_b200 import capi
+
+    if u.lib.ubgl_device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device visible to libubgl.so (there is no CPU fallback)")
+    dev = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(dev)
+    W, H, flag, vx, vy, dt = make_inputs(name)
+    N = W * H
+    sim = u.Simulation(flag, PWIDTH, MU, device=dev)
+    sim.set(capi.VX, vx)
+    sim.set(capi.VY, vy)
+    stream = torch.cuda.ExternalStream(sim.stream(), device=dev)
+    K, Wm = args.steps, args.warmup
+
+    # ---- device-resident throughput (`value`) ----
+    for _ in range(Wm):
+        sim.step(dt)
+    sim.sync()
+    torch.cuda.synchronize()
+    l0 = sim.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(dev) as clk:
+        e0.record(stream)
+        for _ in range(K):
+            sim.step(dt)
+        e1.record(stream)
+        sim.sync()
+        torch.cuda.synchronize()
+    ms_total = e0.elapsed_time(e1)
+    launches = sim.launch_count() - l0
+    ms_step = ms_total / K
+    value = N * K / (ms_total * 1e-3) / 1e6
+    res_after = sim.residual()
+
+    # ---- per-kernel profile (CUDA events around every launch, same stream) ----
+    sim.profile(True)
+    PK = min(K, 5)
+    for _ in range(PK):
+        sim.step(dt)
+    sim.sync()
+    stats = sim.kernel_stats()
+    sim.profile(False)
+    prof_total = sum(ms for _, ms in stats.values())
+    kern = sorted(((ms / PK, n // PK, k, l) for (k, l), (n, ms) in stats.items()), reverse=True)
+    peak, peak_src = peaks()
+    roof = dominant_roofline(kern, W, H, peak, peak_src, prof_total / PK)
+
+    # ---- end to end through the host-mirror API (`e2e`) ----
+    pin = lambda shape: torch.empty(shape, dtype=torch.float32, pin_memory=True).numpy()
+    ax, ay = pin((H, W - 1)), pin((H - 1, W))
+    ax[:] = 0
+    ay[:] = 0
+    outs = dict(vx=pin((H, W - 1)), vy=pin((H - 1, W)), p=pin((H, W)),
+                vx_current=pin((H, W - 1)), vy_current=pin((H - 1, W)))
+    h2d = ax.nbytes + ay.nbytes
+    d2h = sum(a.nbytes for a in outs.values())
+    KE = max(2, min(K, 5))
+    sim.step_host(dt, vx_accum=ax, vy_accum=ay, **outs)
+    t0 = time.perf_counter()
+    for _ in range(KE):
+        sim.step_host(dt, vx_accum=ax, vy_accum=ay, **outs)
+    t_e2e = (time.perf_counter() - t0) / KE
+    e2e = N / t_e2e / 1e6
+
+    # ---- CPU baseline: the reference's own solver on this box's host cores ----
+    cpu = None
+    if not args.no_cpu_baseline:
+        sample = name if N <= 8192 * 8192 else "channel8192"
+        r = cpu_reference_run(sample, 2 if sample != "game" else 20, 1)
+        cpu = {"value": r["value"], "unit": "MLUP/s", "cores": r["cores"], "kind": r["kind"],
+               "sample": f"{sample}: {r['warmup']} warm-up + {r['steps']} timed Simulation::step "
+                         f"({r['ms_per_step']:.0f} ms/step), OMP threads {r['cores']} of {r['nproc']}, rbgs {r['rbgs_path']}"}
+
+    bpc = bytes_per_cell()
+    step_gbs = N * bpc / (ms_step * 1e-3) / 1e9
+    line = {
+        "metric": "fluid_step_throughput", "value": value, "unit": "MLUP/s", "n_gpus": 1, "steps": K,
+        "warmup": Wm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": name, "grid": [W, H], "vcycles_per_step": VCYCLES, "dt": dt,
+                   "l2": f"state {12 * N * 4 / 1e6:.0f} MB per step vs 126 MB L2"
+                         + (" (inputs larger than L2)" if N * 4 > 126e6 else " (L2 RESIDENT: latency bound, HBM % not meaningful)"),
+                   "residual_after": res_after, "fused": True},
+        "roofline": roof,
+        "roofline_step": {"bound": "hbm", "achieved": step_gbs, "peak": peak, "unit": "GB/s",
+                          "frac": step_gbs / peak, "bytes_per_cell": bpc,
+                          "model": "stage-wise algorithmic bytes 152 + 186.7*k B/cell (SURVEY.md 8d), k=2",
+                          "peak_source": peak_src},
+        "cpu_baseline": cpu,
+        "e2e": {"value": e2e, "unit": "MLUP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": t_e2e * 1e3, "api": "ubgl_sim_step_host (pinned host mirrors: accumulators in; vx, vy, p, vx_current, vy_current out)"},
+        "gpu_launches": int(launches),
+        "clocks": clk.summary(),
+        "kernels_ms_per_step": [{"kernel": k, "level": l, "launches": n, "ms": round(ms, 4)} for ms, n, k, l in kern[:12]],
+    }
+    print(json.dumps(line), flush=True)
+
+
+# algorithmic bytes per cell OF ITS LEVEL for each kernel kind (SURVEY.md 8d rule:
+# every distinct input array once, every output once, fp32)
+KERNEL_BYTES = {
+    "rbgs_half": 8.0,           # half of a 16 B/cell red+black sweep
+    "residual": 16.0, "restrict": 5.0, "prolong_correct": 22.0,
+    "mg_pre_fused": 3 * 16.0 + 16.0 + 5.0,          # 3 sweeps + residual + restrict
+    "mg_post_fused": 1.0 + 22.0 + 3 * 16.0,         # zero ec + prolong+correct + 3 sweeps
+    "diffuse": 12.0, "accum": 16.0, "advect": 10.0, "divergence": 12.0, "gradient": 24.0,
+    "prestep_fused": 32.0 + 48.0, "advect_div_fused": 20.0 + 12.0, "finish_fused": 24.0 + 16.0,
+}
+
+
+def dominant_roofline(kern, W, H, peak, peak_src, prof_ms_step):
+    if not kern:
+        return None
+    ms, n, k, l = kern[0]
+    cells = (W >> l) * (H >> l)
+    bpc = KERNEL_BYTES.get(k)
+    if bpc is None:
+        return {"bound": "hbm", "kernel": k, "level": l, "achieved": None, "peak": peak, "unit": "GB/s",
+                "frac": None, "traffic": None}
+    per_launch_ms = ms / max(n, 1)
+    units = 1.0 / n if k in ("mg_pre_fused", "mg_post_fused") else 1.0  # bytes above are per launch
+    bytes_launch = cells * bpc * (1.0 if k in ("mg_pre_fused", "mg_post_fused") else 1.0)
+    ach = bytes_launch / (per_launch_ms * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": k, "level": l, "launches_per_step": n,
+            "avg_launch_ms": per_launch_ms, "share_of_step": ms / prof_ms_step if prof_ms_step else None,
+            "algorithmic_bytes_per_launch": bytes_launch, "achieved": ach, "peak": peak, "unit": "GB/s",
+            "frac": ach / peak, "traffic": None, "peak_source": peak_src}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.gpus == 1:
+        return run_single_gpu(args, args.workload or "channel8192")
+    from ubootgl_b200 import slab_bench
+    return slab_bench.run(args, args.workload or "channel32768")
+
+
+if __name__ == "__main__":
+    main()

@@ -142,6 +142,15 @@ int ubgl_sim_stage_ms(ubgl_sim_t *sim, int stage, float *ms);
 long long ubgl_sim_launch_count(ubgl_sim_t *sim);
 /* the CUDA stream (cudaStream_t) the handle launches on */
 void *ubgl_sim_stream(ubgl_sim_t *sim);
+/* per-kernel profile: ubgl_sim_profile(sim, 1) clears the statistics and
+ * brackets every subsequent launch with CUDA events on the handle's stream
+ * (graph replay is bypassed while on); ubgl_sim_profile(sim, 0) stops.
+ * ubgl_sim_kernel_stats reads launches / summed device ms of one kernel kind at
+ * one MG level (level 0 for non-MG kernels). */
+int ubgl_sim_profile(ubgl_sim_t *sim, int on);
+int ubgl_num_kernel_kinds(void);
+const char *ubgl_kernel_kind_name(int kind);
+int ubgl_sim_kernel_stats(ubgl_sim_t *sim, int kind, int level, long long *count, double *ms);
 
 /* ---- class MG (pressure_solver.hpp:13-76) ---------------------------------- */
 /* MG(int w, int h): level pyramid by integer halving while w>3 && h>3, all

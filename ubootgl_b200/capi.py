@@ -64,6 +64,10 @@ def _load():
         "ubgl_sim_stage_ms": (i, [v, i, FP]),
         "ubgl_sim_launch_count": (ll, [v]),
         "ubgl_sim_stream": (v, [v]),
+        "ubgl_sim_profile": (i, [v, i]),
+        "ubgl_num_kernel_kinds": (i, []),
+        "ubgl_kernel_kind_name": (C.c_char_p, [i]),
+        "ubgl_sim_kernel_stats": (i, [v, i, i, C.POINTER(ll), C.POINTER(C.c_double)]),
         "ubgl_mg_create": (i, [i, i, i, VP]),
         "ubgl_mg_destroy": (i, [v]),
         "ubgl_mg_set_option": (i, [v, i, i]),
@@ -233,6 +237,20 @@ class Simulation:
 
     def launch_count(self):
         return lib.ubgl_sim_launch_count(self._h)
+
+    def profile(self, on):
+        _ck(lib.ubgl_sim_profile(self._h, int(on)))
+
+    def kernel_stats(self):
+        """{(kind_name, level): (launches, total_ms)} of the profiled region."""
+        out = {}
+        for k in range(lib.ubgl_num_kernel_kinds()):
+            for l in range(16):
+                n, ms = C.c_longlong(), C.c_double()
+                _ck(lib.ubgl_sim_kernel_stats(self._h, k, l, C.byref(n), C.byref(ms)))
+                if n.value:
+                    out[(lib.ubgl_kernel_kind_name(k).decode(), l)] = (n.value, ms.value)
+        return out
 
     def stream(self):
         return lib.ubgl_sim_stream(self._h)

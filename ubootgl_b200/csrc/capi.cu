@@ -9,6 +9,14 @@
 #include <vector>
 
 namespace ubgl {
+const char *kind_name(int k) {
+  static const char *names[K_COUNT] = {
+      "other", "fill", "accum", "diffuse", "vbc", "advect", "divergence", "sinks", "rbgs_half",
+      "zero_gradient_bc", "residual", "norm", "restrict", "prolong_correct", "coarsen_flag",
+      "pbc", "gradient", "prestep_fused", "advect_div_fused", "mg_pre_fused", "mg_post_fused",
+      "mg_coarse_fused", "finish_fused"};
+  return (k >= 0 && k < K_COUNT) ? names[k] : "?";
+}
 static thread_local std::string g_err;
 void set_error(const std::string &m) { g_err = m; }
 const char *get_error() { return g_err.c_str(); }
@@ -304,6 +312,31 @@ int ubgl_sim_stage_ms(ubgl_sim_t *sim, int stage, float *ms) {
 }
 
 long long ubgl_sim_launch_count(ubgl_sim_t *sim) { return sim ? sim->s->lc.n : -1; }
+
+int ubgl_sim_profile(ubgl_sim_t *sim, int on) {
+  UBGL_TRY
+  SIM(sim);
+  S.sync();
+  S.lc.collect();
+  if (on) S.lc.reset_stats();
+  S.lc.prof = on != 0;
+  UBGL_CATCH
+}
+
+int ubgl_num_kernel_kinds(void) { return K_COUNT; }
+const char *ubgl_kernel_kind_name(int kind) { return kind_name(kind); }
+
+int ubgl_sim_kernel_stats(ubgl_sim_t *sim, int kind, int level, long long *count, double *ms) {
+  UBGL_TRY
+  SIM(sim);
+  UBGL_REQUIRE(kind >= 0 && kind < K_COUNT && level >= 0 && level < LaunchCounter::MAXLVL,
+               "bad kind/level");
+  S.sync();
+  S.lc.collect();
+  if (count) *count = S.lc.cnt[kind][level];
+  if (ms) *ms = S.lc.ms[kind][level];
+  UBGL_CATCH
+}
 void *ubgl_sim_stream(ubgl_sim_t *sim) { return sim ? (void *)sim->s->stream : nullptr; }
 
 // ---- MG ---------------------------------------------------------------------

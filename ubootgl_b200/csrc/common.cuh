@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdint>
 #include <string>
+#include <vector>
 
 namespace ubgl {
 
@@ -49,9 +50,86 @@ struct ArgError {
     if (!(cond)) throw ::ubgl::ArgError{std::string(text)};                    \
   } while (0)
 
-// Counts kernel launches per handle ("gpu_launches" in bench.py).
-struct LaunchCounter {
-  long long n = 0;
+// Kernel kinds for the per-kernel profile (ubgl_sim_kernel_stats).
+enum Kind {
+  K_OTHER = 0, K_FILL, K_ACCUM, K_DIFFUSE, K_VBC, K_ADVECT, K_DIVERGENCE, K_SINKS, K_RBGS,
+  K_ZGBC, K_RESIDUAL, K_NORM, K_RESTRICT, K_PROLONG, K_COARSEN, K_PBC, K_GRADIENT,
+  K_PRESTEP /* fused accum+diffuse */, K_ADVDIV /* fused advect+BC+divergence */,
+  K_MG_PRE /* fused smooth+residual+restrict */, K_MG_POST /* fused prolong+correct+smooth */,
+  K_MG_COARSE /* all coarse levels in one kernel */, K_FINISH /* fused pBC+gradient+vBC+save */,
+  K_COUNT
 };
+const char *kind_name(int kind);
+
+// Counts kernel launches per handle ("gpu_launches" in bench.py) and, when
+// prof is on, brackets every launch with CUDA events on the launching stream so
+// that bench.py can report per-kernel device time (kind x MG level).
+struct LaunchCounter {
+  static const int MAXLVL = 16;
+  long long n = 0;
+  bool prof = false;
+  struct Rec {
+    cudaEvent_t a, b;
+    int kind, level;
+  };
+  std::vector<Rec> recs;
+  std::vector<cudaEvent_t> pool;
+  double ms[K_COUNT][MAXLVL] = {};
+  long long cnt[K_COUNT][MAXLVL] = {};
+
+  cudaEvent_t get_event() {
+    if (!pool.empty()) {
+      cudaEvent_t e = pool.back();
+      pool.pop_back();
+      return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+  }
+  void pre(int kind, int level, cudaStream_t s) {
+    n++;
+    if (!prof) return;
+    Rec r{get_event(), get_event(), kind, level < MAXLVL ? level : MAXLVL - 1};
+    cudaEventRecord(r.a, s);
+    recs.push_back(r);
+  }
+  void post(cudaStream_t s) {
+    if (prof) cudaEventRecord(recs.back().b, s);
+  }
+  // call after a stream synchronize
+  void collect() {
+    for (auto &r : recs) {
+      float t = 0.f;
+      if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) {
+        ms[r.kind][r.level] += t;
+        cnt[r.kind][r.level]++;
+      }
+      pool.push_back(r.a);
+      pool.push_back(r.b);
+    }
+    recs.clear();
+  }
+  void reset_stats() {
+    for (int k = 0; k < K_COUNT; k++)
+      for (int l = 0; l < MAXLVL; l++) ms[k][l] = 0.0, cnt[k][l] = 0;
+  }
+  ~LaunchCounter() {
+    for (auto &r : recs) {
+      cudaEventDestroy(r.a);
+      cudaEventDestroy(r.b);
+    }
+    for (auto e : pool) cudaEventDestroy(e);
+  }
+};
+
+// Every kernel launch in the library goes through this macro.
+#define UBGL_LAUNCH(lc, kind, level, stream, ...)                              \
+  do {                                                                         \
+    (lc)->pre((kind), (level), (stream));                                      \
+    __VA_ARGS__;                                                               \
+    UBGL_CHECK_LAUNCH();                                                       \
+    (lc)->post((stream));                                                      \
+  } while (0)
 
 } // namespace ubgl

@@ -5,6 +5,8 @@
 
 namespace ubgl {
 
+#define LVL cur_level
+
 // ---------------------------------------------------------------------------
 // grid helpers
 // ---------------------------------------------------------------------------
@@ -43,9 +45,8 @@ void fill_grid(const Grid &g, float v, cudaStream_t s, LaunchCounter *lc) {
   }
   int blocks = (int)((n + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  k_fill<<<blocks, 256, 0, s>>>(g.d, n, v);
-  UBGL_CHECK_LAUNCH();
-  if (lc) lc->n++;
+  LaunchCounter dummy;
+  UBGL_LAUNCH(lc ? lc : &dummy, K_FILL, 0, s, k_fill<<<blocks, 256, 0, s>>>(g.d, n, v));
 }
 
 // ---------------------------------------------------------------------------
@@ -252,9 +253,7 @@ void DeviceMG::update_fields(const Grid &flag0) {
                                 sizeof(float) * flag0.pitch, sizeof(float) * flag0.w, flag0.h,
                                 cudaMemcpyDeviceToDevice, stream));
   for (size_t l = 1; l < lv.size(); l++) {
-    k_coarsen_flag<<<grd2d(lv[l].w, lv[l].h), blk2d(), 0, stream>>>(lv[l - 1].flagc, lv[l].flagc);
-    UBGL_CHECK_LAUNCH();
-    lc->n++;
+    UBGL_LAUNCH(lc, K_COARSEN, LVL, stream, k_coarsen_flag<<<grd2d(lv[l].w, lv[l].h), blk2d(), 0, stream>>>(lv[l - 1].flagc, lv[l].flagc));
   }
 }
 
@@ -262,17 +261,13 @@ void DeviceMG::rbgs(const Grid &p, const Grid &f, const Grid &flag, float hh, fl
   dim3 b = blk2d();
   dim3 g(ceil_div((p.w - 2 + 1) / 2, b.x), ceil_div(p.h - 2, b.y));
   for (int color = 0; color < 2; color++) {
-    k_rbgs_half<<<g, b, 0, stream>>>(p, f, flag, hh, alpha, color);
-    UBGL_CHECK_LAUNCH();
-    lc->n++;
+    UBGL_LAUNCH(lc, K_RBGS, LVL, stream, k_rbgs_half<<<g, b, 0, stream>>>(p, f, flag, hh, alpha, color));
   }
 }
 
 void DeviceMG::zero_gradient_bc(const Grid &p) {
   int n = p.w > p.h ? p.w : p.h;
-  k_zero_gradient_bc<<<ceil_div(n, 256), 256, 0, stream>>>(p);
-  UBGL_CHECK_LAUNCH();
-  lc->n++;
+  UBGL_LAUNCH(lc, K_ZGBC, LVL, stream, k_zero_gradient_bc<<<ceil_div(n, 256), 256, 0, stream>>>(p));
 }
 
 void DeviceMG::residual(const Grid &p, const Grid &f, const Grid &flag, const Grid &r, float hh,
@@ -280,13 +275,9 @@ void DeviceMG::residual(const Grid &p, const Grid &f, const Grid &flag, const Gr
   dim3 g = grd2d(p.w, p.h);
   UBGL_REQUIRE(!want_norm || (int)(g.x * g.y) <= n_partials, "residual: grid larger than MG");
   float ihsq = 1.0f / hh / hh;
-  k_residual<<<g, blk2d(), 0, stream>>>(p, f, flag, r, ihsq, want_norm ? d_partials : nullptr);
-  UBGL_CHECK_LAUNCH();
-  lc->n++;
+  UBGL_LAUNCH(lc, K_RESIDUAL, LVL, stream, k_residual<<<g, blk2d(), 0, stream>>>(p, f, flag, r, ihsq, want_norm ? d_partials : nullptr));
   if (want_norm) {
-    k_finish_norm<<<1, 1024, 0, stream>>>(d_partials, g.x * g.y, d_norm);
-    UBGL_CHECK_LAUNCH();
-    lc->n++;
+    UBGL_LAUNCH(lc, K_NORM, LVL, stream, k_finish_norm<<<1, 1024, 0, stream>>>(d_partials, g.x * g.y, d_norm));
   }
 }
 
@@ -298,33 +289,26 @@ float DeviceMG::residual_norm_result() {
 }
 
 void DeviceMG::restrict_fw(const Grid &r, const Grid &rc) {
-  k_restrict<<<grd2d(rc.w, rc.h), blk2d(), 0, stream>>>(r, rc);
-  UBGL_CHECK_LAUNCH();
-  lc->n++;
+  UBGL_LAUNCH(lc, K_RESTRICT, LVL, stream, k_restrict<<<grd2d(rc.w, rc.h), blk2d(), 0, stream>>>(r, rc));
 }
 
 void DeviceMG::prolongate(const Grid &e, const Grid &ec, const Grid &flagc, const Grid &flag) {
-  k_prolongate<<<grd2d(e.w, e.h), blk2d(), 0, stream>>>(e, ec, flagc, flag);
-  UBGL_CHECK_LAUNCH();
-  lc->n++;
+  UBGL_LAUNCH(lc, K_PROLONG, LVL, stream, k_prolongate<<<grd2d(e.w, e.h), blk2d(), 0, stream>>>(e, ec, flagc, flag));
 }
 
 void DeviceMG::correct(const Grid &p, const Grid &e) {
-  k_correct<<<grd2d(p.w - 2, p.h - 2), blk2d(), 0, stream>>>(p, e);
-  UBGL_CHECK_LAUNCH();
-  lc->n++;
+  UBGL_LAUNCH(lc, K_PROLONG, LVL, stream, k_correct<<<grd2d(p.w - 2, p.h - 2), blk2d(), 0, stream>>>(p, e));
 }
 
 void DeviceMG::prolongate_correct(const Grid &p, const Grid &ec, const Grid &flagc,
                                   const Grid &flag) {
-  k_prolongate_correct<<<grd2d(p.w - 2, p.h - 2), blk2d(), 0, stream>>>(p, ec, flagc, flag);
-  UBGL_CHECK_LAUNCH();
-  lc->n++;
+  UBGL_LAUNCH(lc, K_PROLONG, LVL, stream, k_prolongate_correct<<<grd2d(p.w - 2, p.h - 2), blk2d(), 0, stream>>>(p, ec, flagc, flag));
 }
 
 void DeviceMG::solve(const Grid &p, const Grid &f, const Grid &flag, float hh, bool zgbc) {
   UBGL_REQUIRE(p.w == lv[0].w && p.h == lv[0].h, "solve: grid size mismatch");
   solve_level(p, f, flag, hh, 0, zgbc);
+  cur_level = 0;
 }
 
 // MG::solveLevel (pressure_solver.cpp:201-248), plain path: one kernel per
@@ -332,6 +316,7 @@ void DeviceMG::solve(const Grid &p, const Grid &f, const Grid &flag, float hh, b
 void DeviceMG::solve_level(const Grid &p, const Grid &f, const Grid &flag, float hh, int level,
                            bool zgbc) {
   const int nl = levels();
+  cur_level = level;
   if (level == nl - 2) {
     for (int i = 0; i < 5; i++) rbgs(p, f, flag, hh, 1.0f);
     return;
@@ -348,6 +333,7 @@ void DeviceMG::solve_level(const Grid &p, const Grid &f, const Grid &flag, float
   fill_grid(C.ec, 0.0f, stream, lc);
   float hc = hh * ((float)p.w - 1.0f) / ((float)C.w - 1.0f);
   solve_level(C.ec, C.rc, C.flagc, hc, level + 1, false);
+  cur_level = level;
   prolongate_correct(p, C.ec, C.flagc, flag);
   if (bc) zero_gradient_bc(p);
   for (int i = 0; i < 3; i++) {

@@ -42,6 +42,7 @@ public:
                           const Grid &flag);
 
   bool fused = true;
+  int cur_level = 0; // MG level the operator launches are attributed to (profile)
   int device;
   cudaStream_t stream;
   LaunchCounter *lc;

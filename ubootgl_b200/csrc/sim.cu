@@ -7,6 +7,8 @@
 
 namespace ubgl {
 
+#define LVL 0
+
 static inline dim3 blk2d() { return dim3(32, 8); }
 static inline dim3 grd2d(int w, int h) { return dim3(ceil_div(w, 32), ceil_div(h, 8)); }
 
@@ -354,34 +356,25 @@ void DeviceSim::update_flag(const float *host_flag) {
 void DeviceSim::sync() { UBGL_CUDA(cudaStreamSynchronize(stream)); }
 
 void DeviceSim::apply_accum() {
-  k_apply_accum<<<grd2d(W - 3, H - 2), blk2d(), 0, stream>>>(vx[vxf], vx_accum);
-  UBGL_CHECK_LAUNCH();
-  k_apply_accum<<<grd2d(W - 2, H - 3), blk2d(), 0, stream>>>(vy[vyf], vy_accum);
-  UBGL_CHECK_LAUNCH();
-  lc.n += 2;
+  UBGL_LAUNCH(&lc, K_ACCUM, LVL, stream, k_apply_accum<<<grd2d(W - 3, H - 2), blk2d(), 0, stream>>>(vx[vxf], vx_accum));
+  UBGL_LAUNCH(&lc, K_ACCUM, LVL, stream, k_apply_accum<<<grd2d(W - 2, H - 3), blk2d(), 0, stream>>>(vy[vyf], vy_accum));
 }
 
 void DeviceSim::set_vbcs() {
-  k_set_vbcs<<<1, 1024, 0, stream>>>(vx[vxf], vx[1 - vxf], vy[vyf], vy[1 - vyf], bcW, bcE, bcN,
-                                     bcS);
-  UBGL_CHECK_LAUNCH();
-  lc.n++;
+  UBGL_LAUNCH(&lc, K_VBC, LVL, stream, k_set_vbcs<<<1, 1024, 0, stream>>>(vx[vxf], vx[1 - vxf], vy[vyf], vy[1 - vyf], bcW, bcE, bcN,
+                                     bcS));
 }
 
 void DeviceSim::diffuse() {
   float a = dt * mu * ((float)W - 1.0f) / pwidth; // simulation.cpp:105
   float den = 1.0f + 4.0f * a;
   for (int i = 1; i < 3; i++) {
-    k_diffuse_vx<<<grd2d(W - 3, H - 2), blk2d(), 0, stream>>>(vx[vxf], vx[1 - vxf], flag, a, den);
-    UBGL_CHECK_LAUNCH();
-    lc.n++;
+    UBGL_LAUNCH(&lc, K_DIFFUSE, LVL, stream, k_diffuse_vx<<<grd2d(W - 3, H - 2), blk2d(), 0, stream>>>(vx[vxf], vx[1 - vxf], flag, a, den));
     vxf = 1 - vxf;
     set_vbcs();
   }
   for (int i = 1; i < 3; i++) {
-    k_diffuse_vy<<<grd2d(W - 2, H - 3), blk2d(), 0, stream>>>(vy[vyf], vy[1 - vyf], flag, a, den);
-    UBGL_CHECK_LAUNCH();
-    lc.n++;
+    UBGL_LAUNCH(&lc, K_DIFFUSE, LVL, stream, k_diffuse_vy<<<grd2d(W - 2, H - 3), blk2d(), 0, stream>>>(vy[vyf], vy[1 - vyf], flag, a, den));
     vyf = 1 - vyf;
     set_vbcs();
   }
@@ -392,20 +385,15 @@ void DeviceSim::advect() {
   float half = 0.5f * dt * ih, full = dt * ih; // simulation.cpp:276,286
   dim3 b(32, 8);
   dim3 g(ceil_div(W - 2, 32), ceil_div(H - 2, 8));
-  k_advect_vx<<<g, b, 0, stream>>>(vx[vxf], vy[vyf], vx[1 - vxf], flag, half, full);
-  UBGL_CHECK_LAUNCH();
-  k_advect_vy<<<g, b, 0, stream>>>(vx[vxf], vy[vyf], vy[1 - vyf], flag, H, half, full);
-  UBGL_CHECK_LAUNCH();
-  lc.n += 2;
+  UBGL_LAUNCH(&lc, K_ADVECT, LVL, stream, k_advect_vx<<<g, b, 0, stream>>>(vx[vxf], vy[vyf], vx[1 - vxf], flag, half, full));
+  UBGL_LAUNCH(&lc, K_ADVECT, LVL, stream, k_advect_vy<<<g, b, 0, stream>>>(vx[vxf], vy[vyf], vy[1 - vyf], flag, H, half, full));
   vxf = 1 - vxf;
   vyf = 1 - vyf;
 }
 
 void DeviceSim::project() {
   float ih = 1.0f / h;
-  k_divergence<<<grd2d(W - 2, H - 2), blk2d(), 0, stream>>>(vx[vxf], vy[vyf], f, ih);
-  UBGL_CHECK_LAUNCH();
-  lc.n++;
+  UBGL_LAUNCH(&lc, K_DIVERGENCE, LVL, stream, k_divergence<<<grd2d(W - 2, H - 2), blk2d(), 0, stream>>>(vx[vxf], vy[vyf], f, ih));
 
   // sinks (simulation.cpp:173-187): grid position, border skip, decay and erase
   // are host-side list work exactly as in the reference; only the 3x3 stamps
@@ -435,18 +423,13 @@ void DeviceSim::project() {
     UBGL_CUDA(cudaMemcpyAsync(d_sinks, stamps.data(), sizeof(float) * stamps.size(),
                               cudaMemcpyHostToDevice, stream));
     UBGL_CUDA(cudaStreamSynchronize(stream)); // stamps is a stack-lifetime staging buffer
-    k_stamp_sinks<<<1, 32, 0, stream>>>(f, d_sinks, n);
-    UBGL_CHECK_LAUNCH();
-    lc.n++;
+    UBGL_LAUNCH(&lc, K_SINKS, LVL, stream, k_stamp_sinks<<<1, 32, 0, stream>>>(f, d_sinks, n));
   }
 
   for (int c = 0; c < vcycles; c++) mg->solve(p, f, flag, h, true);
 
-  k_set_pbc<<<1, 1024, 0, stream>>>(p, bcW, bcE, bcN, bcS);
-  UBGL_CHECK_LAUNCH();
-  k_gradient<<<grd2d(W - 2, H - 2), blk2d(), 0, stream>>>(vx[vxf], vy[vyf], p, flag, ih);
-  UBGL_CHECK_LAUNCH();
-  lc.n += 2;
+  UBGL_LAUNCH(&lc, K_PBC, LVL, stream, k_set_pbc<<<1, 1024, 0, stream>>>(p, bcW, bcE, bcN, bcS));
+  UBGL_LAUNCH(&lc, K_GRADIENT, LVL, stream, k_gradient<<<grd2d(W - 2, H - 2), blk2d(), 0, stream>>>(vx[vxf], vy[vyf], p, flag, ih));
 }
 
 void DeviceSim::save_current() {
