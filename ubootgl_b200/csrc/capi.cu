@@ -233,7 +233,7 @@ int ubgl_sim_step_host(ubgl_sim_t *sim, float dt, const ubgl_host_mirrors *m) {
   if (m->flag) {
     Grid g = S.field(F_FLAG);
     upload_grid(g, m->flag, g.w, g.h, S.stream);
-    S.mg->update_fields(g);
+    S.flag_changed(true);
   }
   if (m->vx_accum) {
     Grid g = S.field(F_VX_ACCUM);
@@ -403,6 +403,7 @@ int ubgl_mg_update_fields(ubgl_mg_t *mg, const float *flag) {
   NEED(flag, "flag");
   upload_grid(M.flag, flag, M.W, M.H, M.stream);
   M.mg->update_fields(M.flag);
+  M.mg->invalidate_mask0();
   UBGL_CUDA(cudaStreamSynchronize(M.stream));
   UBGL_CATCH
 }
@@ -423,7 +424,10 @@ int ubgl_mg_upload(ubgl_mg_t *mg, const float *p, const float *f, const float *f
   MGH(mg);
   if (p) upload_grid(M.p, p, M.W, M.H, M.stream);
   if (f) upload_grid(M.f, f, M.W, M.H, M.stream);
-  if (flag) upload_grid(M.flag, flag, M.W, M.H, M.stream);
+  if (flag) {
+    upload_grid(M.flag, flag, M.W, M.H, M.stream);
+    M.mg->invalidate_mask0();
+  }
   UBGL_CUDA(cudaStreamSynchronize(M.stream));
   UBGL_CATCH
 }
@@ -455,6 +459,7 @@ int ubgl_mg_solve_host(ubgl_mg_t *mg, float *p, const float *f, const float *fla
   upload_grid(M.p, p, M.W, M.H, M.stream);
   upload_grid(M.f, f, M.W, M.H, M.stream);
   upload_grid(M.flag, flag, M.W, M.H, M.stream);
+  M.mg->invalidate_mask0();
   M.mg->solve(M.p, M.f, M.flag, h, zero_gradient_bc != 0);
   download_grid(M.p, p, M.W, M.H, M.stream);
   UBGL_CUDA(cudaStreamSynchronize(M.stream));

@@ -221,8 +221,15 @@ DeviceMG::DeviceMG(int W, int H, int device_, cudaStream_t stream_, LaunchCounte
     if (l >= 1 && l + 1 < lv.size()) { // level levels-1 is never visited (:203)
       L.rc = alloc_grid(L.w, L.h, L.pitch);
       L.ec = alloc_grid(L.w, L.h, L.pitch);
+      L.eb = alloc_grid(L.w, L.h, L.pitch);
+      UBGL_CUDA(cudaMalloc(&L.mask, (size_t)L.pitch * L.h));
     }
   }
+  UBGL_CUDA(cudaMalloc(&mask0, (size_t)lv[0].pitch * lv[0].h));
+  UBGL_CUDA(cudaMalloc(&d_nonbinary, sizeof(int)));
+  UBGL_CUDA(cudaMemset(d_nonbinary, 0, sizeof(int)));
+  for (size_t l = 1; l + 1 < lv.size(); l++) // all-ones coarse flags of MG(int,int)
+    launch_make_mask(lv[l].flagc, lv[l].mask, d_nonbinary, stream, lc, (int)l);
   dim3 g = grd2d(W, H);
   n_partials = g.x * g.y;
   UBGL_CUDA(cudaMalloc(&d_partials, sizeof(double) * n_partials));
@@ -236,7 +243,12 @@ DeviceMG::~DeviceMG() {
     free_grid(L.rc);
     free_grid(L.ec);
     free_grid(L.r);
+    free_grid(L.eb);
+    if (L.mask) cudaFree(L.mask);
   }
+  free_grid(scratch0);
+  if (mask0) cudaFree(mask0);
+  if (d_nonbinary) cudaFree(d_nonbinary);
   if (d_partials) cudaFree(d_partials);
   if (d_norm) cudaFree(d_norm);
 }
@@ -253,8 +265,26 @@ void DeviceMG::update_fields(const Grid &flag0) {
                                 sizeof(float) * flag0.pitch, sizeof(float) * flag0.w, flag0.h,
                                 cudaMemcpyDeviceToDevice, stream));
   for (size_t l = 1; l < lv.size(); l++) {
-    UBGL_LAUNCH(lc, K_COARSEN, LVL, stream, k_coarsen_flag<<<grd2d(lv[l].w, lv[l].h), blk2d(), 0, stream>>>(lv[l - 1].flagc, lv[l].flagc));
+    UBGL_LAUNCH(lc, K_COARSEN, (int)l, stream, k_coarsen_flag<<<grd2d(lv[l].w, lv[l].h), blk2d(), 0, stream>>>(lv[l - 1].flagc, lv[l].flagc));
+    if (l + 1 < lv.size())
+      launch_make_mask(lv[l].flagc, lv[l].mask, d_nonbinary, stream, lc, (int)l);
   }
+}
+
+// (Re)build the level-0 stencil mask from the flag grid the caller solves with.
+// Synchronises the stream (reads back the "non-binary flag seen" bit), so the
+// owners call it when the flag changes, not inside the step.
+void DeviceMG::prepare_mask0(const Grid &flag) {
+  if (mask0_src == flag.d) return;
+  UBGL_REQUIRE(flag.w == lv[0].w && flag.h == lv[0].h && flag.pitch == lv[0].pitch,
+               "flag grid does not match the MG level-0 layout");
+  UBGL_CUDA(cudaMemsetAsync(d_nonbinary, 0, sizeof(int), stream));
+  launch_make_mask(flag, mask0, d_nonbinary, stream, lc, 0);
+  int nb = 0;
+  UBGL_CUDA(cudaMemcpyAsync(&nb, d_nonbinary, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  UBGL_CUDA(cudaStreamSynchronize(stream));
+  mask0_binary = (nb == 0);
+  mask0_src = flag.d;
 }
 
 void DeviceMG::rbgs(const Grid &p, const Grid &f, const Grid &flag, float hh, float alpha) {
@@ -307,8 +337,41 @@ void DeviceMG::prolongate_correct(const Grid &p, const Grid &ec, const Grid &fla
 
 void DeviceMG::solve(const Grid &p, const Grid &f, const Grid &flag, float hh, bool zgbc) {
   UBGL_REQUIRE(p.w == lv[0].w && p.h == lv[0].h, "solve: grid size mismatch");
+  if (fused && levels() >= 3 && p.pitch == lv[0].pitch && f.pitch == lv[0].pitch) {
+    prepare_mask0(flag);
+    if (mask0_binary) {
+      solve_fused(p, f, flag, hh, zgbc);
+      return;
+    }
+  }
   solve_level(p, f, flag, hh, 0, zgbc);
   cur_level = 0;
+}
+
+// MG::solveLevel (pressure_solver.cpp:201-248) with the temporally blocked tile
+// kernels of mg_fused.cu: per level one PRE pass (3 sweeps + residual +
+// restriction) on the way down, one 5-sweep pass on the coarsest used level
+// (levels-2), one POST pass (prolongation + correction + 3 sweeps) on the way up.
+void DeviceMG::solve_fused(const Grid &p, const Grid &f, const Grid &flag, float hh0, bool zgbc) {
+  (void)flag;
+  const int L = levels() - 2;
+  if (!scratch0.d) scratch0 = alloc_grid(lv[0].w, lv[0].h, lv[0].pitch);
+  std::vector<float> hh(L + 1);
+  hh[0] = hh0;
+  for (int l = 0; l < L; l++) // :229
+    hh[l + 1] = hh[l] * ((float)lv[l].w - 1.0f) / ((float)lv[l + 1].w - 1.0f);
+  for (int l = 0; l < L; l++) {
+    const Grid &fl = (l == 0) ? f : lv[l].rc;
+    launch_mg_pre(l == 0 ? p.d : nullptr, l == 0 ? scratch0.d : lv[l].eb.d, fl,
+                  l == 0 ? mask0 : lv[l].mask, lv[l + 1].rc, hh[l], zgbc && l == 0, stream, lc, l);
+  }
+  launch_mg_smooth5(lv[L].ec.d, lv[L].rc, lv[L].mask, hh[L], stream, lc, L);
+  for (int l = L - 1; l >= 0; l--) {
+    const Grid &fl = (l == 0) ? f : lv[l].rc;
+    launch_mg_post(l == 0 ? scratch0.d : lv[l].eb.d, l == 0 ? p.d : lv[l].ec.d, fl,
+                   l == 0 ? mask0 : lv[l].mask, lv[l + 1].ec, lv[l + 1].flagc, hh[l],
+                   zgbc && l == 0, stream, lc, l);
+  }
 }
 
 // MG::solveLevel (pressure_solver.cpp:201-248), plain path: one kernel per

@@ -12,6 +12,8 @@ struct MGLevel {
   Grid rc;    // rcs[l]     restricted residual = rhs of this level (l >= 1)
   Grid ec;    // ecs[l]     error / solution of this level            (l >= 1)
   Grid r;     // rs[l]      residual scratch, only materialised by the plain path
+  Grid eb;    // ping-pong partner of ec for the fused tile kernels (l >= 1)
+  uint8_t *mask = nullptr; // 5-bit stencil mask of flagc (pitch bytes per row), l >= 1
 };
 
 class DeviceMG {
@@ -41,6 +43,11 @@ public:
   void prolongate_correct(const Grid &p, const Grid &ec, const Grid &flagc,
                           const Grid &flag);
 
+  // The fused path needs binary flags; level 0 uses the caller's flag grid
+  // (pressure_solver.hpp:59-62), whose mask is rebuilt when it changes.
+  void invalidate_mask0() { mask0_src = nullptr; }
+  void prepare_mask0(const Grid &flag);
+
   bool fused = true;
   int cur_level = 0; // MG level the operator launches are attributed to (profile)
   int device;
@@ -51,11 +58,29 @@ private:
   void solve_level(const Grid &p, const Grid &f, const Grid &flag, float hh,
                    int level, bool zgbc);
   void ensure_r(int level);
+  void solve_fused(const Grid &p, const Grid &f, const Grid &flag, float hh, bool zgbc);
+  uint8_t *mask0 = nullptr;        // stencil mask of the level-0 flag
+  const float *mask0_src = nullptr; // flag buffer mask0 was built from
+  bool mask0_binary = false;
+  Grid scratch0;                   // level-0 ping-pong partner of the caller's p
+  int *d_nonbinary = nullptr;
   std::vector<MGLevel> lv;
   double *d_partials = nullptr; // per-block partial sums of r^2
   double *d_norm = nullptr;
   int n_partials = 0;
 };
+
+// mg_fused.cu
+void launch_mg_pre(const float *p_in, float *p_out, const Grid &f, const uint8_t *mask,
+                   const Grid &rc, float hh, bool zgbc, cudaStream_t stream, LaunchCounter *lc,
+                   int level);
+void launch_mg_post(const float *p_in, float *p_out, const Grid &f, const uint8_t *mask,
+                    const Grid &ec, const Grid &flagc, float hh, bool zgbc, cudaStream_t stream,
+                    LaunchCounter *lc, int level);
+void launch_mg_smooth5(float *p_out, const Grid &f, const uint8_t *mask, float hh,
+                       cudaStream_t stream, LaunchCounter *lc, int level);
+void launch_make_mask(const Grid &flag, uint8_t *mask, int *d_nonbinary, cudaStream_t stream,
+                      LaunchCounter *lc, int level);
 
 Grid alloc_grid(int w, int h, int pitch_floats, bool zero = true);
 void free_grid(Grid &g);

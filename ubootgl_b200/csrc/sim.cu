@@ -287,6 +287,7 @@ DeviceSim::DeviceSim(const float *host_flag, int W_, int H_, float pwidth_, floa
     UBGL_CUDA(cudaStreamSynchronize(stream));
   }
   mg->update_fields(flag);
+  mg->prepare_mask0(flag);
   UBGL_CUDA(cudaStreamSynchronize(stream));
 }
 
@@ -337,6 +338,16 @@ void DeviceSim::upload(int id, const float *host) {
   Grid g = field(id);
   upload_grid(g, host, g.w, g.h, stream);
   UBGL_CUDA(cudaStreamSynchronize(stream)); // host buffer is only borrowed for the call
+  if (id == F_FLAG) flag_changed(false);
+}
+
+// The level-0 flag changed: refresh what is derived from it.  `pyramid` also
+// rebuilds the coarse flags (MG::updateFields); a bare write to sim.flag does
+// not, exactly as in the reference (simulation.hpp:85 vs ubootgl_app.cpp:111-112).
+void DeviceSim::flag_changed(bool pyramid) {
+  if (pyramid) mg->update_fields(flag);
+  mg->invalidate_mask0();
+  mg->prepare_mask0(flag);
 }
 
 void DeviceSim::download(int id, float *host) {
@@ -349,7 +360,7 @@ void DeviceSim::download(int id, float *host) {
 void DeviceSim::update_flag(const float *host_flag) {
   UBGL_REQUIRE(host_flag != nullptr, "update_flag: null host pointer");
   upload_grid(flag, host_flag, W, H, stream);
-  mg->update_fields(flag);
+  flag_changed(true);
   UBGL_CUDA(cudaStreamSynchronize(stream));
 }
 

@@ -28,6 +28,7 @@ public:
   void upload(int id, const float *host);
   void download(int id, float *host);
   void update_flag(const float *host_flag);
+  void flag_changed(bool pyramid);
 
   void stage(int st, float dt);
   void step(float dt);
