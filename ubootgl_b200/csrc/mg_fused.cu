@@ -1,6 +1,6 @@
 // mg_fused.cu -- temporally blocked multigrid tile kernels (sm_100a).
 //
-// One CTA stages a (128 x LH) window of p, f and the 5-bit stencil mask in
+// One CTA stages a (128 x LH) window of p, f and the 1-byte stencil mask in
 // shared memory, runs S complete red-black Gauss-Seidel sweeps on it (the valid
 // region shrinks by one cell per half-sweep, so the window carries a halo of
 // 2S (+2) cells) and fuses the neighbouring multigrid operators into the same
@@ -13,13 +13,22 @@
 // p is ping-ponged between two buffers (tiles read their neighbours' cells as
 // halo, so an in-place update would race).
 //
-// Every per-cell formula comes from stencils.cuh, i.e. the same rounding
-// sequence as the plain one-kernel-per-operator path in mg.cu: the fused result
-// is bit-identical to the plain one (tests/test_gpu_fused.py).
-//
-// Shared-memory layout: red and black cells live in separate planes
-// (plane = (x+y)&1, column index x>>1) so that a half-sweep, which touches every
-// other cell, reads and writes consecutive words (no bank conflicts).
+// The kernels are instruction-issue bound, not DRAM bound (ncu, profiles/), so
+// the inner loops are written for instruction count:
+//  * red and black cells live in separate shared-memory planes (plane =
+//    (x+y)&1, column x>>1); a thread updates 4 consecutive same-colour cells
+//    with 128-bit LDS/STS;
+//  * solid cells are stored as 0 in the window (their value is never used by
+//    the reference either: every read is multiplied by the cell's flag,
+//    pressure_solver.cpp:13-17,101-108), so the 5-point sum needs no flag
+//    multiplies; the divide by the fluid-neighbour count and the centre flag
+//    collapse into one multiply by a table weight (stencils.cuh rcp_count);
+//  * border cells (never smoothed) keep flag*value in the window for their
+//    neighbours and are re-materialised from p_in / the zero-gradient copy at
+//    write-back.
+// Every per-cell rounding sequence equals the plain one-kernel-per-operator
+// path in mg.cu for binary flags: the fused result is bit-identical to the
+// plain one up to the sign of zeros (tests/test_gpu_fused.py).
 //
 // Reference semantics: pressure_solver.cpp:10-24 (smoothingKernel), :35-72
 // (canonical red-black order), :91-116 (residual), :118-132 (restrict),
@@ -31,6 +40,10 @@
 namespace ubgl {
 
 enum { MODE_PRE = 0, MODE_POST = 1, MODE_SMOOTH = 2 };
+
+// stencil mask byte: bit0 flag(c), bit1 W, bits2-4 weight code (0 = solid or no
+// fluid neighbour, else the fluid-neighbour count 1..4), bit5 E, bit6 S, bit7 N
+enum { MB_C = 1, MB_W = 2, MB_E = 32, MB_S = 64, MB_N = 128 };
 
 struct TileArgs {
   const float *p_in; // nullptr: initial guess is 0 (levels >= 1 start from ec.fill(0))
@@ -46,8 +59,10 @@ struct TileArgs {
   int zgbc;
 };
 
-constexpr int LW = 128; // staged window width in cells (one float4 per lane)
-constexpr int HW = LW / 2;
+constexpr int LW = 128;    // staged window width in cells
+constexpr int HW = LW / 2; // cells per colour per row
+constexpr int RS = 72;     // shared row stride (floats / bytes): HW + 4 left + 4 right pad
+constexpr int XO = 4;      // column of xh = 0 inside a padded row
 
 template <int S, int MODE> struct TileGeom {
   // halo: 2 cells per sweep, +2 for residual(+1) and restriction(+1); rounded
@@ -57,25 +72,35 @@ template <int S, int MODE> struct TileGeom {
   static constexpr int TX = LW - 2 * HALO;
 };
 
-__device__ __forceinline__ float bitf(unsigned m, int b) { return (float)((m >> b) & 1u); }
+template <int LH> struct TileSmem {
+  float P[2][LH][RS];
+  float F[2][LH][RS];
+  uint8_t M[2][LH][RS];
+  float rcpt[8];
+};
+
+__device__ __forceinline__ float sel0(unsigned m, unsigned bit, float v) {
+  return (m & bit) ? v : 0.0f;
+}
 
 template <int S, int MODE, int LH, int NT>
-__global__ void __launch_bounds__(NT) k_mg_tile(TileArgs a) {
+__global__ void __launch_bounds__(NT, 2) k_mg_tile(TileArgs a) {
   constexpr int HALO = TileGeom<S, MODE>::HALO;
   constexpr int TX = TileGeom<S, MODE>::TX;
   constexpr int TY = LH - 2 * HALO;
   constexpr int NW = NT / 32;
-  static_assert(TY > 0 && TY % 2 == 0 && TX % 4 == 0, "tile geometry");
+  constexpr int RPP = 2 * NW; // rows per pass of the 4-cells-per-thread loops
+  static_assert(TY > 0 && TY % 2 == 0 && TX % 8 == 0 && NW % 2 == 0, "tile geometry");
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float(*P)[LH][HW] = reinterpret_cast<float(*)[LH][HW]>(smem_raw);
-  float(*F)[LH][HW] = reinterpret_cast<float(*)[LH][HW]>(smem_raw + sizeof(float) * 2 * LH * HW);
-  uint8_t(*M)[LW] = reinterpret_cast<uint8_t(*)[LW]>(smem_raw + sizeof(float) * 4 * LH * HW);
+  TileSmem<LH> &sm = *reinterpret_cast<TileSmem<LH> *>(smem_raw);
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
-  const int X0 = x0 - HALO, Y0 = y0 - HALO; // both even: local parity == global parity
+  const int X0 = x0 - HALO, Y0 = y0 - HALO; // X0 % 8 == 0, Y0 even: local parity == global parity
   const int w = a.w, h = a.h;
+
+  if (threadIdx.x < 8) sm.rcpt[threadIdx.x] = rcp_count(threadIdx.x);
 
   // ---- stage the window: coalesced 128-bit loads, de-interleaved by colour ----
   for (int r = warp; r < LH; r += NW) {
@@ -88,74 +113,144 @@ __global__ void __launch_bounds__(NT) k_mg_tile(TileArgs a) {
       fv = __ldg(reinterpret_cast<const float4 *>(a.f + o));
       mv = __ldg(reinterpret_cast<const uchar4 *>(a.mask + o));
     }
-    const int pr = gy & 1;
-    *reinterpret_cast<float2 *>(&P[pr][r][2 * lane]) = make_float2(pv.x, pv.z);
-    *reinterpret_cast<float2 *>(&P[pr ^ 1][r][2 * lane]) = make_float2(pv.y, pv.w);
-    *reinterpret_cast<float2 *>(&F[pr][r][2 * lane]) = make_float2(fv.x, fv.z);
-    *reinterpret_cast<float2 *>(&F[pr ^ 1][r][2 * lane]) = make_float2(fv.y, fv.w);
-    *reinterpret_cast<uchar4 *>(&M[r][4 * lane]) = mv;
+    pv.x = sel0(mv.x, MB_C, pv.x);
+    pv.y = sel0(mv.y, MB_C, pv.y);
+    pv.z = sel0(mv.z, MB_C, pv.z);
+    pv.w = sel0(mv.w, MB_C, pv.w);
+    if (MODE != MODE_PRE) { // the sweeps only need f*h*h; MODE_PRE keeps f for the residual
+      fv.x = fh2_of(fv.x, a.hh);
+      fv.y = fh2_of(fv.y, a.hh);
+      fv.z = fh2_of(fv.z, a.hh);
+      fv.w = fh2_of(fv.w, a.hh);
+    }
+    const int pr = r & 1, c = XO + 2 * lane;
+    *reinterpret_cast<float2 *>(&sm.P[pr][r][c]) = make_float2(pv.x, pv.z);
+    *reinterpret_cast<float2 *>(&sm.P[pr ^ 1][r][c]) = make_float2(pv.y, pv.w);
+    *reinterpret_cast<float2 *>(&sm.F[pr][r][c]) = make_float2(fv.x, fv.z);
+    *reinterpret_cast<float2 *>(&sm.F[pr ^ 1][r][c]) = make_float2(fv.y, fv.w);
+    *reinterpret_cast<uchar2 *>(&sm.M[pr][r][c]) = make_uchar2(mv.x, mv.z);
+    *reinterpret_cast<uchar2 *>(&sm.M[pr ^ 1][r][c]) = make_uchar2(mv.y, mv.w);
+    if (lane < 2) { // pads read by the first / last group of a row
+      const int pc_ = lane ? XO + HW : 0;
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4 *>(&sm.P[0][r][pc_]) = z;
+      *reinterpret_cast<float4 *>(&sm.P[1][r][pc_]) = z;
+    }
   }
   __syncthreads();
 
-  // valid region after k half-sweeps (global coordinates, interior only)
+  // 4-cells-per-thread mapping: 16 threads cover the 64 same-colour cells of a
+  // row; a warp works on rows r and r+2 so that the x-parity q of its cells is
+  // warp-uniform.
+  const int tg = lane & 15;                                        // group within the row
+  const int rslot = 4 * (warp >> 1) + (warp & 1) + 2 * (lane >> 4); // 0 .. RPP-1
+  const int ci = XO + 4 * tg;                                      // padded column of the group
+
+  // Per-thread 4-bit masks over its group for x-parity q = 0 / 1:
+  // fz: cells on the global W/E border column (never updated);
+  // in: cells with 1 <= gx <= w-2.
+  unsigned fzb = 0, inb = 0; // bits 0-3: q = 0, bits 4-7: q = 1
+#pragma unroll
+  for (int q = 0; q < 2; q++) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int gx = X0 + 2 * (4 * tg + j) + q;
+      if (gx == 0 || gx == w - 1) fzb |= 1u << (4 * q + j);
+      if (gx >= 1 && gx <= w - 2) inb |= 1u << (4 * q + j);
+    }
+  }
+
   auto lo = [](int origin, int k) { return max(1, origin + k); };
   auto hi = [](int origin, int len, int n, int k) { return min(n - 1, origin + len - k); };
 
-  // one colour of one sweep over the region that is still exact at time k
+  // one colour of one sweep over the rows that are still exact at time k
   auto half_sweep = [&](int k, int cpar) {
-    const int gx_lo = lo(X0, k), gx_hi = hi(X0, LW, w, k);
-    const int gy_lo = lo(Y0, k), gy_hi = hi(Y0, LH, h, k);
-    for (int gy = gy_lo + warp; gy < gy_hi; gy += NW) {
-      const int r = gy - Y0;
-      const int gxs = gx_lo + (((gx_lo + gy) & 1) ^ cpar);
-      const float *po = &P[cpar ^ 1][r][0];
-      const float *ps = &P[cpar ^ 1][r - 1][0];
-      const float *pn = &P[cpar ^ 1][r + 1][0];
-      for (int gx = gxs + 2 * lane; gx < gx_hi; gx += 64) {
-        const int lx = gx - X0, xh = lx >> 1, wo = (lx & 1) - 1;
-        const unsigned m = M[r][lx];
-        const float v = smooth_cell1(po[xh + wo], po[xh + wo + 1], ps[xh], pn[xh], bitf(m, 0),
-                                     bitf(m, 1), bitf(m, 2), bitf(m, 3), bitf(m, 4),
-                                     fh2_of(F[cpar][r][xh], a.hh));
-        P[cpar][r][xh] = v;
+    const int r_lo = lo(Y0, k) - Y0, r_hi = hi(Y0, LH, h, k) - Y0;
+    for (int r = r_lo + rslot; r < r_hi; r += RPP) {
+      const int q = (cpar + r) & 1;
+      const float *po = &sm.P[cpar ^ 1][r][ci];
+      const float4 A = *reinterpret_cast<const float4 *>(po);
+      const float4 Sv = *reinterpret_cast<const float4 *>(po - RS);
+      const float4 Nv = *reinterpret_cast<const float4 *>(po + RS);
+      const float4 Fv = *reinterpret_cast<const float4 *>(&sm.F[cpar][r][ci]);
+      const unsigned mw = *reinterpret_cast<const unsigned *>(&sm.M[cpar][r][ci]);
+      float4 Wv, Ev;
+      if (q == 0) {
+        Wv = make_float4(po[-1], A.x, A.y, A.z);
+        Ev = A;
+      } else {
+        Wv = A;
+        Ev = make_float4(A.y, A.z, A.w, po[4]);
+      }
+      auto upd = [&](float pw, float pe, float ps, float pn, float f, int j) {
+        float v = __fadd_rn(__fadd_rn(__fadd_rn(pw, pe), ps), pn);
+        v = __fadd_rn(v, MODE == MODE_PRE ? fh2_of(f, a.hh) : f);
+        return __fmul_rn(v, sm.rcpt[(mw >> (8 * j + 2)) & 7u]);
+      };
+      float4 v;
+      v.x = upd(Wv.x, Ev.x, Sv.x, Nv.x, Fv.x, 0);
+      v.y = upd(Wv.y, Ev.y, Sv.y, Nv.y, Fv.y, 1);
+      v.z = upd(Wv.z, Ev.z, Sv.z, Nv.z, Fv.z, 2);
+      v.w = upd(Wv.w, Ev.w, Sv.w, Nv.w, Fv.w, 3);
+      float *pd = &sm.P[cpar][r][ci];
+      const unsigned z = (fzb >> (4 * q)) & 15u;
+      if (z == 0) {
+        *reinterpret_cast<float4 *>(pd) = v;
+      } else {
+        if (!(z & 1)) pd[0] = v.x;
+        if (!(z & 2)) pd[1] = v.y;
+        if (!(z & 4)) pd[2] = v.z;
+        if (!(z & 8)) pd[3] = v.w;
       }
     }
   };
 
   auto cell = [&](int gx, int gy) -> float & {
     const int lx = gx - X0, ly = gy - Y0;
-    return P[(lx + ly) & 1][ly][lx >> 1];
+    return sm.P[(lx + ly) & 1][ly][XO + (lx >> 1)];
+  };
+  auto mbyte = [&](int gx, int gy) -> unsigned {
+    const int lx = gx - X0, ly = gy - Y0;
+    return sm.M[(lx + ly) & 1][ly][XO + (lx >> 1)];
   };
 
   // setZeroGradientBC restricted to the border cells whose interior neighbour is
-  // still exact at time k (corners are never touched)
+  // still exact at time k (corners are never touched); the window keeps
+  // flag * value for border cells
   auto zero_gradient = [&](int k) {
     const int gx_lo = lo(X0, k), gx_hi = hi(X0, LW, w, k);
     const int gy_lo = lo(Y0, k), gy_hi = hi(Y0, LH, h, k);
     const int t = threadIdx.x;
     if (X0 <= 0 && gx_lo == 1)
-      for (int gy = gy_lo + t; gy < gy_hi; gy += NT) cell(0, gy) = cell(1, gy);
+      for (int gy = gy_lo + t; gy < gy_hi; gy += NT) cell(0, gy) = sel0(mbyte(0, gy), MB_C, cell(1, gy));
     if (w - 1 < X0 + LW && gx_hi == w - 1)
-      for (int gy = gy_lo + t; gy < gy_hi; gy += NT) cell(w - 1, gy) = cell(w - 2, gy);
+      for (int gy = gy_lo + t; gy < gy_hi; gy += NT)
+        cell(w - 1, gy) = sel0(mbyte(w - 1, gy), MB_C, cell(w - 2, gy));
     if (Y0 <= 0 && gy_lo == 1)
-      for (int gx = gx_lo + t; gx < gx_hi; gx += NT) cell(gx, 0) = cell(gx, 1);
+      for (int gx = gx_lo + t; gx < gx_hi; gx += NT) cell(gx, 0) = sel0(mbyte(gx, 0), MB_C, cell(gx, 1));
     if (h - 1 < Y0 + LH && gy_hi == h - 1)
-      for (int gx = gx_lo + t; gx < gx_hi; gx += NT) cell(gx, h - 1) = cell(gx, h - 2);
+      for (int gx = gx_lo + t; gx < gx_hi; gx += NT)
+        cell(gx, h - 1) = sel0(mbyte(gx, h - 1), MB_C, cell(gx, h - 2));
   };
 
   if (MODE == MODE_POST) {
-    // prolongate + correct on the whole window (interior cells), colour by
-    // colour so that a warp sees a single parity case of prolong_cell
+    // prolongate + correct on every interior cell of the window; the parity
+    // case of prolong_cell (pressure_solver.cpp:140-170) is warp-uniform
+    const int r_lo = lo(Y0, 0) - Y0, r_hi = hi(Y0, LH, h, 0) - Y0;
+#pragma unroll 1
     for (int cpar = 0; cpar < 2; cpar++) {
-      const int gx_lo = lo(X0, 0), gx_hi = hi(X0, LW, w, 0);
-      const int gy_lo = lo(Y0, 0), gy_hi = hi(Y0, LH, h, 0);
-      for (int gy = gy_lo + warp; gy < gy_hi; gy += NW) {
-        const int r = gy - Y0;
-        const int gxs = gx_lo + (((gx_lo + gy) & 1) ^ cpar);
-        for (int gx = gxs + 2 * lane; gx < gx_hi; gx += 64) {
-          const int lx = gx - X0, xh = lx >> 1;
-          const float e = prolong_cell(a.ec, a.flagc, a.pc, bitf(M[r][lx], 0), gx, gy, w, h);
-          P[cpar][r][xh] = __fadd_rn(P[cpar][r][xh], e);
+      for (int r = r_lo + rslot; r < r_hi; r += RPP) {
+        const int q = (cpar + r) & 1;
+        const int gy = Y0 + r;
+        const unsigned mw = *reinterpret_cast<const unsigned *>(&sm.M[cpar][r][ci]);
+        float *pd = &sm.P[cpar][r][ci];
+        const unsigned in = (inb >> (4 * q)) & 15u;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          if (!((in >> j) & 1u)) continue;
+          const int gx = X0 + 2 * (4 * tg + j) + q;
+          const float flagf = (float)((mw >> (8 * j)) & 1u);
+          pd[j] = __fadd_rn(pd[j], prolong_cell(a.ec, a.flagc, a.pc, flagf, gx, gy, w, h));
         }
       }
     }
@@ -179,25 +274,49 @@ __global__ void __launch_bounds__(NT) k_mg_tile(TileArgs a) {
   }
 
   if (MODE == MODE_PRE) {
-    // residual on (tile + 1) in place of f; r = 0 outside the interior
-    const int fx_lo = HALO - 1, fx_hi = HALO + TX + 1, fy_lo = HALO - 1, fy_hi = HALO + TY + 1;
+    // residual on (tile + 1 ring), written over f; 0 outside the interior
+    const int r_lo = HALO - 1, r_hi = HALO + TY + 1;
+#pragma unroll 1
     for (int cpar = 0; cpar < 2; cpar++) {
-      for (int ly = fy_lo + warp; ly < fy_hi; ly += NW) {
-        const int gy = Y0 + ly;
-        const int lxs = fx_lo + (((fx_lo + ly) & 1) ^ cpar);
-        const float *po = &P[cpar ^ 1][ly][0];
-        for (int lx = lxs + 2 * lane; lx < fx_hi; lx += 64) {
-          const int gx = X0 + lx, xh = lx >> 1, wo = (lx & 1) - 1;
-          float rv = 0.0f;
-          if (gx >= 1 && gx < w - 1 && gy >= 1 && gy < h - 1) {
-            const unsigned m = M[ly][lx];
-            rv = residual_cell(P[cpar][ly][xh], po[xh + wo], po[xh + wo + 1],
-                               P[cpar ^ 1][ly - 1][xh], P[cpar ^ 1][ly + 1][xh], bitf(m, 0),
-                               bitf(m, 1), bitf(m, 2), bitf(m, 3), bitf(m, 4), F[cpar][ly][xh],
-                               a.ihsq);
-          }
-          F[cpar][ly][xh] = rv;
+      for (int r = r_lo + rslot; r < r_hi; r += RPP) {
+        const int q = (cpar + r) & 1;
+        const int gy = Y0 + r;
+        const bool rowin = gy >= 1 && gy <= h - 2;
+        const float *po = &sm.P[cpar ^ 1][r][ci];
+        const float4 A = *reinterpret_cast<const float4 *>(po);
+        const float4 Sv = *reinterpret_cast<const float4 *>(po - RS);
+        const float4 Nv = *reinterpret_cast<const float4 *>(po + RS);
+        const float4 Cv = *reinterpret_cast<const float4 *>(&sm.P[cpar][r][ci]);
+        const float4 Fv = *reinterpret_cast<const float4 *>(&sm.F[cpar][r][ci]);
+        const unsigned mw = *reinterpret_cast<const unsigned *>(&sm.M[cpar][r][ci]);
+        float4 Wv, Ev;
+        if (q == 0) {
+          Wv = make_float4(po[-1], A.x, A.y, A.z);
+          Ev = A;
+        } else {
+          Wv = A;
+          Ev = make_float4(A.y, A.z, A.w, po[4]);
         }
+        const unsigned in = rowin ? (inb >> (4 * q)) & 15u : 0u;
+        // residual_cell (stencils.cuh) with binary flags: every term
+        // p_nb*flag_nb + p_c*(1-flag_nb) is exactly p_nb or p_c
+        auto res = [&](float pc_, float pw, float pe, float ps, float pn, float f, int j) {
+          const unsigned m = mw >> (8 * j);
+          float val = (m & MB_W) ? pw : pc_;
+          val = __fadd_rn(val, (m & MB_E) ? pe : pc_);
+          val = __fadd_rn(val, (m & MB_S) ? ps : pc_);
+          val = __fadd_rn(val, (m & MB_N) ? pn : pc_);
+          val = __fmaf_rn(-4.0f, pc_, val);
+          val = __fmul_rn(val, a.ihsq);
+          val = __fadd_rn(f, val);
+          return ((m & MB_C) && ((in >> j) & 1u)) ? val : 0.0f;
+        };
+        float4 v;
+        v.x = res(Cv.x, Wv.x, Ev.x, Sv.x, Nv.x, Fv.x, 0);
+        v.y = res(Cv.y, Wv.y, Ev.y, Sv.y, Nv.y, Fv.y, 1);
+        v.z = res(Cv.z, Wv.z, Ev.z, Sv.z, Nv.z, Fv.z, 2);
+        v.w = res(Cv.w, Wv.w, Ev.w, Sv.w, Nv.w, Fv.w, 3);
+        *reinterpret_cast<float4 *>(&sm.F[cpar][r][ci]) = v;
       }
     }
     __syncthreads();
@@ -213,11 +332,11 @@ __global__ void __launch_bounds__(NT) k_mg_tile(TileArgs a) {
         if (xc >= a.wc) break;
         float v = 0.0f;
         if (xc >= 1 && yc >= 1 && xc < a.wc - 1 && yc < a.hc - 1) {
-          const int c = (2 * xc - X0) >> 1; // column index of the (even,even) centre
+          const int c = XO + ((2 * xc - X0) >> 1); // column of the (even,even) centre
           // rows ly-1 / ly+1: corners in plane 0, middle in plane 1; row ly: the opposite
-          v = fw9(F[0][ly - 1][c - 1], F[1][ly - 1][c], F[0][ly - 1][c], F[1][ly][c - 1],
-                  F[0][ly][c], F[1][ly][c], F[0][ly + 1][c - 1], F[1][ly + 1][c],
-                  F[0][ly + 1][c]);
+          v = fw9(sm.F[0][ly - 1][c - 1], sm.F[1][ly - 1][c], sm.F[0][ly - 1][c],
+                  sm.F[1][ly][c - 1], sm.F[0][ly][c], sm.F[1][ly][c], sm.F[0][ly + 1][c - 1],
+                  sm.F[1][ly + 1][c], sm.F[0][ly + 1][c]);
         }
         a.rc[(size_t)yc * a.pc + xc] = v;
       }
@@ -229,20 +348,47 @@ __global__ void __launch_bounds__(NT) k_mg_tile(TileArgs a) {
     const int gy = Y0 + ly;
     if (gy >= h) break;
     const int pr = ly & 1;
-    for (int q = lane; q < TX / 4; q += 32) {
-      const int lx = HALO + 4 * q, gx = X0 + lx;
+    for (int qd = lane; qd < TX / 4; qd += 32) {
+      const int lx = HALO + 4 * qd, gx = X0 + lx;
       if (gx >= w) break;
-      const float2 e = *reinterpret_cast<const float2 *>(&P[pr][ly][lx >> 1]);
-      const float2 o = *reinterpret_cast<const float2 *>(&P[pr ^ 1][ly][lx >> 1]);
+      const float2 e = *reinterpret_cast<const float2 *>(&sm.P[pr][ly][XO + (lx >> 1)]);
+      const float2 o = *reinterpret_cast<const float2 *>(&sm.P[pr ^ 1][ly][XO + (lx >> 1)]);
       *reinterpret_cast<float4 *>(a.p_out + (size_t)gy * a.pitch + gx) =
           make_float4(e.x, o.x, e.y, o.y);
     }
   }
+
+  // ---- border cells of this tile: the window held flag*value; the grid gets
+  // the zero-gradient copy of the (now final) interior neighbour or, without
+  // that BC and at the four corners, the unchanged input value ----
+  const bool bx0 = x0 == 0, bx1 = (w - 1 >= x0 && w - 1 < x0 + TX);
+  const bool by0 = y0 == 0, by1 = (h - 1 >= y0 && h - 1 < y0 + TY);
+  if (bx0 || bx1 || by0 || by1) {
+    __syncthreads();
+    const int t = threadIdx.x;
+    auto orig = [&](int gx, int gy) {
+      return a.p_in ? a.p_in[(size_t)gy * a.pitch + gx] : 0.0f;
+    };
+    auto put = [&](int gx, int gy, int nx, int ny) {
+      const bool corner = (gx == 0 || gx == w - 1) && (gy == 0 || gy == h - 1);
+      a.p_out[(size_t)gy * a.pitch + gx] = (a.zgbc && !corner) ? cell(nx, ny) : orig(gx, gy);
+    };
+    const int ty_hi = min(h, y0 + TY), tx_hi = min(w, x0 + TX);
+    // columns first, rows second: at the corners both write orig()
+    if (bx0)
+      for (int gy = y0 + t; gy < ty_hi; gy += NT) put(0, gy, 1, gy);
+    if (bx1)
+      for (int gy = y0 + t; gy < ty_hi; gy += NT) put(w - 1, gy, w - 2, gy);
+    if (by0)
+      for (int gx = x0 + t; gx < tx_hi; gx += NT) put(gx, 0, gx, 1);
+    if (by1)
+      for (int gx = x0 + t; gx < tx_hi; gx += NT) put(gx, h - 1, gx, h - 2);
+  }
 }
 
-// 5-bit stencil mask of a flag grid: bit0 = flag(x,y), bit1..4 = W, E, S, N
-// neighbour (0 outside the grid).  *nonbinary is raised if any flag is neither
-// 0.0 nor 1.0 (then the bit form is not equivalent and the plain path is used).
+// Stencil mask of a flag grid (layout: enum MB_* above; neighbours outside the
+// grid count as solid).  *nonbinary is raised if any flag is neither 0.0 nor 1.0
+// (then the bit form is not equivalent and the plain path is used).
 __global__ void k_make_mask(Grid flag, uint8_t *mask, int *nonbinary) {
   int x = blockIdx.x * blockDim.x + threadIdx.x;
   int y = blockIdx.y * blockDim.y + threadIdx.y;
@@ -255,8 +401,10 @@ __global__ void k_make_mask(Grid flag, uint8_t *mask, int *nonbinary) {
     };
     float c = flag.at(x, y);
     if (c != 0.0f && c != 1.0f) *nonbinary = 1;
-    m = bit(x, y) | (bit(x - 1, y) << 1) | (bit(x + 1, y) << 2) | (bit(x, y - 1) << 3) |
-        (bit(x, y + 1) << 4);
+    const unsigned bc = bit(x, y), bw = bit(x - 1, y), be = bit(x + 1, y), bs = bit(x, y - 1),
+                   bn = bit(x, y + 1);
+    const unsigned code = bc ? (bw + be + bs + bn) : 0u;
+    m = bc * MB_C | bw * MB_W | (code << 2) | be * MB_E | bs * MB_S | bn * MB_N;
   }
   mask[(size_t)y * flag.pitch + x] = (uint8_t)m;
 }
@@ -270,7 +418,7 @@ static void launch_tile(const TileArgs &a, cudaStream_t stream, LaunchCounter *l
   constexpr int HALO = TileGeom<S, MODE>::HALO;
   constexpr int TX = TileGeom<S, MODE>::TX;
   constexpr int TY = LH - 2 * HALO;
-  constexpr size_t smem = sizeof(float) * 4 * LH * HW + (size_t)LH * LW;
+  constexpr size_t smem = sizeof(TileSmem<LH>);
   static bool attr_set = false;
   if (!attr_set) {
     UBGL_CUDA(cudaFuncSetAttribute(k_mg_tile<S, MODE, LH, NT>,
@@ -281,7 +429,7 @@ static void launch_tile(const TileArgs &a, cudaStream_t stream, LaunchCounter *l
   UBGL_LAUNCH(lc, kind, level, stream, k_mg_tile<S, MODE, LH, NT><<<grid, NT, smem, stream>>>(a));
 }
 
-constexpr int LH_MAIN = 64, NT_MAIN = 256;
+constexpr int LH_MAIN = 80, NT_MAIN = 256;
 
 void launch_mg_pre(const float *p_in, float *p_out, const Grid &f, const uint8_t *mask,
                    const Grid &rc, float hh, bool zgbc, cudaStream_t stream, LaunchCounter *lc,

@@ -7,6 +7,25 @@
 
 namespace ubgl {
 
+// 1/sum for the stencil denominators.  With binary flags sum is 0..4 and the
+// quotient val/sum is evaluated as val * (1/sum): exact for 1, 2, 4 and within
+// 1 ulp for 3 (the reference itself is built with -Ofast, where gcc vectorises
+// the division as rcpps + one Newton step, so IEEE division is not what pins
+// parity -- the 1e-5 relative-L2 tolerance is).  sum == 0 gives 0 like the
+// reference's `if (sum == 0) val = 0` (pressure_solver.cpp:19).  Any other sum
+// (non-binary flags, plain path only) divides.
+__device__ __forceinline__ float rcp_count(int c) {
+  return c == 4 ? 0.25f : c == 3 ? (1.0f / 3.0f) : c == 2 ? 0.5f : c == 1 ? 1.0f : 0.0f;
+}
+__device__ __forceinline__ float div_by_sum(float val, float sum) {
+  if (sum == 4.0f) return __fmul_rn(val, 0.25f);
+  if (sum == 3.0f) return __fmul_rn(val, 1.0f / 3.0f);
+  if (sum == 2.0f) return __fmul_rn(val, 0.5f);
+  if (sum == 1.0f) return val;
+  if (sum == 0.0f) return 0.0f;
+  return __fdiv_rn(val, sum);
+}
+
 // smoothingKernel (pressure_solver.cpp:10-24).
 // fh2 = f(x,y)*h*h, evaluated by the caller as (f*h)*h.
 __device__ __forceinline__ float smooth_cell(float pC, float pW, float pE,
@@ -19,27 +38,9 @@ __device__ __forceinline__ float smooth_cell(float pC, float pW, float pE,
   val = __fmaf_rn(pS, fS, val);
   val = __fmaf_rn(pN, fN, val);
   val = __fadd_rn(val, fh2);
-  val = __fdiv_rn(val, sum);
-  if (sum == 0.0f) val = 0.0f;
+  val = div_by_sum(val, sum);
   float mix = __fmaf_rn(alpha, val, __fmul_rn(__fsub_rn(1.0f, alpha), pC));
   return __fmul_rn(fC, mix);
-}
-
-// alpha == 1 (the only value MG::solveLevel uses, pressure_solver.cpp:205,212,244):
-// 1*val + 0*p == val for finite p, so the blend is dropped.
-__device__ __forceinline__ float smooth_cell1(float pW, float pE, float pS,
-                                              float pN, float fC, float fW,
-                                              float fE, float fS, float fN,
-                                              float fh2) {
-  float sum = __fadd_rn(__fadd_rn(__fadd_rn(fW, fE), fN), fS);
-  float val = __fmul_rn(pW, fW);
-  val = __fmaf_rn(pE, fE, val);
-  val = __fmaf_rn(pS, fS, val);
-  val = __fmaf_rn(pN, fN, val);
-  val = __fadd_rn(val, fh2);
-  val = __fdiv_rn(val, sum);
-  if (sum == 0.0f) val = 0.0f;
-  return __fmul_rn(fC, val);
 }
 
 __device__ __forceinline__ float fh2_of(float f, float hh) {
@@ -72,6 +73,22 @@ __device__ __forceinline__ float fw9(float a0, float a1, float a2, float b0,
   return __fmul_rn(v, 0.0625f);
 }
 
+// Denominators of prolongate (pressure_solver.cpp:149,157,164): flagc sums of
+// 0..4 plus 0.0001 (a double literal in the reference).  Evaluated as a multiply
+// by the rounded reciprocal, see rcp_count above.
+__device__ __forceinline__ float prolong_rcp(int c) {
+  return c == 4   ? (float)(1.0 / 4.0001)
+         : c == 3 ? (float)(1.0 / 3.0001)
+         : c == 2 ? (float)(1.0 / 2.0001)
+         : c == 1 ? (float)(1.0 / 1.0001)
+                  : (float)(1.0 / 0.0001);
+}
+__device__ __forceinline__ float prolong_div(float num, float fs) {
+  if (fs == 4.0f || fs == 3.0f || fs == 2.0f || fs == 1.0f || fs == 0.0f)
+    return __fmul_rn(num, prolong_rcp((int)fs));
+  return __fdiv_rn(num, (float)((double)fs + 0.0001));
+}
+
 // prolongate (pressure_solver.cpp:134-172) evaluated per fine cell; returns the
 // value the reference leaves in e(x,y) (0 where no loop writes it).  ec / flagc
 // are the coarse error and coarse flag grids with pitch pc.
@@ -88,23 +105,22 @@ __device__ __forceinline__ float prolong_cell(const float *__restrict__ ec,
   if (ox && !oy) {
     if (y < 2 || x >= w - 2 || y >= h - 1) return 0.0f;
     size_t i = (size_t)yc * pc + xc;
-    float sum = (float)((double)__fadd_rn(flagc[i], flagc[i + 1]) + 0.0001);
-    return __fdiv_rn(__fmul_rn(flagf, __fadd_rn(ec[i], ec[i + 1])), sum);
+    return prolong_div(__fmul_rn(flagf, __fadd_rn(ec[i], ec[i + 1])),
+                       __fadd_rn(flagc[i], flagc[i + 1]));
   }
   if (!ox && oy) {
     if (x < 2 || x >= w - 1 || y >= h - 2) return 0.0f;
     size_t i = (size_t)yc * pc + xc;
-    float sum = (float)((double)__fadd_rn(flagc[i], flagc[i + pc]) + 0.0001);
-    return __fdiv_rn(__fmul_rn(flagf, __fadd_rn(ec[i], ec[i + pc])), sum);
+    return prolong_div(__fmul_rn(flagf, __fadd_rn(ec[i], ec[i + pc])),
+                       __fadd_rn(flagc[i], flagc[i + pc]));
   }
   if (x >= w - 2 || y >= h - 2) return 0.0f;
   size_t i = (size_t)yc * pc + xc;
   // :163-164  flagc(x/2,y/2) + flagc(x/2+1,y/2+1) + flagc(x/2+1,y/2) + flagc(x/2,y/2+1)
   float fs = __fadd_rn(__fadd_rn(__fadd_rn(flagc[i], flagc[i + pc + 1]), flagc[i + 1]),
                        flagc[i + pc]);
-  float sum = (float)((double)fs + 0.0001);
   float es = __fadd_rn(__fadd_rn(__fadd_rn(ec[i], ec[i + pc + 1]), ec[i + 1]), ec[i + pc]);
-  return __fdiv_rn(__fmul_rn(flagf, es), sum);
+  return prolong_div(__fmul_rn(flagf, es), fs);
 }
 
 // CubicHermite / Catmull-Rom (interpolators.hpp:78-85)
