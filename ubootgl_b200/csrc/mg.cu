@@ -369,7 +369,7 @@ void DeviceMG::solve_fused(const Grid &p, const Grid &f, const Grid &flag, float
   for (int l = L - 1; l >= 0; l--) {
     const Grid &fl = (l == 0) ? f : lv[l].rc;
     launch_mg_post(l == 0 ? scratch0.d : lv[l].eb.d, l == 0 ? p.d : lv[l].ec.d, fl,
-                   l == 0 ? mask0 : lv[l].mask, lv[l + 1].ec, lv[l + 1].flagc, hh[l],
+                   l == 0 ? mask0 : lv[l].mask, lv[l + 1].ec, lv[l + 1].mask, hh[l],
                    zgbc && l == 0, stream, lc, l);
   }
 }

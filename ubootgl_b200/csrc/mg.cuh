@@ -75,7 +75,7 @@ void launch_mg_pre(const float *p_in, float *p_out, const Grid &f, const uint8_t
                    const Grid &rc, float hh, bool zgbc, cudaStream_t stream, LaunchCounter *lc,
                    int level);
 void launch_mg_post(const float *p_in, float *p_out, const Grid &f, const uint8_t *mask,
-                    const Grid &ec, const Grid &flagc, float hh, bool zgbc, cudaStream_t stream,
+                    const Grid &ec, const uint8_t *maskc, float hh, bool zgbc, cudaStream_t stream,
                     LaunchCounter *lc, int level);
 void launch_mg_smooth5(float *p_out, const Grid &f, const uint8_t *mask, float hh,
                        cudaStream_t stream, LaunchCounter *lc, int level);

@@ -53,7 +53,7 @@ struct TileArgs {
   int w, h, pitch;
   float *rc;          // MODE_PRE: restricted residual (coarse grid)
   const float *ec;    // MODE_POST: coarse error
-  const float *flagc; // MODE_POST: coarse flags (fp32, as the reference sums them)
+  const uint8_t *maskc; // MODE_POST: stencil mask of the coarse level (coarse flag sums)
   int wc, hc, pc;
   float hh, ihsq;
   int zgbc;
@@ -234,23 +234,55 @@ __global__ void __launch_bounds__(NT, 2) k_mg_tile(TileArgs a) {
   };
 
   if (MODE == MODE_POST) {
-    // prolongate + correct on every interior cell of the window; the parity
-    // case of prolong_cell (pressure_solver.cpp:140-170) is warp-uniform
-    const int r_lo = lo(Y0, 0) - Y0, r_hi = hi(Y0, LH, h, 0) - Y0;
-#pragma unroll 1
-    for (int cpar = 0; cpar < 2; cpar++) {
-      for (int r = r_lo + rslot; r < r_hi; r += RPP) {
-        const int q = (cpar + r) & 1;
-        const int gy = Y0 + r;
-        const unsigned mw = *reinterpret_cast<const unsigned *>(&sm.M[cpar][r][ci]);
-        float *pd = &sm.P[cpar][r][ci];
-        const unsigned in = (inb >> (4 * q)) & 15u;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          if (!((in >> j) & 1u)) continue;
-          const int gx = X0 + 2 * (4 * tg + j) + q;
-          const float flagf = (float)((mw >> (8 * j)) & 1u);
-          pd[j] = __fadd_rn(pd[j], prolong_cell(a.ec, a.flagc, a.pc, flagf, gx, gy, w, h));
+    // prolongate + correct (pressure_solver.cpp:134-181) on every cell of the
+    // window: one thread per COARSE cell (xc,yc) updates its four fine cells
+    // (2xc,2yc) (2xc+1,2yc) (2xc,2yc+1) (2xc+1,2yc+1); same rounding sequence
+    // as prolong_cell (stencils.cuh), the coarse flag sums come from the coarse
+    // level's stencil mask (C, E, N bits of cell i and the E bit of the cell
+    // above it).
+    const int xcb = X0 >> 1, ycb = Y0 >> 1;
+    for (int j = warp; j < LH / 2; j += NW) {
+      const int yc = ycb + j, y = 2 * yc;
+      if (yc < 0 || yc >= a.hc) continue;
+      const bool y_e = y >= 2 && y <= h - 2; // rows of the even-y loops (:140,:146)
+      const bool y_o = y + 1 <= h - 3;       // rows of the odd-y loops  (:153,:161)
+      const float *ecr = a.ec + (size_t)yc * a.pc;
+      const uint8_t *mcr = a.maskc + (size_t)yc * a.pc;
+      for (int k = lane; k < HW; k += 32) {
+        const int xc = xcb + k, x = 2 * xc;
+        if (xc < 0 || xc >= a.wc) continue;
+        const bool x_e = x >= 2 && x <= w - 2, x_o = x + 1 <= w - 3;
+        const float e00 = __ldg(ecr + xc);
+        const float e10 = x_o ? __ldg(ecr + xc + 1) : 0.0f;
+        const float e01 = y_o ? __ldg(ecr + a.pc + xc) : 0.0f;
+        const float e11 = (x_o && y_o) ? __ldg(ecr + a.pc + xc + 1) : 0.0f;
+        const unsigned mc = __ldg(mcr + xc);
+        const unsigned mn = y_o ? __ldg(mcr + a.pc + xc) : 0u;
+        const int fC = mc & 1, fE = (mc >> 5) & 1, fN = (mc >> 7) & 1, fNE = (mn >> 5) & 1;
+        const int c = XO + k;
+        if (y_e) {
+          if (x_e) {
+            const float e = sel0(sm.M[0][2 * j][c], MB_C, e00);
+            sm.P[0][2 * j][c] = __fadd_rn(sm.P[0][2 * j][c], e);
+          }
+          if (x_o) {
+            const float e = __fmul_rn(sel0(sm.M[1][2 * j][c], MB_C, __fadd_rn(e00, e10)),
+                                      prolong_rcp(fC + fE));
+            sm.P[1][2 * j][c] = __fadd_rn(sm.P[1][2 * j][c], e);
+          }
+        }
+        if (y_o) {
+          if (x_e) {
+            const float e = __fmul_rn(sel0(sm.M[1][2 * j + 1][c], MB_C, __fadd_rn(e00, e01)),
+                                      prolong_rcp(fC + fN));
+            sm.P[1][2 * j + 1][c] = __fadd_rn(sm.P[1][2 * j + 1][c], e);
+          }
+          if (x_o) {
+            const float es = __fadd_rn(__fadd_rn(__fadd_rn(e00, e11), e10), e01);
+            const float e = __fmul_rn(sel0(sm.M[0][2 * j + 1][c], MB_C, es),
+                                      prolong_rcp(fC + fNE + fE + fN));
+            sm.P[0][2 * j + 1][c] = __fadd_rn(sm.P[0][2 * j + 1][c], e);
+          }
         }
       }
     }
@@ -443,12 +475,12 @@ void launch_mg_pre(const float *p_in, float *p_out, const Grid &f, const uint8_t
 }
 
 void launch_mg_post(const float *p_in, float *p_out, const Grid &f, const uint8_t *mask,
-                    const Grid &ec, const Grid &flagc, float hh, bool zgbc, cudaStream_t stream,
+                    const Grid &ec, const uint8_t *maskc, float hh, bool zgbc, cudaStream_t stream,
                     LaunchCounter *lc, int level) {
   TileArgs a{};
   a.p_in = p_in; a.p_out = p_out; a.f = f.d; a.mask = mask;
   a.w = f.w; a.h = f.h; a.pitch = f.pitch;
-  a.ec = ec.d; a.flagc = flagc.d; a.wc = ec.w; a.hc = ec.h; a.pc = ec.pitch;
+  a.ec = ec.d; a.maskc = maskc; a.wc = ec.w; a.hc = ec.h; a.pc = ec.pitch;
   a.hh = hh; a.ihsq = 1.0f / hh / hh; a.zgbc = zgbc ? 1 : 0;
   launch_tile<3, MODE_POST, LH_MAIN, NT_MAIN>(a, stream, lc, K_MG_POST, level);
 }
