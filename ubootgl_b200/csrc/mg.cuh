@@ -47,6 +47,8 @@ public:
   // (pressure_solver.hpp:59-62), whose mask is rebuilt when it changes.
   void invalidate_mask0() { mask0_src = nullptr; }
   void prepare_mask0(const Grid &flag);
+  const uint8_t *mask0_ptr() const { return mask0; }
+  bool mask0_is_binary() const { return mask0_src != nullptr && mask0_binary; }
 
   bool fused = true;
   int cur_level = 0; // MG level the operator launches are attributed to (profile)

@@ -4,6 +4,7 @@
 #include "stencils.cuh"
 #include <cmath>
 #include <cstring>
+#include <utility>
 
 namespace ubgl {
 
@@ -27,7 +28,7 @@ __global__ void k_apply_accum(Grid v, Grid acc) {
 }
 
 // diffuse, x-velocity pass (simulation.cpp:113-129)
-__global__ void k_diffuse_vx(Grid src, Grid dst, Grid flag, float a, float den) {
+__global__ void k_diffuse_vx(Grid src, Grid dst, Grid flag, float a, float rden) {
   int x = 1 + blockIdx.x * blockDim.x + threadIdx.x;
   int y = 1 + blockIdx.y * blockDim.y + threadIdx.y;
   if (x >= src.w - 1 || y >= src.h - 1) return;
@@ -40,11 +41,11 @@ __global__ void k_diffuse_vx(Grid src, Grid dst, Grid flag, float a, float den) 
   float fvs = __fmul_rn(fl[-fp], fl[-fp - 1]);
   float mC = __fmul_rn(fl[0], fl[1]);
   dst.d[(size_t)y * dst.pitch + x] =
-      diffuse_cell(v[0], v[1], mE, v[-1], mW, v[vp], fvn, v[-vp], fvs, mC, a, den);
+      diffuse_cell(v[0], v[1], mE, v[-1], mW, v[vp], fvn, v[-vp], fvs, mC, a, rden);
 }
 
 // diffuse, y-velocity pass (simulation.cpp:139-155)
-__global__ void k_diffuse_vy(Grid src, Grid dst, Grid flag, float a, float den) {
+__global__ void k_diffuse_vy(Grid src, Grid dst, Grid flag, float a, float rden) {
   int x = 1 + blockIdx.x * blockDim.x + threadIdx.x;
   int y = 1 + blockIdx.y * blockDim.y + threadIdx.y;
   if (x >= src.w - 1 || y >= src.h - 1) return;
@@ -57,7 +58,7 @@ __global__ void k_diffuse_vy(Grid src, Grid dst, Grid flag, float a, float den) 
   float fvw = __fmul_rn(fl[-1], fl[fp - 1]);
   float mC = __fmul_rn(fl[0], fl[fp]);
   dst.d[(size_t)y * dst.pitch + x] =
-      diffuse_cell(v[0], v[-vp], mS, v[vp], mN, v[1], fve, v[-1], fvw, mC, a, den);
+      diffuse_cell(v[0], v[-vp], mS, v[vp], mN, v[1], fve, v[-1], fvw, mC, a, rden);
 }
 
 // setVBCs (simulation.cpp:80-102): column loops, then row loops (the row loops
@@ -263,14 +264,12 @@ DeviceSim::DeviceSim(const float *host_flag, int W_, int H_, float pwidth_, floa
   UBGL_CUDA(cudaSetDevice(device));
   UBGL_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
   pitch = round_up(W, 32);
-  for (int b = 0; b < 2; b++) {
-    vx[b] = alloc_grid(W - 1, H, pitch);
-    vy[b] = alloc_grid(W, H - 1, pitch);
+  for (int b = 0; b < 3; b++) {
+    vxb[b] = alloc_grid(W - 1, H, pitch);
+    vyb[b] = alloc_grid(W, H - 1, pitch);
   }
   vx_accum = alloc_grid(W - 1, H, pitch);
   vy_accum = alloc_grid(W, H - 1, pitch);
-  vx_current = alloc_grid(W - 1, H, pitch);
-  vy_current = alloc_grid(W, H - 1, pitch);
   p = alloc_grid(W, H, pitch);
   f = alloc_grid(W, H, pitch);
   flag = alloc_grid(W, H, pitch);
@@ -282,7 +281,7 @@ DeviceSim::DeviceSim(const float *host_flag, int W_, int H_, float pwidth_, floa
   {
     std::vector<float> col(H, 1.0f); // vx.f(0,y) = vx.b(0,y) = 1 (:58-60)
     for (int b = 0; b < 2; b++)
-      UBGL_CUDA(cudaMemcpy2DAsync(vx[b].d, sizeof(float) * pitch, col.data(), sizeof(float),
+      UBGL_CUDA(cudaMemcpy2DAsync(vxb[b].d, sizeof(float) * pitch, col.data(), sizeof(float),
                                   sizeof(float), H, cudaMemcpyHostToDevice, stream));
     UBGL_CUDA(cudaStreamSynchronize(stream));
   }
@@ -295,11 +294,11 @@ DeviceSim::~DeviceSim() {
   cudaSetDevice(device);
   if (stream) cudaStreamSynchronize(stream);
   mg.reset();
-  for (int b = 0; b < 2; b++) {
-    free_grid(vx[b]);
-    free_grid(vy[b]);
+  for (int b = 0; b < 3; b++) {
+    free_grid(vxb[b]);
+    free_grid(vyb[b]);
   }
-  free_grid(vx_accum); free_grid(vy_accum); free_grid(vx_current); free_grid(vy_current);
+  free_grid(vx_accum); free_grid(vy_accum);
   free_grid(p); free_grid(f); free_grid(flag); free_grid(r);
   if (d_sinks) cudaFree(d_sinks);
   if (stream) cudaStreamDestroy(stream);
@@ -308,10 +307,10 @@ DeviceSim::~DeviceSim() {
 Grid DeviceSim::field(int id) {
   switch (id) {
   case F_FLAG: return flag;
-  case F_VX: return vx[vxf];
-  case F_VY: return vy[vyf];
-  case F_VXB: return vx[1 - vxf];
-  case F_VYB: return vy[1 - vyf];
+  case F_VX: return vxb[ixf];
+  case F_VY: return vyb[iyf];
+  case F_VXB: return vxb[ixb];
+  case F_VYB: return vyb[iyb];
   case F_P: return p;
   case F_F: return f;
   case F_VX_ACCUM: return vx_accum;
@@ -319,8 +318,8 @@ Grid DeviceSim::field(int id) {
   case F_R:
     if (!r.d) r = alloc_grid(W, H, pitch);
     return r;
-  case F_VX_CURRENT: return vx_current;
-  case F_VY_CURRENT: return vy_current;
+  case F_VX_CURRENT: return vxb[ixc];
+  case F_VY_CURRENT: return vyb[iyc];
   }
   throw ArgError{"unknown field id"};
 }
@@ -367,26 +366,26 @@ void DeviceSim::update_flag(const float *host_flag) {
 void DeviceSim::sync() { UBGL_CUDA(cudaStreamSynchronize(stream)); }
 
 void DeviceSim::apply_accum() {
-  UBGL_LAUNCH(&lc, K_ACCUM, LVL, stream, k_apply_accum<<<grd2d(W - 3, H - 2), blk2d(), 0, stream>>>(vx[vxf], vx_accum));
-  UBGL_LAUNCH(&lc, K_ACCUM, LVL, stream, k_apply_accum<<<grd2d(W - 2, H - 3), blk2d(), 0, stream>>>(vy[vyf], vy_accum));
+  UBGL_LAUNCH(&lc, K_ACCUM, LVL, stream, k_apply_accum<<<grd2d(W - 3, H - 2), blk2d(), 0, stream>>>(vxb[ixf], vx_accum));
+  UBGL_LAUNCH(&lc, K_ACCUM, LVL, stream, k_apply_accum<<<grd2d(W - 2, H - 3), blk2d(), 0, stream>>>(vyb[iyf], vy_accum));
 }
 
 void DeviceSim::set_vbcs() {
-  UBGL_LAUNCH(&lc, K_VBC, LVL, stream, k_set_vbcs<<<1, 1024, 0, stream>>>(vx[vxf], vx[1 - vxf], vy[vyf], vy[1 - vyf], bcW, bcE, bcN,
+  UBGL_LAUNCH(&lc, K_VBC, LVL, stream, k_set_vbcs<<<1, 1024, 0, stream>>>(vxb[ixf], vxb[ixb], vyb[iyf], vyb[iyb], bcW, bcE, bcN,
                                      bcS));
 }
 
 void DeviceSim::diffuse() {
   float a = dt * mu * ((float)W - 1.0f) / pwidth; // simulation.cpp:105
-  float den = 1.0f + 4.0f * a;
+  float rden = 1.0f / (1.0f + 4.0f * a);
   for (int i = 1; i < 3; i++) {
-    UBGL_LAUNCH(&lc, K_DIFFUSE, LVL, stream, k_diffuse_vx<<<grd2d(W - 3, H - 2), blk2d(), 0, stream>>>(vx[vxf], vx[1 - vxf], flag, a, den));
-    vxf = 1 - vxf;
+    UBGL_LAUNCH(&lc, K_DIFFUSE, LVL, stream, k_diffuse_vx<<<grd2d(W - 3, H - 2), blk2d(), 0, stream>>>(vxb[ixf], vxb[ixb], flag, a, rden));
+    std::swap(ixf, ixb);
     set_vbcs();
   }
   for (int i = 1; i < 3; i++) {
-    UBGL_LAUNCH(&lc, K_DIFFUSE, LVL, stream, k_diffuse_vy<<<grd2d(W - 2, H - 3), blk2d(), 0, stream>>>(vy[vyf], vy[1 - vyf], flag, a, den));
-    vyf = 1 - vyf;
+    UBGL_LAUNCH(&lc, K_DIFFUSE, LVL, stream, k_diffuse_vy<<<grd2d(W - 2, H - 3), blk2d(), 0, stream>>>(vyb[iyf], vyb[iyb], flag, a, rden));
+    std::swap(iyf, iyb);
     set_vbcs();
   }
 }
@@ -396,16 +395,23 @@ void DeviceSim::advect() {
   float half = 0.5f * dt * ih, full = dt * ih; // simulation.cpp:276,286
   dim3 b(32, 8);
   dim3 g(ceil_div(W - 2, 32), ceil_div(H - 2, 8));
-  UBGL_LAUNCH(&lc, K_ADVECT, LVL, stream, k_advect_vx<<<g, b, 0, stream>>>(vx[vxf], vy[vyf], vx[1 - vxf], flag, half, full));
-  UBGL_LAUNCH(&lc, K_ADVECT, LVL, stream, k_advect_vy<<<g, b, 0, stream>>>(vx[vxf], vy[vyf], vy[1 - vyf], flag, H, half, full));
-  vxf = 1 - vxf;
-  vyf = 1 - vyf;
+  UBGL_LAUNCH(&lc, K_ADVECT, LVL, stream, k_advect_vx<<<g, b, 0, stream>>>(vxb[ixf], vyb[iyf], vxb[ixb], flag, half, full));
+  UBGL_LAUNCH(&lc, K_ADVECT, LVL, stream, k_advect_vy<<<g, b, 0, stream>>>(vxb[ixf], vyb[iyf], vyb[iyb], flag, H, half, full));
+  std::swap(ixf, ixb);
+  std::swap(iyf, iyb);
 }
 
 void DeviceSim::project() {
   float ih = 1.0f / h;
-  UBGL_LAUNCH(&lc, K_DIVERGENCE, LVL, stream, k_divergence<<<grd2d(W - 2, H - 2), blk2d(), 0, stream>>>(vx[vxf], vy[vyf], f, ih));
+  UBGL_LAUNCH(&lc, K_DIVERGENCE, LVL, stream, k_divergence<<<grd2d(W - 2, H - 2), blk2d(), 0, stream>>>(vxb[ixf], vyb[iyf], f, ih));
+  project_sinks();
+  for (int c = 0; c < vcycles; c++) mg->solve(p, f, flag, h, true);
 
+  UBGL_LAUNCH(&lc, K_PBC, LVL, stream, k_set_pbc<<<1, 1024, 0, stream>>>(p, bcW, bcE, bcN, bcS));
+  UBGL_LAUNCH(&lc, K_GRADIENT, LVL, stream, k_gradient<<<grd2d(W - 2, H - 2), blk2d(), 0, stream>>>(vxb[ixf], vyb[iyf], p, flag, ih));
+}
+
+void DeviceSim::project_sinks() {
   // sinks (simulation.cpp:173-187): grid position, border skip, decay and erase
   // are host-side list work exactly as in the reference; only the 3x3 stamps
   // touch device memory.
@@ -436,17 +442,12 @@ void DeviceSim::project() {
     UBGL_CUDA(cudaStreamSynchronize(stream)); // stamps is a stack-lifetime staging buffer
     UBGL_LAUNCH(&lc, K_SINKS, LVL, stream, k_stamp_sinks<<<1, 32, 0, stream>>>(f, d_sinks, n));
   }
-
-  for (int c = 0; c < vcycles; c++) mg->solve(p, f, flag, h, true);
-
-  UBGL_LAUNCH(&lc, K_PBC, LVL, stream, k_set_pbc<<<1, 1024, 0, stream>>>(p, bcW, bcE, bcN, bcS));
-  UBGL_LAUNCH(&lc, K_GRADIENT, LVL, stream, k_gradient<<<grd2d(W - 2, H - 2), blk2d(), 0, stream>>>(vx[vxf], vy[vyf], p, flag, ih));
 }
 
 void DeviceSim::save_current() {
-  UBGL_CUDA(cudaMemcpyAsync(vx_current.d, vx[vxf].d, vx_current.bytes(), cudaMemcpyDeviceToDevice,
+  UBGL_CUDA(cudaMemcpyAsync(vxb[ixc].d, vxb[ixf].d, vxb[ixc].bytes(), cudaMemcpyDeviceToDevice,
                             stream));
-  UBGL_CUDA(cudaMemcpyAsync(vy_current.d, vy[vyf].d, vy_current.bytes(), cudaMemcpyDeviceToDevice,
+  UBGL_CUDA(cudaMemcpyAsync(vyb[iyc].d, vyb[iyf].d, vyb[iyc].bytes(), cudaMemcpyDeviceToDevice,
                             stream));
 }
 
@@ -466,26 +467,46 @@ void DeviceSim::stage(int st, float dt_) {
 // Simulation::step (simulation.cpp:356-374)
 void DeviceSim::step(float dt_) {
   dt = dt_;
+  const bool fz = fused && mg->mask0_is_binary();
   cudaEvent_t ev[8];
   if (timing)
     for (auto &e : ev) UBGL_CUDA(cudaEventCreate(&e));
   int k = 0;
   auto mark = [&]() { if (timing) UBGL_CUDA(cudaEventRecord(ev[k++], stream)); };
   mark();
-  apply_accum();
-  mark();
-  diffuse();
-  mark();
-  advect();
-  mark();
-  set_vbcs();
-  mark();
-  project();
-  mark();
-  set_vbcs();
-  mark();
-  save_current();
-  mark();
+  if (fz) {
+    mark(); // applyAccumulatedVelocity is part of the fused diffuse pass
+    fused_prestep();
+    fused_borders(false, false);
+    mark();
+    advect();
+    mark();
+    fused_borders(false, false);
+    mark();
+    fused_divergence();
+    project_sinks();
+    for (int c = 0; c < vcycles; c++) mg->solve(p, f, flag, h, true);
+    fused_gradient_save(); // reads only interior p: independent of setPBC
+    mark();
+    fused_borders(true, true); // setPBC + setVBCs, also into vx_current / vy_current
+    mark();
+    mark();
+  } else {
+    apply_accum();
+    mark();
+    diffuse();
+    mark();
+    advect();
+    mark();
+    set_vbcs();
+    mark();
+    project();
+    mark();
+    set_vbcs();
+    mark();
+    save_current();
+    mark();
+  }
   if (timing) {
     UBGL_CUDA(cudaStreamSynchronize(stream));
     float ms[7];

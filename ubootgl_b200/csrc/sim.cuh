@@ -57,9 +57,19 @@ public:
   float stage_ms[ST_COUNT] = {0, 0, 0, 0, 0, 0};
 
 private:
-  Grid vx[2], vy[2];
-  int vxf = 0, vyf = 0; // front index; back = 1 - front (db2dgrid.hpp:64)
-  Grid vx_accum, vy_accum, vx_current, vy_current, p, f, flag, r;
+  // Three buffers per velocity component in the roles front / back
+  // (db2dgrid.hpp:52-109) / vx_current (simulation.hpp:130).  swap() exchanges
+  // front and back; the fused diffuse writes its result into the buffer that
+  // holds the (dead until save) vx_current role and rotates the roles.
+  Grid vxb[3], vyb[3];
+  int ixf = 0, ixb = 1, ixc = 2, iyf = 0, iyb = 1, iyc = 2;
+  Grid vx_accum, vy_accum, p, f, flag, r;
+  void project_sinks();
+  // sim_fused.cu
+  void fused_prestep();
+  void fused_borders(bool with_p, bool with_current);
+  void fused_divergence();
+  void fused_gradient_save();
   float *d_sinks = nullptr; // ix, iy, z triples stamped into f
   int cap_sinks = 0;
   bool r_alloc = false;

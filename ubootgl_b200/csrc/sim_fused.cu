@@ -1,0 +1,450 @@
+// sim_fused.cu -- fused non-multigrid kernels of Simulation::step (sm_100a).
+//
+//   k_prestep<COMP> : applyAccumulatedVelocity + both diffuse passes of one
+//                     velocity component in one tile pass (simulation.cpp:
+//                     376-396, 104-162), the setVBCs between the passes applied
+//                     to the window in shared memory.
+//   k_vbc_cols/rows : setVBCs (simulation.cpp:80-102) and setPBC (:36-45), fully
+//                     parallel over the perimeter (column phase, then row phase).
+//   k_divergence4   : project part 1 (:166-171), 128-bit accesses, also zeroes
+//                     the accumulator interiors (:384,392).
+//   k_gradient_save : gradient subtraction + saveCurrentVelocityFields
+//                     (:196-207, :16-19) in one pass.
+//
+// Flags are read as the level-0 stencil mask (1 B/cell, mg_fused.cu MB_*), so
+// the fused step requires binary flags; otherwise DeviceSim uses the plain
+// kernels of sim.cu.  Per-cell arithmetic = stencils.cuh, i.e. bit-identical to
+// the plain path (tests/test_gpu_fused.py).
+#include "sim.cuh"
+#include "stencils.cuh"
+
+namespace ubgl {
+
+enum { MB_C = 1, MB_W = 2, MB_E = 32, MB_S = 64, MB_N = 128 };
+
+// ---------------------------------------------------------------------------
+// k_prestep
+// ---------------------------------------------------------------------------
+constexpr int PW = 128;        // window width (one float4 per lane)
+constexpr int PTX = PW - 8;    // tile width  (halo 2, rounded to 4 for alignment)
+constexpr int PTY = 32;        // tile height
+constexpr int PWH = PTY + 4;   // window height (halo 2)
+constexpr int PRS = PW + 8;    // shared row stride, data at column 4
+constexpr int PNT = 256;
+
+struct PrestepArgs {
+  const float *A;   // front buffer (input)
+  const float *K;   // buffer whose BORDER cells are the "kept" values of the
+                    // first setVBCs after pass 1 (vx: the old back buffer)
+  float *acc;       // accumulator (read; zeroed later by k_divergence4)
+  float *B;         // old back buffer: receives the pass-1 result (interior)
+  float *Cout;      // receives the pass-2 result (interior) + border values
+  const uint8_t *mask;
+  int gw, gh;       // size of this staggered grid
+  int H;            // rows of the cell grid (mask)
+  int pitch;
+  float a, rden;
+  int bcLo, bcHi;   // BC of the column sides (W, E)
+  int bcS, bcN;
+};
+
+struct PrestepSmem {
+  float V[PWH][PRS]; // v0 = front + accum, later the pass-2 result
+  float D[PWH][PRS]; // pass-1 result with its boundary values
+  uint8_t M[PWH][PRS];
+};
+
+// BC value of a border cell given its interior neighbour a and its own value b.
+// vx: columns are "parallel" sides, rows "perpendicular" (simulation.cpp:83-91);
+// vy the other way round (:92-100).
+template <int COMP> __device__ __forceinline__ float bc_col(int bc, float a, float b) {
+  return COMP == 0 ? vbc_par(bc, a, b) : vbc_per(bc, a, b);
+}
+template <int COMP> __device__ __forceinline__ float bc_row(int bc, float a, float b) {
+  return COMP == 0 ? vbc_per(bc, a, b) : vbc_par(bc, a, b);
+}
+
+template <int COMP> __global__ void __launch_bounds__(PNT) k_prestep(PrestepArgs g) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  PrestepSmem &sm = *reinterpret_cast<PrestepSmem *>(smem_raw);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int NW = PNT / 32;
+  const int x0 = blockIdx.x * PTX, y0 = blockIdx.y * PTY;
+  const int X0 = x0 - 4, Y0 = y0 - 2;
+  const int gw = g.gw, gh = g.gh;
+
+  auto interior = [&](int gx, int gy) { return gx >= 1 && gx <= gw - 2 && gy >= 1 && gy <= gh - 2; };
+
+  // ---- stage: v0 = A (+ acc on the interior), keep-values, mask ----
+  for (int r = warp; r < PWH; r += NW) {
+    const int gy = Y0 + r, gx = X0 + 4 * lane;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f), k = v;
+    uchar4 m = make_uchar4(0, 0, 0, 0);
+    if (gy >= 0 && gx >= 0 && gx < g.pitch) {
+      const size_t o = (size_t)gy * g.pitch + gx;
+      if (gy < gh) {
+        v = *reinterpret_cast<const float4 *>(g.A + o);
+        const bool rowin = gy >= 1 && gy <= gh - 2;
+        if (rowin) {
+          const float4 ac = *reinterpret_cast<const float4 *>(g.acc + o);
+          if (gx >= 1 && gx <= gw - 2) v.x = __fadd_rn(v.x, ac.x);
+          if (gx + 1 >= 1 && gx + 1 <= gw - 2) v.y = __fadd_rn(v.y, ac.y);
+          if (gx + 2 >= 1 && gx + 2 <= gw - 2) v.z = __fadd_rn(v.z, ac.z);
+          if (gx + 3 >= 1 && gx + 3 <= gw - 2) v.w = __fadd_rn(v.w, ac.w);
+        }
+        k = v;
+        if (COMP == 0 && (!rowin || gx == 0 || (gw - 1 >= gx && gw - 1 <= gx + 3)))
+          k = *reinterpret_cast<const float4 *>(g.K + o);
+      }
+      if (gy < g.H) m = __ldg(reinterpret_cast<const uchar4 *>(g.mask + o));
+    }
+    *reinterpret_cast<float4 *>(&sm.V[r][4 + 4 * lane]) = v;
+    *reinterpret_cast<float4 *>(&sm.D[r][4 + 4 * lane]) = k;
+    *reinterpret_cast<uchar4 *>(&sm.M[r][4 + 4 * lane]) = m;
+    if (lane < 2) {
+      const int c = lane ? 4 + PW : 0;
+      *reinterpret_cast<float4 *>(&sm.V[r][c]) = make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4 *>(&sm.D[r][c]) = make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<uchar4 *>(&sm.M[r][c]) = make_uchar4(0, 0, 0, 0);
+    }
+  }
+  __syncthreads();
+
+  // setVBCs on the window held in `arr` (non-corner border cells whose interior
+  // neighbour is inside the window; corners are never read by the 5-point pass)
+  auto fix_borders = [&](float(*arr)[PRS]) {
+    const int t = threadIdx.x;
+    const int ly_lo = max(0, 1 - Y0), ly_hi = min(PWH, gh - 1 - Y0); // rows with 1 <= gy <= gh-2
+    const int lx_lo = max(0, 1 - X0), lx_hi = min(PW, gw - 1 - X0);
+    if (X0 <= 0 && -X0 + 1 < PW) {
+      const int c = 4 - X0;
+      for (int r = ly_lo + t; r < ly_hi; r += PNT) arr[r][c] = bc_col<COMP>(g.bcLo, arr[r][c + 1], arr[r][c]);
+    }
+    if (gw - 1 - X0 >= 1 && gw - 1 - X0 < PW) {
+      const int c = 4 + gw - 1 - X0;
+      for (int r = ly_lo + t; r < ly_hi; r += PNT) arr[r][c] = bc_col<COMP>(g.bcHi, arr[r][c - 1], arr[r][c]);
+    }
+    if (Y0 <= 0 && -Y0 + 1 < PWH) {
+      const int r = -Y0;
+      for (int c = lx_lo + t; c < lx_hi; c += PNT) arr[r][4 + c] = bc_row<COMP>(g.bcS, arr[r + 1][4 + c], arr[r][4 + c]);
+    }
+    if (gh - 1 - Y0 >= 1 && gh - 1 - Y0 < PWH) {
+      const int r = gh - 1 - Y0;
+      for (int c = lx_lo + t; c < lx_hi; c += PNT) arr[r][4 + c] = bc_row<COMP>(g.bcN, arr[r - 1][4 + c], arr[r][4 + c]);
+    }
+  };
+
+  const bool edge = X0 <= 0 || Y0 <= 0 || gw - 1 - X0 < PW || gh - 1 - Y0 < PWH;
+  if (COMP == 1) {
+    // vy: the setVBCs calls issued during the vx passes (simulation.cpp:132) have
+    // already refreshed vy's border from its post-accumulation interior
+    if (edge) {
+      fix_borders(sm.V);
+      __syncthreads();
+      // those values are what the BC after vy's first pass keeps
+      for (int i = threadIdx.x; i < PWH * (PW / 4); i += PNT) {
+        const int r = i / (PW / 4), c = 4 + 4 * (i % (PW / 4));
+        const int gy = Y0 + r, gx = X0 + c - 4;
+        if (gy == 0 || gy == gh - 1 || gx == 0 || (gw - 1 >= gx && gw - 1 <= gx + 3))
+          *reinterpret_cast<float4 *>(&sm.D[r][c]) = *reinterpret_cast<const float4 *>(&sm.V[r][c]);
+      }
+      __syncthreads();
+    }
+  }
+
+  // one diffuse pass over window rows [r_lo, r_hi), 4 cells per thread
+  auto pass = [&](float(*src)[PRS], float(*dst)[PRS], int r_lo, int r_hi, int g_lo, int g_hi) {
+    const int ng = g_hi - g_lo;
+    for (int i = threadIdx.x; i < (r_hi - r_lo) * ng; i += PNT) {
+      const int r = r_lo + i / ng, c = 4 + 4 * (g_lo + i % ng);
+      const int gy = Y0 + r, gx = X0 + c - 4;
+      if (gy < 1 || gy > gh - 2) continue;
+      const float4 C4 = *reinterpret_cast<const float4 *>(&src[r][c]);
+      const float4 N4 = *reinterpret_cast<const float4 *>(&src[r + 1][c]);
+      const float4 S4 = *reinterpret_cast<const float4 *>(&src[r - 1][c]);
+      const float wv = src[r][c - 1], ev = src[r][c + 4];
+      const unsigned mc = *reinterpret_cast<const unsigned *>(&sm.M[r][c]);
+      const unsigned mn = *reinterpret_cast<const unsigned *>(&sm.M[r + 1][c]);
+      const unsigned ms = *reinterpret_cast<const unsigned *>(&sm.M[r - 1][c]);
+      const unsigned mE = sm.M[r][c + 4], mW = sm.M[r][c - 1];
+      const float cc[4] = {C4.x, C4.y, C4.z, C4.w};
+      const float nn[4] = {N4.x, N4.y, N4.z, N4.w};
+      const float ss[4] = {S4.x, S4.y, S4.z, S4.w};
+      const float ww[4] = {wv, C4.x, C4.y, C4.z};
+      const float ee[4] = {C4.y, C4.z, C4.w, ev};
+      float out[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const unsigned bC = (mc >> (8 * j)) & 255u;
+        const unsigned bE = j < 3 ? (mc >> (8 * j + 8)) & 255u : mE;
+        const unsigned bW = j > 0 ? (mc >> (8 * j - 8)) & 255u : mW;
+        const unsigned bN = (mn >> (8 * j)) & 255u, bS = (ms >> (8 * j)) & 255u;
+        auto both = [](unsigned b, unsigned bits) { return (b & bits) == bits; };
+        const float c0 = cc[j];
+        float val;
+        bool mC;
+        if (COMP == 0) { // simulation.cpp:117-127
+          val = both(bE, MB_C | MB_E) ? ee[j] : 0.0f;
+          val = __fadd_rn(both(bC, MB_C | MB_W) ? ww[j] : 0.0f, val);
+          val = __fadd_rn(val, both(bN, MB_C | MB_W) ? nn[j] : -c0);
+          val = __fadd_rn(val, both(bS, MB_C | MB_W) ? ss[j] : -c0);
+          mC = both(bC, MB_C | MB_E);
+        } else { // simulation.cpp:143-153
+          val = both(bC, MB_C | MB_S) ? ss[j] : 0.0f;
+          val = __fadd_rn(both(bN, MB_C | MB_N) ? nn[j] : 0.0f, val);
+          val = __fadd_rn(val, both(bE, MB_C | MB_N) ? ee[j] : -c0);
+          val = __fadd_rn(val, both(bW, MB_C | MB_N) ? ww[j] : -c0);
+          mC = both(bC, MB_C | MB_N);
+        }
+        out[j] = mC ? __fmul_rn(__fmaf_rn(g.a, val, c0), g.rden) : 0.0f;
+      }
+      if (gx >= 1 && gx + 3 <= gw - 2) {
+        *reinterpret_cast<float4 *>(&dst[r][c]) = make_float4(out[0], out[1], out[2], out[3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+          if (gx + j >= 1 && gx + j <= gw - 2) dst[r][c + j] = out[j];
+      }
+    }
+  };
+
+  pass(sm.V, sm.D, 1, PWH - 1, 0, PW / 4); // pass 1 (i = 1), simulation.cpp:113-129 / :139-155
+  __syncthreads();
+  if (edge) {
+    fix_borders(sm.D); // swap + setVBCs, simulation.cpp:130-132
+    __syncthreads();
+  }
+  pass(sm.D, sm.V, 2, PWH - 2, 1, PW / 4 - 1); // pass 2 (i = 2) on the tile proper
+  __syncthreads();
+
+  // ---- write back: B <- pass 1 (interior), Cout <- pass 2 (interior) and the
+  // boundary values the next setVBCs keeps ----
+  for (int i = threadIdx.x; i < PTY * (PTX / 4); i += PNT) {
+    const int r = 2 + i / (PTX / 4), c = 8 + 4 * (i % (PTX / 4));
+    const int gy = Y0 + r, gx = X0 + c - 4;
+    if (gy >= gh || gx >= gw) continue;
+    const size_t o = (size_t)gy * g.pitch + gx;
+    const float4 d1 = *reinterpret_cast<const float4 *>(&sm.D[r][c]);
+    const float4 d2 = *reinterpret_cast<const float4 *>(&sm.V[r][c]);
+    if (gy >= 1 && gy <= gh - 2 && gx >= 1 && gx + 3 <= gw - 2) {
+      *reinterpret_cast<float4 *>(g.B + o) = d1;
+      *reinterpret_cast<float4 *>(g.Cout + o) = d2;
+    } else {
+      const float a1[4] = {d1.x, d1.y, d1.z, d1.w}, a2[4] = {d2.x, d2.y, d2.z, d2.w};
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        if (gx + j >= gw) break;
+        if (interior(gx + j, gy)) {
+          g.B[o + j] = a1[j];
+          g.Cout[o + j] = a2[j];
+        } else {
+          g.Cout[o + j] = a1[j];
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// setVBCs / setPBC, parallel over the perimeter.  Column phase and row phase are
+// separate launches: the row phase reads the column results at x = 0 / w-1 and
+// wins at the corners, exactly as the reference's loop order.
+// ---------------------------------------------------------------------------
+struct BorderArgs {
+  Grid xf, xb, yf, yb; // velocity front / back buffers (both are written)
+  Grid xc, yc;         // optional third copy (vx_current / vy_current), d == nullptr: none
+  Grid p;              // optional: setPBC on p, d == nullptr: none
+  int bcW, bcE, bcN, bcS;
+};
+
+__device__ __forceinline__ void put3(const Grid &a, const Grid &b, const Grid &c, int x, int y, float v) {
+  a.at(x, y) = v;
+  b.at(x, y) = v;
+  if (c.d) c.at(x, y) = v;
+}
+
+__global__ void k_vbc_cols(BorderArgs g) {
+  const int y = blockIdx.x * blockDim.x + threadIdx.x;
+  if (y < g.xf.h) {
+    const int w = g.xf.w;
+    put3(g.xf, g.xb, g.xc, 0, y, vbc_par(g.bcW, g.xf.at(1, y), g.xf.at(0, y)));
+    put3(g.xf, g.xb, g.xc, w - 1, y, vbc_par(g.bcE, g.xf.at(w - 2, y), g.xf.at(w - 1, y)));
+  }
+  if (y < g.yf.h) {
+    const int w = g.yf.w;
+    put3(g.yf, g.yb, g.yc, 0, y, vbc_per(g.bcW, g.yf.at(1, y), g.yf.at(0, y)));
+    put3(g.yf, g.yb, g.yc, w - 1, y, vbc_per(g.bcE, g.yf.at(w - 2, y), g.yf.at(w - 1, y)));
+  }
+  if (g.p.d && y < g.p.h) {
+    g.p.at(0, y) = single_pbc(g.bcW, g.p.at(1, y));
+    g.p.at(g.p.w - 1, y) = single_pbc(g.bcE, g.p.at(g.p.w - 2, y));
+  }
+}
+
+__global__ void k_vbc_rows(BorderArgs g) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x < g.xf.w) {
+    const int h = g.xf.h;
+    put3(g.xf, g.xb, g.xc, x, 0, vbc_per(g.bcS, g.xf.at(x, 1), g.xf.at(x, 0)));
+    put3(g.xf, g.xb, g.xc, x, h - 1, vbc_per(g.bcN, g.xf.at(x, h - 2), g.xf.at(x, h - 1)));
+  }
+  if (x < g.yf.w) {
+    const int h = g.yf.h;
+    put3(g.yf, g.yb, g.yc, x, 0, vbc_par(g.bcS, g.yf.at(x, 1), g.yf.at(x, 0)));
+    put3(g.yf, g.yb, g.yc, x, h - 1, vbc_par(g.bcN, g.yf.at(x, h - 2), g.yf.at(x, h - 1)));
+  }
+  if (g.p.d && x < g.p.w) {
+    g.p.at(x, 0) = single_pbc(g.bcS, g.p.at(x, 1));
+    g.p.at(x, g.p.h - 1) = single_pbc(g.bcN, g.p.at(x, g.p.h - 2));
+  }
+}
+
+// ---------------------------------------------------------------------------
+// divergence (simulation.cpp:166-171) + zeroing of the accumulator interiors
+// (:384,:392).  One thread = 4 consecutive cells of a row.
+// ---------------------------------------------------------------------------
+__global__ void k_divergence4(Grid vx, Grid vy, Grid f, Grid ax, Grid ay, float ih) {
+  const int x = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
+  const int y = 1 + blockIdx.y * blockDim.y + threadIdx.y;
+  const int W = f.w, H = f.h;
+  if (x >= W - 1 || y >= H - 1) return;
+  const size_t o = (size_t)y * f.pitch + x; // all grids share the pitch
+  const float4 a = *reinterpret_cast<const float4 *>(vx.d + o);
+  const float aw = x > 0 ? vx.d[o - 1] : 0.0f;
+  const float4 b = *reinterpret_cast<const float4 *>(vy.d + o);
+  const float4 c = *reinterpret_cast<const float4 *>(vy.d + o - f.pitch);
+  auto dv = [&](float xe, float xw, float yn, float ys) {
+    return __fmul_rn(-ih, __fsub_rn(__fadd_rn(__fsub_rn(xe, xw), yn), ys));
+  };
+  const float r[4] = {dv(a.x, aw, b.x, c.x), dv(a.y, a.x, b.y, c.y), dv(a.z, a.y, b.z, c.z),
+                      dv(a.w, a.z, b.w, c.w)};
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (x >= 1 && x + 3 <= W - 3 && y <= H - 3) { // every cell interior in f, vx and vy
+    *reinterpret_cast<float4 *>(f.d + o) = make_float4(r[0], r[1], r[2], r[3]);
+    *reinterpret_cast<float4 *>(ax.d + o) = z;
+    *reinterpret_cast<float4 *>(ay.d + o) = z;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int xx = x + j;
+      if (xx < 1 || xx > W - 2) continue;
+      f.d[o + j] = r[j];
+      if (xx <= W - 3) ax.d[o + j] = 0.0f; // vx interior: 1..W-3 x 1..H-2
+      if (y <= H - 3) ay.d[o + j] = 0.0f;  // vy interior: 1..W-2 x 1..H-3
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// gradient subtraction (simulation.cpp:196-207) + saveCurrentVelocityFields
+// (:16-19) for the interior faces; the border faces of vx_current / vy_current
+// are written by the setVBCs kernels that follow.
+// ---------------------------------------------------------------------------
+__global__ void k_gradient_save(Grid vx, Grid vy, Grid p, const uint8_t *mask, Grid cx, Grid cy,
+                                float ih) {
+  const int x = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
+  const int y = 1 + blockIdx.y * blockDim.y + threadIdx.y;
+  const int W = p.w, H = p.h;
+  if (x >= W - 1 || y >= H - 1) return;
+  const size_t o = (size_t)y * p.pitch + x;
+  const float4 pc = *reinterpret_cast<const float4 *>(p.d + o);
+  const float4 pn = *reinterpret_cast<const float4 *>(p.d + o + p.pitch);
+  const float pe = x + 4 < p.pitch ? p.d[o + 4] : 0.0f;
+  const unsigned m = *reinterpret_cast<const unsigned *>(mask + o);
+  float4 ux = *reinterpret_cast<const float4 *>(vx.d + o);
+  float4 uy = *reinterpret_cast<const float4 *>(vy.d + o);
+  auto gx = [&](float v, float p1, float p0, int j) {
+    const unsigned b = (m >> (8 * j)) & (MB_C | MB_E);
+    return b == (MB_C | MB_E) ? __fmaf_rn(-ih, __fsub_rn(p1, p0), v) : v;
+  };
+  auto gy = [&](float v, float p1, float p0, int j) {
+    const unsigned b = (m >> (8 * j)) & (MB_C | MB_N);
+    return b == (MB_C | MB_N) ? __fmaf_rn(-ih, __fsub_rn(p1, p0), v) : v;
+  };
+  ux.x = gx(ux.x, pc.y, pc.x, 0);
+  ux.y = gx(ux.y, pc.z, pc.y, 1);
+  ux.z = gx(ux.z, pc.w, pc.z, 2);
+  ux.w = gx(ux.w, pe, pc.w, 3);
+  uy.x = gy(uy.x, pn.x, pc.x, 0);
+  uy.y = gy(uy.y, pn.y, pc.y, 1);
+  uy.z = gy(uy.z, pn.z, pc.z, 2);
+  uy.w = gy(uy.w, pn.w, pc.w, 3);
+  if (x >= 1 && x + 3 <= W - 3 && y <= H - 3) {
+    *reinterpret_cast<float4 *>(vx.d + o) = ux;
+    *reinterpret_cast<float4 *>(vy.d + o) = uy;
+    *reinterpret_cast<float4 *>(cx.d + o) = ux;
+    *reinterpret_cast<float4 *>(cy.d + o) = uy;
+  } else {
+    const float ax[4] = {ux.x, ux.y, ux.z, ux.w}, ay[4] = {uy.x, uy.y, uy.z, uy.w};
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int xx = x + j;
+      if (xx < 1 || xx > W - 2) continue;
+      if (xx <= W - 3) { // vx faces 1..W-3 x 1..H-2
+        vx.d[o + j] = ax[j];
+        cx.d[o + j] = ax[j];
+      }
+      if (y <= H - 3) { // vy faces 1..W-2 x 1..H-3
+        vy.d[o + j] = ay[j];
+        cy.d[o + j] = ay[j];
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// launchers (DeviceSim members)
+// ---------------------------------------------------------------------------
+void DeviceSim::fused_prestep() {
+  const float a = dt * mu * ((float)W - 1.0f) / pwidth; // simulation.cpp:105
+  const float rden = 1.0f / (1.0f + 4.0f * a);
+  static bool attr_set = false;
+  if (!attr_set) {
+    UBGL_CUDA(cudaFuncSetAttribute(k_prestep<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)sizeof(PrestepSmem)));
+    UBGL_CUDA(cudaFuncSetAttribute(k_prestep<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)sizeof(PrestepSmem)));
+    attr_set = true;
+  }
+  PrestepArgs g{};
+  g.mask = mg->mask0_ptr();
+  g.H = H; g.pitch = pitch; g.a = a; g.rden = rden;
+  g.bcLo = bcW; g.bcHi = bcE; g.bcS = bcS; g.bcN = bcN;
+  // vx: A = front, B = back, Cout = the vx_current buffer; afterwards the roles
+  // rotate: front <- Cout, back stays, vx_current <- A (dead until save)
+  g.A = vxb[ixf].d; g.K = vxb[ixb].d; g.acc = vx_accum.d; g.B = vxb[ixb].d; g.Cout = vxb[ixc].d;
+  g.gw = W - 1; g.gh = H;
+  dim3 gx(ceil_div(g.gw, PTX), ceil_div(g.gh, PTY));
+  UBGL_LAUNCH(&lc, K_PRESTEP, 0, stream, k_prestep<0><<<gx, PNT, sizeof(PrestepSmem), stream>>>(g));
+  std::swap(ixf, ixc);
+  g.A = vyb[iyf].d; g.K = vyb[iyf].d; g.acc = vy_accum.d; g.B = vyb[iyb].d; g.Cout = vyb[iyc].d;
+  g.gw = W; g.gh = H - 1;
+  dim3 gy(ceil_div(g.gw, PTX), ceil_div(g.gh, PTY));
+  UBGL_LAUNCH(&lc, K_PRESTEP, 0, stream, k_prestep<1><<<gy, PNT, sizeof(PrestepSmem), stream>>>(g));
+  std::swap(iyf, iyc);
+}
+
+void DeviceSim::fused_borders(bool with_p, bool with_current) {
+  BorderArgs g{};
+  g.xf = vxb[ixf]; g.xb = vxb[ixb]; g.yf = vyb[iyf]; g.yb = vyb[iyb];
+  if (with_current) {
+    g.xc = vxb[ixc];
+    g.yc = vyb[iyc];
+  }
+  if (with_p) g.p = p;
+  g.bcW = bcW; g.bcE = bcE; g.bcN = bcN; g.bcS = bcS;
+  UBGL_LAUNCH(&lc, K_VBC, 0, stream, k_vbc_cols<<<ceil_div(H, 128), 128, 0, stream>>>(g));
+  UBGL_LAUNCH(&lc, K_VBC, 0, stream, k_vbc_rows<<<ceil_div(W, 128), 128, 0, stream>>>(g));
+}
+
+void DeviceSim::fused_divergence() {
+  dim3 b(32, 8), g(ceil_div(ceil_div(W - 1, 4), 32), ceil_div(H - 2, 8));
+  UBGL_LAUNCH(&lc, K_DIVERGENCE, 0, stream, k_divergence4<<<g, b, 0, stream>>>(vxb[ixf], vyb[iyf], f, vx_accum, vy_accum, 1.0f / h));
+}
+
+void DeviceSim::fused_gradient_save() {
+  dim3 b(32, 8), g(ceil_div(ceil_div(W - 1, 4), 32), ceil_div(H - 2, 8));
+  UBGL_LAUNCH(&lc, K_FINISH, 0, stream, k_gradient_save<<<g, b, 0, stream>>>(vxb[ixf], vyb[iyf], p, mg->mask0_ptr(), vxb[ixc], vyb[iyc], 1.0f / h));
+}
+
+} // namespace ubgl

@@ -141,12 +141,13 @@ __device__ __forceinline__ float cubic_hermite(float t, float A, float B, float 
 __device__ __forceinline__ float diffuse_cell(float c, float vA, float mA, float vB,
                                               float mB, float vN, float fvn,
                                               float vS, float fvs, float mC,
-                                              float a, float den) {
+                                              float a, float rden) {
   float val = __fmul_rn(vA, mA);
   val = __fmaf_rn(vB, mB, val);
   val = __fadd_rn(val, __fmaf_rn(vN, fvn, __fmul_rn(__fsub_rn(1.0f, fvn), -c)));
   val = __fadd_rn(val, __fmaf_rn(vS, fvs, __fmul_rn(__fsub_rn(1.0f, fvs), -c)));
-  return __fdiv_rn(__fmul_rn(mC, __fmaf_rn(a, val, c)), den);
+  // (v + a*val) / (1 + 4a) as a multiply by the rounded reciprocal (see rcp_count)
+  return __fmul_rn(__fmul_rn(mC, __fmaf_rn(a, val, c)), rden);
 }
 
 // VBCPar / VBCPer (simulation.cpp:50-78); bc numbering = Simulation::BC.
