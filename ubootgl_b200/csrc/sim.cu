@@ -101,6 +101,19 @@ __global__ void k_set_vbcs(Grid xf, Grid xb, Grid yf, Grid yb, int bcW, int bcE,
   }
 }
 
+// Catmull-Rom weights of the four taps: CubicHermite (interpolators.hpp:78-85)
+// a*t^3 + b*t^2 + c*t + d regrouped by tap, i.e. the same cubic evaluated as a
+// weighted sum (differs from the reference's Horner form only in rounding,
+// ~1e-7 relative; the kernel is issue bound and this form needs 40 instead of
+// 95 floating-point instructions per bicubic sample).
+__device__ __forceinline__ void cr_weights(float t, float &w0, float &w1, float &w2, float &w3) {
+  const float t2 = __fmul_rn(t, t);
+  w0 = __fmul_rn(__fmaf_rn(__fmaf_rn(-0.5f, t, 1.0f), t, -0.5f), t);
+  w1 = __fmaf_rn(__fmaf_rn(1.5f, t, -2.5f), t2, 1.0f);
+  w2 = __fmul_rn(__fmaf_rn(__fmaf_rn(-1.5f, t, 2.0f), t, 0.5f), t);
+  w3 = __fmul_rn(__fmaf_rn(0.5f, t, -0.5f), t2);
+}
+
 // bicubicSample (interpolators.hpp:92-206): clamp to [3, w-3] x [3, h-3]
 // (:94-97), truncate (:99-103), 4x4 taps at rows iy-1..iy+2 / cols ix-1..ix+2,
 // vertical Hermite per column first, then horizontal (:132-204).
@@ -108,18 +121,23 @@ __device__ __forceinline__ float bicubic(const float *__restrict__ g, int pitch,
                                          float cx, float cy) {
   cx = fmaxf(fminf(cx, (float)w - 3.0f), 3.0f);
   cy = fmaxf(fminf(cy, (float)h - 3.0f), 3.0f);
-  int icx = (int)cx, icy = (int)cy;
-  float stx = __fsub_rn(cx, truncf(cx)), sty = __fsub_rn(cy, truncf(cy));
-  const float *b = g + (size_t)(icy - 1) * pitch + (icx - 1);
-  float c0 = cubic_hermite(sty, __ldg(b + 0), __ldg(b + pitch + 0), __ldg(b + 2 * pitch + 0),
-                           __ldg(b + 3 * pitch + 0));
-  float c1 = cubic_hermite(sty, __ldg(b + 1), __ldg(b + pitch + 1), __ldg(b + 2 * pitch + 1),
-                           __ldg(b + 3 * pitch + 1));
-  float c2 = cubic_hermite(sty, __ldg(b + 2), __ldg(b + pitch + 2), __ldg(b + 2 * pitch + 2),
-                           __ldg(b + 3 * pitch + 2));
-  float c3 = cubic_hermite(sty, __ldg(b + 3), __ldg(b + pitch + 3), __ldg(b + 2 * pitch + 3),
-                           __ldg(b + 3 * pitch + 3));
-  return cubic_hermite(stx, c0, c1, c2, c3);
+  const int icx = (int)cx, icy = (int)cy;
+  const float stx = __fsub_rn(cx, (float)icx), sty = __fsub_rn(cy, (float)icy);
+  float y0, y1, y2, y3, x0, x1, x2, x3;
+  cr_weights(sty, y0, y1, y2, y3);
+  cr_weights(stx, x0, x1, x2, x3);
+  const float *r0 = g + ((icy - 1) * pitch + (icx - 1));
+  const float *r1 = r0 + pitch, *r2 = r1 + pitch, *r3 = r2 + pitch;
+  auto col = [&](int j) {
+    float c = __fmul_rn(y0, __ldg(r0 + j));
+    c = __fmaf_rn(y1, __ldg(r1 + j), c);
+    c = __fmaf_rn(y2, __ldg(r2 + j), c);
+    return __fmaf_rn(y3, __ldg(r3 + j), c);
+  };
+  float v = __fmul_rn(x0, col(0));
+  v = __fmaf_rn(x1, col(1), v);
+  v = __fmaf_rn(x2, col(2), v);
+  return __fmaf_rn(x3, col(3), v);
 }
 
 // advect, x-velocity faces (simulation.cpp:246-297).  blockDim.x == 32 and the
