@@ -133,8 +133,12 @@ int ubgl_sim_sync(ubgl_sim_t *sim);
 int ubgl_sim_residual(ubgl_sim_t *sim, float *l2);
 /* MG::solve(p, f, flag, h, true) on the resident fields, `cycles` times */
 int ubgl_sim_mg_solve(ubgl_sim_t *sim, int cycles);
+/* MG::solve(p, f, flag, h, zeroGradientBC) with an explicit grid spacing and BC
+ * switch, on the resident fields (Simulation::mg used as a stand-alone solver) */
+int ubgl_sim_mg_solve_ex(ubgl_sim_t *sim, float h, int zero_gradient_bc, int cycles);
 /* device address + pitch (in floats) of a resident field, for zero-copy
- * producers/consumers (tracers, interop, benchmark input generation). */
+ * producers/consumers (tracers, interop, benchmark input generation).  The
+ * velocity buffers rotate roles inside step(): query again after every step. */
 int ubgl_sim_device_ptr(ubgl_sim_t *sim, int field, void **dptr, int *pitch);
 /* per-stage device time of the last step when UBGL_OPT_TIMING=1 */
 int ubgl_sim_stage_ms(ubgl_sim_t *sim, int stage, float *ms);

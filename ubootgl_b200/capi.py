@@ -60,6 +60,7 @@ def _load():
         "ubgl_sim_sync": (i, [v]),
         "ubgl_sim_residual": (i, [v, FP]),
         "ubgl_sim_mg_solve": (i, [v, i]),
+        "ubgl_sim_mg_solve_ex": (i, [v, f, i, i]),
         "ubgl_sim_device_ptr": (i, [v, i, VP, IP]),
         "ubgl_sim_stage_ms": (i, [v, i, FP]),
         "ubgl_sim_launch_count": (ll, [v]),

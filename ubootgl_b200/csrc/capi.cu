@@ -291,6 +291,14 @@ int ubgl_sim_mg_solve(ubgl_sim_t *sim, int cycles) {
   UBGL_CATCH
 }
 
+int ubgl_sim_mg_solve_ex(ubgl_sim_t *sim, float h, int zero_gradient_bc, int cycles) {
+  UBGL_TRY
+  SIM(sim);
+  UBGL_REQUIRE(cycles >= 0 && h > 0.0f, "bad cycles / h");
+  S.mg_solve_ex(h, zero_gradient_bc != 0, cycles);
+  UBGL_CATCH
+}
+
 int ubgl_sim_device_ptr(ubgl_sim_t *sim, int field, void **dptr, int *pitch) {
   UBGL_TRY
   SIM(sim);

@@ -545,6 +545,10 @@ float DeviceSim::residual() {
   return mg->residual_norm_result();
 }
 
+void DeviceSim::mg_solve_ex(float hh, bool zgbc, int cycles) {
+  for (int c = 0; c < cycles; c++) mg->solve(p, f, flag, hh, zgbc);
+}
+
 void DeviceSim::mg_solve(int cycles) {
   for (int c = 0; c < cycles; c++) mg->solve(p, f, flag, h, true);
 }

@@ -34,6 +34,7 @@ public:
   void step(float dt);
   float residual();
   void mg_solve(int cycles);
+  void mg_solve_ex(float hh, bool zgbc, int cycles);
   void sync();
 
   // stages (plain path)

@@ -1,0 +1,102 @@
+// simulation.hpp -- drop-in for the reference's class Simulation
+// (te42kyfo/ubootgl simulation.hpp:18-141) whose step() runs on a B200.
+//
+// The public data members the game reads and writes directly (flag, vx, vy, p,
+// vx_accum, vy_accum, vx_current, vy_current, sinks, mg, h, ... -- SURVEY.md
+// 8b) are kept as HOST MIRRORS of the device-resident state:
+//   step() entry: every mirror the host touched since the last step is
+//                 uploaded (flag -> also rebuilds the MG flag pyramid;
+//                 accumulators are consumed and zeroed under accum_mutex;
+//                 sinks are handed over);
+//   step() exit : vx, vy (front and back), p, f, vx_current, vy_current and the
+//                 surviving sinks are downloaded.
+// setSyncMode(RESIDENT) switches the automatic downloads off for benchmarks;
+// syncToHost() fetches on demand.  Floating-item advection
+// (advect_floating_items.cpp) and the entt registry are outside the hot path
+//  -- the reference's own file compiles against this header.
+#pragma once
+#include "db2dgrid.hpp"
+#include "pressure_solver.hpp"
+#include <memory>
+#include <mutex>
+#include <random>
+#include <sstream>
+#include <vector>
+
+struct ubgl_sim;
+
+class Simulation {
+public:
+  enum class BC { INFLOW, OUTFLOW, OUTFLOW_ZERO_PRESSURE, NOSLIP }; // simulation.hpp:69
+  enum class SyncMode { MIRROR, RESIDENT };
+
+  Simulation(float pwidth, float mu, int width, int height);         // simulation.hpp:20-30
+  Simulation(const Single2DGrid &flagInput, float pwidth, float mu); // simulation.hpp:32-67
+  ~Simulation();
+
+  float singlePBC(BC bc, float b);
+  float VBCPar(BC bc, float a, float b);
+  float VBCPer(BC bc, float a, float b);
+  void setPBC();
+  void setVBCs();
+
+  float *getFlag() { return flag.data(); }
+  float *getP() { return p.data(); }
+  float *getR(); // computes the residual field on the device first
+
+  void setGrids(glm::ivec2 c, float val); // simulation.hpp:82-98
+
+  float psampleFlagNearest(glm::vec2 pc);
+  float psampleFlagLinear(glm::vec2 pc);
+  glm::vec2 psampleFlagNormal(glm::vec2 pc);
+
+  void diffuse();
+  void project();
+  void centerP();
+  float getDT();
+  void advect();
+  void applyAccumulatedVelocity();
+  void saveCurrentVelocityFields();
+  void step(float timestep);
+
+  // ---- additions of the drop-in ----
+  void setSyncMode(SyncMode m) { mode_ = m; }
+  void syncToDevice();  // upload every dirty mirror now
+  void syncToHost();    // download vx, vy, p, f, vx_current, vy_current, sinks
+  float residualNorm(); // calculateResidualField on the resident fields
+  long long kernelLaunches() const;
+  ubgl_sim *handle() { return dev_.get(); }
+
+  float pwidth;
+  float mu;
+  int width, height;
+  float dt = 0.0f;
+
+  BC bcWest = BC::INFLOW, bcEast = BC::OUTFLOW_ZERO_PRESSURE, bcNorth = BC::NOSLIP,
+     bcSouth = BC::NOSLIP;
+
+  std::stringstream diag;
+
+  DoubleBuffered2DGrid vx, vy;
+  Single2DGrid vx_accum, vy_accum;
+  Single2DGrid vx_current, vy_current;
+  std::mutex accum_mutex;
+  Single2DGrid p, f, flag, r;
+  MG mg;
+  float h;
+
+  std::default_random_engine gen;
+  std::uniform_real_distribution<float> disx;
+  std::uniform_real_distribution<float> disy;
+
+  std::vector<glm::vec3> sinks;
+
+private:
+  void create();
+  void runStage(int stage);
+  void pushBCs();
+  void download(int field, ubgl_host::MirrorStore &m);
+  std::shared_ptr<ubgl_sim> dev_;
+  SyncMode mode_ = SyncMode::MIRROR;
+  BC sentBC_[4] = {BC::INFLOW, BC::OUTFLOW_ZERO_PRESSURE, BC::NOSLIP, BC::NOSLIP};
+};
