@@ -183,6 +183,41 @@ int ubgl_mg_sync(ubgl_mg_t *mg);
 long long ubgl_mg_launch_count(ubgl_mg_t *mg);
 void *ubgl_mg_stream(ubgl_mg_t *mg);
 
+/* ---- Simulation::step row-slab decomposed over the GPUs of one box ---------- */
+/* (new).  One process (or thread) per GPU, each with one handle.
+ * GPU r owns the cell rows [own_lo, own_hi) and stores [st_lo, st_hi) (own rows
+ * plus ghost rows); upload/download move the STORED rows of a field, unpadded
+ * (w x nrows as ubgl_slab_field_rows reports).  Bootstrap: every rank creates its
+ * handle, the ranks exchange their ubgl_slab_ipc_export() blobs by any means
+ * (bench.py: torch.distributed all_gather), then every rank calls
+ * ubgl_slab_connect() with all blobs -- collective: it also builds the coarse
+ * flag pyramid, which needs the neighbours' rows.  ubgl_slab_step is
+ * Simulation::step(dt) (simulation.cpp:356-374); halo rows move by peer stores
+ * over NVLink inside the step, without host synchronisation. */
+typedef struct ubgl_slab ubgl_slab_t;
+/* pure host arithmetic, no CUDA: the decomposition a (W,H,nranks) run uses */
+int ubgl_slab_plan(int W, int H, int nranks, int rank, int *dist_levels, int *ghost, int *own_lo,
+                   int *own_hi, int *st_lo, int *st_hi);
+int ubgl_slab_create(const float *flag_stored_rows, int W, int H, float pwidth, float mu, int device,
+                     int rank, int nranks, ubgl_slab_t **out);
+int ubgl_slab_destroy(ubgl_slab_t *s);
+int ubgl_slab_ipc_size(void); /* bytes of one export blob */
+int ubgl_slab_ipc_export(ubgl_slab_t *s, void *blob);
+int ubgl_slab_connect(ubgl_slab_t *s, const void *blobs /* nranks blobs, indexed by rank */);
+int ubgl_slab_field_rows(ubgl_slab_t *s, int field, int *row_lo, int *nrows, int *w);
+int ubgl_slab_upload(ubgl_slab_t *s, int field, const float *host);
+int ubgl_slab_download(ubgl_slab_t *s, int field, float *host);
+int ubgl_slab_set_option(ubgl_slab_t *s, int option, int value); /* UBGL_OPT_VCYCLES */
+int ubgl_slab_set_sinks(ubgl_slab_t *s, const float *xyz, int n);
+int ubgl_slab_step(ubgl_slab_t *s, float dt);
+int ubgl_slab_sync(ubgl_slab_t *s);
+/* sum of r^2 over the own rows (calculateResidualField); add the ranks, take sqrt */
+int ubgl_slab_residual_sumsq(ubgl_slab_t *s, double *sumsq);
+long long ubgl_slab_launch_count(ubgl_slab_t *s);
+void *ubgl_slab_stream(ubgl_slab_t *s);
+/* halo exchanges issued and bytes pushed to peers so far */
+int ubgl_slab_stats(ubgl_slab_t *s, long long *exchanges, long long *halo_bytes);
+
 /* ---- pressure_solver.cpp free functions, host grids in/out ---------------- */
 /* rbgs(p,f,flag,h,alpha) x sweeps, canonical red-black order
  * (pressure_solver.cpp:35-72; the pipelined path :73-87 is not reproduced) */

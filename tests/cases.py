@@ -39,6 +39,34 @@ def channel_flag(W, H, seed=1234, ndiscs=32, radius=None, closed_box=False):
     return flag, g
 
 
+def channel_flag_rows(W, H, y0, y1, seed=1234, ndiscs=32, radius=None, closed_box=False):
+    """Rows [y0, y1) of channel_flag(W, H, ...) without building the whole grid
+    (the 32768^2 slab runs generate only the rows a rank stores)."""
+    rows = np.ones((y1 - y0, W), np.float32)
+    if y0 <= 0 < y1:
+        rows[0 - y0, :] = 0
+    if y0 <= H - 1 < y1:
+        rows[H - 1 - y0, :] = 0
+    if closed_box:
+        rows[:, 0] = 0
+        rows[:, W - 1] = 0
+    g = LCG(seed)
+    r = (H / 32.0) if radius is None else radius
+    for _ in range(ndiscs):
+        cx = (0.1 + 0.8 * g.u()) * W
+        cy = (0.15 + 0.7 * g.u()) * H
+        x0, x1 = max(1, int(np.floor(cx - r))), min(W - 2, int(np.floor(cx + r)))
+        ya, yb = max(1, int(np.floor(cy - r))), min(H - 2, int(np.floor(cy + r)))
+        ya, yb = max(ya, y0), min(yb, y1 - 1)
+        if x1 < x0 or yb < ya:
+            continue
+        yy, xx = np.mgrid[ya:yb + 1, x0:x1 + 1]
+        m = (xx - cx) ** 2 + (yy - cy) ** 2 <= r * r
+        sub = rows[ya - y0:yb + 1 - y0, x0:x1 + 1]
+        sub[m] = 0
+    return rows
+
+
 def dipole_rhs(flag, g, n=64, amp=1000.0):
     """Zero-sum dipoles f(x,y)=+amp, f(x+3,y)=-amp at LCG positions in fluid."""
     H, W = flag.shape

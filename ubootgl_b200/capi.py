@@ -84,6 +84,23 @@ def _load():
         "ubgl_mg_sync": (i, [v]),
         "ubgl_mg_launch_count": (ll, [v]),
         "ubgl_mg_stream": (v, [v]),
+        "ubgl_slab_plan": (i, [i, i, i, i, IP, IP, IP, IP, IP, IP]),
+        "ubgl_slab_create": (i, [FP, i, i, f, f, i, i, i, VP]),
+        "ubgl_slab_destroy": (i, [v]),
+        "ubgl_slab_ipc_size": (i, []),
+        "ubgl_slab_ipc_export": (i, [v, v]),
+        "ubgl_slab_connect": (i, [v, v]),
+        "ubgl_slab_field_rows": (i, [v, i, IP, IP, IP]),
+        "ubgl_slab_upload": (i, [v, i, FP]),
+        "ubgl_slab_download": (i, [v, i, FP]),
+        "ubgl_slab_set_option": (i, [v, i, i]),
+        "ubgl_slab_set_sinks": (i, [v, FP, i]),
+        "ubgl_slab_step": (i, [v, f]),
+        "ubgl_slab_sync": (i, [v]),
+        "ubgl_slab_residual_sumsq": (i, [v, C.POINTER(C.c_double)]),
+        "ubgl_slab_launch_count": (ll, [v]),
+        "ubgl_slab_stream": (v, [v]),
+        "ubgl_slab_stats": (i, [v, C.POINTER(ll), C.POINTER(ll)]),
         "ubgl_rbgs": (i, [FP, FP, FP, i, i, f, f, i]),
         "ubgl_residual": (i, [FP, FP, FP, FP, i, i, f, FP]),
         "ubgl_restrict": (i, [FP, i, i, FP]),
@@ -320,6 +337,109 @@ class MG:
 
     def launch_count(self):
         return lib.ubgl_mg_launch_count(self._h)
+
+
+def slab_plan(W, H, nranks, rank):
+    """The row decomposition a (W, H, nranks) run uses -- pure host arithmetic."""
+    v = [C.c_int() for _ in range(6)]
+    _ck(lib.ubgl_slab_plan(W, H, nranks, rank, *[C.byref(x) for x in v]))
+    k = ("dist_levels", "ghost", "own_lo", "own_hi", "st_lo", "st_hi")
+    return dict(zip(k, (x.value for x in v)))
+
+
+class SlabSimulation:
+    """One rank's slab of a Simulation decomposed over the GPUs of a box.
+
+    ``flag_rows`` covers this rank's STORED rows (slab_plan st_lo..st_hi).
+    ``exchange`` is a callable(bytes) -> list[bytes] that all-gathers a blob
+    across the ranks (torch.distributed in bench.py / the tests)."""
+
+    def __init__(self, flag_rows, W, H, rank, nranks, exchange, pwidth=0.8, mu=0.001, device=None):
+        self.W, self.H, self.rank, self.nranks = W, H, rank, nranks
+        self.plan = slab_plan(W, H, nranks, rank)
+        flag_rows = _f32(flag_rows)
+        if flag_rows.shape != (self.plan["st_hi"] - self.plan["st_lo"], W):
+            raise UbglError(f"flag rows {flag_rows.shape} do not match the stored rows of the plan")
+        self.h = np.float32(pwidth) / (np.float32(W) - np.float32(1.0))
+        self._h = C.c_void_p()
+        _ck(lib.ubgl_slab_create(_fp(flag_rows), W, H, pwidth, mu, rank if device is None else device,
+                                 rank, nranks, C.byref(self._h)))
+        n = lib.ubgl_slab_ipc_size()
+        blob = C.create_string_buffer(n)
+        _ck(lib.ubgl_slab_ipc_export(self._h, blob))
+        blobs = exchange(blob.raw)
+        assert len(blobs) == nranks and all(len(b) == n for b in blobs)
+        allb = C.create_string_buffer(b"".join(blobs), n * nranks)
+        _ck(lib.ubgl_slab_connect(self._h, allb))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.ubgl_slab_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def field_rows(self, field):
+        a, b, c = C.c_int(), C.c_int(), C.c_int()
+        _ck(lib.ubgl_slab_field_rows(self._h, field, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def set(self, field, rows):
+        r0, n, w = self.field_rows(field)
+        rows = _f32(rows)
+        if rows.shape != (n, w):
+            raise UbglError(f"field {field}: got {rows.shape}, stored rows are {(n, w)}")
+        _ck(lib.ubgl_slab_upload(self._h, field, _fp(rows)))
+
+    def set_from_global(self, field, a):
+        r0, n, w = self.field_rows(field)
+        self.set(field, a[r0:r0 + n])
+
+    def get(self, field):
+        """(first stored row, array of the stored rows)"""
+        r0, n, w = self.field_rows(field)
+        a = np.empty((n, w), np.float32)
+        _ck(lib.ubgl_slab_download(self._h, field, _fp(a)))
+        return r0, a
+
+    def get_own(self, field):
+        """(own_lo, rows this rank owns)"""
+        r0, a = self.get(field)
+        lo, hi = self.plan["own_lo"], min(self.plan["own_hi"], r0 + a.shape[0])
+        return lo, a[lo - r0:hi - r0]
+
+    def set_option(self, opt, val):
+        _ck(lib.ubgl_slab_set_option(self._h, opt, int(val)))
+
+    def set_sinks(self, xyz):
+        xyz = _f32(np.asarray(xyz, np.float32).reshape(-1, 3))
+        _ck(lib.ubgl_slab_set_sinks(self._h, _fp(xyz), len(xyz)))
+
+    def step(self, dt):
+        _ck(lib.ubgl_slab_step(self._h, dt))
+
+    def sync(self):
+        _ck(lib.ubgl_slab_sync(self._h))
+
+    def residual_sumsq(self):
+        v = C.c_double()
+        _ck(lib.ubgl_slab_residual_sumsq(self._h, C.byref(v)))
+        return v.value
+
+    def launch_count(self):
+        return lib.ubgl_slab_launch_count(self._h)
+
+    def stream(self):
+        return lib.ubgl_slab_stream(self._h)
+
+    def stats(self):
+        a, b = C.c_longlong(), C.c_longlong()
+        _ck(lib.ubgl_slab_stats(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
 
 # ---- pressure_solver.cpp free functions -------------------------------------

@@ -3,6 +3,7 @@
 #include "../../include/ubgl.h"
 #include "mg.cuh"
 #include "sim.cuh"
+#include "slab.cuh"
 #include <cstring>
 #include <memory>
 #include <new>
@@ -14,7 +15,7 @@ const char *kind_name(int k) {
       "other", "fill", "accum", "diffuse", "vbc", "advect", "divergence", "sinks", "rbgs_half",
       "zero_gradient_bc", "residual", "norm", "restrict", "prolong_correct", "coarsen_flag",
       "pbc", "gradient", "prestep_fused", "advect_div_fused", "mg_pre_fused", "mg_post_fused",
-      "mg_coarse_fused", "finish_fused"};
+      "mg_coarse_fused", "finish_fused", "halo_push", "halo_wait"};
   return (k >= 0 && k < K_COUNT) ? names[k] : "?";
 }
 static thread_local std::string g_err;
@@ -499,6 +500,140 @@ int ubgl_mg_sync(ubgl_mg_t *mg) {
 
 long long ubgl_mg_launch_count(ubgl_mg_t *mg) { return mg ? mg->lc.n : -1; }
 void *ubgl_mg_stream(ubgl_mg_t *mg) { return mg ? (void *)mg->stream : nullptr; }
+
+// ---- slabs ------------------------------------------------------------------
+struct ubgl_slab {
+  std::unique_ptr<SlabSim> s;
+};
+#define SLAB(h)                                                                \
+  NEED(h, "slab");                                                             \
+  SlabSim &S = *(h)->s;                                                        \
+  UBGL_CUDA(cudaSetDevice(S.device));
+
+int ubgl_slab_plan(int W, int H, int nranks, int rank, int *dist_levels, int *ghost, int *own_lo,
+                   int *own_hi, int *st_lo, int *st_hi) {
+  UBGL_TRY
+  SlabPlan P = make_slab_plan(W, H, nranks, rank);
+  Rows R = P.rows(0);
+  if (dist_levels) *dist_levels = P.ndist;
+  if (ghost) *ghost = P.ghost;
+  if (own_lo) *own_lo = R.own_lo;
+  if (own_hi) *own_hi = R.own_hi;
+  if (st_lo) *st_lo = R.st_lo;
+  if (st_hi) *st_hi = R.st_hi;
+  UBGL_CATCH
+}
+
+int ubgl_slab_create(const float *flag, int W, int H, float pwidth, float mu, int device, int rank,
+                     int nranks, ubgl_slab_t **out) {
+  UBGL_TRY
+  NEED(out, "out");
+  *out = nullptr;
+  NEED(flag, "flag");
+  require_device(device);
+  std::unique_ptr<ubgl_slab> h(new ubgl_slab);
+  h->s.reset(new SlabSim(flag, W, H, pwidth, mu, device, rank, nranks));
+  *out = h.release();
+  UBGL_CATCH
+}
+
+int ubgl_slab_destroy(ubgl_slab_t *s) {
+  UBGL_TRY
+  delete s;
+  UBGL_CATCH
+}
+
+int ubgl_slab_ipc_size(void) { return 64; }
+
+int ubgl_slab_ipc_export(ubgl_slab_t *s, void *blob) {
+  UBGL_TRY
+  SLAB(s);
+  NEED(blob, "blob");
+  S.ipc_export(blob);
+  UBGL_CATCH
+}
+
+int ubgl_slab_connect(ubgl_slab_t *s, const void *blobs) {
+  UBGL_TRY
+  SLAB(s);
+  NEED(blobs, "blobs");
+  S.connect(blobs);
+  S.finish_setup();
+  UBGL_CATCH
+}
+
+int ubgl_slab_field_rows(ubgl_slab_t *s, int field, int *row_lo, int *nrows, int *w) {
+  UBGL_TRY
+  SLAB(s);
+  NEED(row_lo, "row_lo"); NEED(nrows, "nrows"); NEED(w, "w");
+  UBGL_REQUIRE(field >= 0 && field < UBGL_NUM_FIELDS, "bad field id");
+  S.field_rows(field, row_lo, nrows, w);
+  UBGL_CATCH
+}
+
+int ubgl_slab_upload(ubgl_slab_t *s, int field, const float *host) {
+  UBGL_TRY
+  SLAB(s);
+  S.upload(field, host);
+  UBGL_CATCH
+}
+
+int ubgl_slab_download(ubgl_slab_t *s, int field, float *host) {
+  UBGL_TRY
+  SLAB(s);
+  S.download(field, host);
+  UBGL_CATCH
+}
+
+int ubgl_slab_set_option(ubgl_slab_t *s, int option, int value) {
+  UBGL_TRY
+  SLAB(s);
+  UBGL_REQUIRE(option == UBGL_OPT_VCYCLES && value >= 0, "slab: only UBGL_OPT_VCYCLES >= 0");
+  S.vcycles = value;
+  UBGL_CATCH
+}
+
+int ubgl_slab_set_sinks(ubgl_slab_t *s, const float *xyz, int n) {
+  UBGL_TRY
+  SLAB(s);
+  UBGL_REQUIRE(n >= 0 && (n == 0 || xyz), "bad sink list");
+  S.sinks.resize(n);
+  for (int i = 0; i < n; i++) S.sinks[i] = Sink{xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
+  UBGL_CATCH
+}
+
+int ubgl_slab_step(ubgl_slab_t *s, float dt) {
+  UBGL_TRY
+  SLAB(s);
+  S.step(dt);
+  UBGL_CATCH
+}
+
+int ubgl_slab_sync(ubgl_slab_t *s) {
+  UBGL_TRY
+  SLAB(s);
+  S.sync();
+  UBGL_CATCH
+}
+
+int ubgl_slab_residual_sumsq(ubgl_slab_t *s, double *sumsq) {
+  UBGL_TRY
+  SLAB(s);
+  NEED(sumsq, "sumsq");
+  *sumsq = S.residual_sumsq();
+  UBGL_CATCH
+}
+
+long long ubgl_slab_launch_count(ubgl_slab_t *s) { return s ? s->s->lc.n : -1; }
+void *ubgl_slab_stream(ubgl_slab_t *s) { return s ? (void *)s->s->stream : nullptr; }
+
+int ubgl_slab_stats(ubgl_slab_t *s, long long *exchanges, long long *halo_bytes) {
+  UBGL_TRY
+  SLAB(s);
+  if (exchanges) *exchanges = S.exchanges;
+  if (halo_bytes) *halo_bytes = (long long)S.halo_bytes;
+  UBGL_CATCH
+}
 
 // ---- free operators with host grids ------------------------------------------
 namespace {

@@ -22,6 +22,14 @@ struct Grid {
   size_t bytes() const { return sizeof(float) * (size_t)pitch * h; }
 };
 
+// Row-slab decomposition (csrc/slab.cu): of a level's rows, [st_lo, st_hi) are
+// stored on this GPU (own rows + ghost rows) and [own_lo, own_hi) are computed
+// here.  Slab grids keep GLOBAL row indices: Grid::d is the virtual address of
+// row 0, so kernels index them exactly like single-GPU grids.
+struct Rows {
+  int st_lo, st_hi, own_lo, own_hi;
+};
+
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
@@ -57,6 +65,7 @@ enum Kind {
   K_PRESTEP /* fused accum+diffuse */, K_ADVDIV /* fused advect+BC+divergence */,
   K_MG_PRE /* fused smooth+residual+restrict */, K_MG_POST /* fused prolong+correct+smooth */,
   K_MG_COARSE /* all coarse levels in one kernel */, K_FINISH /* fused pBC+gradient+vBC+save */,
+  K_HALO_PUSH /* peer-store halo rows + signal */, K_HALO_WAIT,
   K_COUNT
 };
 const char *kind_name(int kind);

@@ -151,10 +151,10 @@ __global__ void k_restrict(Grid r, Grid rc) {
 
 // MG::updateFields level step (pressure_solver.hpp:36-55): threshold of the
 // full-weighted fine flag at 0.2 (double compare); border cells stay 1.0.
-__global__ void k_coarsen_flag(Grid fine, Grid fc) {
+__global__ void k_coarsen_flag(Grid fine, Grid fc, int r_lo, int r_hi) {
   int x = blockIdx.x * blockDim.x + threadIdx.x;
-  int y = blockIdx.y * blockDim.y + threadIdx.y;
-  if (x >= fc.w || y >= fc.h) return;
+  int y = r_lo + blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= fc.w || y >= r_hi) return;
   float v = 1.0f;
   if (x >= 1 && y >= 1 && x < fc.w - 1 && y < fc.h - 1) {
     const float *a = fine.d + (size_t)(2 * y - 1) * fine.pitch + 2 * x;
@@ -199,6 +199,11 @@ __global__ void k_prolongate_correct(Grid p, Grid ec, Grid flagc, Grid flag) {
 // ---------------------------------------------------------------------------
 static inline dim3 blk2d() { return dim3(32, 8); }
 static inline dim3 grd2d(int w, int h) { return dim3(ceil_div(w, 32), ceil_div(h, 8)); }
+
+void launch_coarsen_flag(const Grid &fine, const Grid &fc, int r_lo, int r_hi, cudaStream_t stream,
+                         LaunchCounter *lc, int level) {
+  UBGL_LAUNCH(lc, K_COARSEN, level, stream, k_coarsen_flag<<<grd2d(fc.w, r_hi - r_lo), blk2d(), 0, stream>>>(fine, fc, r_lo, r_hi));
+}
 
 DeviceMG::DeviceMG(int W, int H, int device_, cudaStream_t stream_, LaunchCounter *lc_)
     : device(device_), stream(stream_), lc(lc_) {
@@ -265,7 +270,7 @@ void DeviceMG::update_fields(const Grid &flag0) {
                                 sizeof(float) * flag0.pitch, sizeof(float) * flag0.w, flag0.h,
                                 cudaMemcpyDeviceToDevice, stream));
   for (size_t l = 1; l < lv.size(); l++) {
-    UBGL_LAUNCH(lc, K_COARSEN, (int)l, stream, k_coarsen_flag<<<grd2d(lv[l].w, lv[l].h), blk2d(), 0, stream>>>(lv[l - 1].flagc, lv[l].flagc));
+    launch_coarsen_flag(lv[l - 1].flagc, lv[l].flagc, 0, lv[l].h, stream, lc, (int)l);
     if (l + 1 < lv.size())
       launch_make_mask(lv[l].flagc, lv[l].mask, d_nonbinary, stream, lc, (int)l);
   }

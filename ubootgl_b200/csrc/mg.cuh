@@ -75,14 +75,19 @@ private:
 // mg_fused.cu
 void launch_mg_pre(const float *p_in, float *p_out, const Grid &f, const uint8_t *mask,
                    const Grid &rc, float hh, bool zgbc, cudaStream_t stream, LaunchCounter *lc,
-                   int level);
+                   int level, const Rows *rows = nullptr);
 void launch_mg_post(const float *p_in, float *p_out, const Grid &f, const uint8_t *mask,
                     const Grid &ec, const uint8_t *maskc, float hh, bool zgbc, cudaStream_t stream,
-                    LaunchCounter *lc, int level);
+                    LaunchCounter *lc, int level, const Rows *rows = nullptr,
+                    const Rows *crows = nullptr);
 void launch_mg_smooth5(float *p_out, const Grid &f, const uint8_t *mask, float hh,
                        cudaStream_t stream, LaunchCounter *lc, int level);
 void launch_make_mask(const Grid &flag, uint8_t *mask, int *d_nonbinary, cudaStream_t stream,
-                      LaunchCounter *lc, int level);
+                      LaunchCounter *lc, int level, const Rows *rows = nullptr,
+                    const Rows *crows = nullptr);
+// MG::updateFields level step on coarse rows [r_lo, r_hi) (mg.cu)
+void launch_coarsen_flag(const Grid &fine, const Grid &fc, int r_lo, int r_hi, cudaStream_t stream,
+                         LaunchCounter *lc, int level);
 
 Grid alloc_grid(int w, int h, int pitch_floats, bool zero = true);
 void free_grid(Grid &g);

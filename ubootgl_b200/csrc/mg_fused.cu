@@ -57,6 +57,11 @@ struct TileArgs {
   int wc, hc, pc;
   float hh, ihsq;
   int zgbc;
+  // row-slab decomposition (csrc/slab.cu): rows [st_lo, st_hi) of this level are
+  // stored on this GPU (p_in, p_out, f, mask are addressed with GLOBAL row
+  // indices), rows [own_lo, own_hi) are computed and written.  Single GPU: 0, h.
+  int st_lo, st_hi, own_lo, own_hi;
+  int c_lo, c_hi; // MODE_POST: rows of the coarse level stored here (single GPU: 0, hc)
 };
 
 constexpr int LW = 128;    // staged window width in cells
@@ -96,8 +101,8 @@ __global__ void __launch_bounds__(NT, 2) k_mg_tile(TileArgs a) {
   TileSmem<LH> &sm = *reinterpret_cast<TileSmem<LH> *>(smem_raw);
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
-  const int X0 = x0 - HALO, Y0 = y0 - HALO; // X0 % 8 == 0, Y0 even: local parity == global parity
+  const int x0 = blockIdx.x * TX, y0 = a.own_lo + blockIdx.y * TY;
+  const int X0 = x0 - HALO, Y0 = y0 - HALO; // X0 % 4 == 0, Y0 even: local parity == global parity
   const int w = a.w, h = a.h;
 
   if (threadIdx.x < 8) sm.rcpt[threadIdx.x] = rcp_count(threadIdx.x);
@@ -107,7 +112,7 @@ __global__ void __launch_bounds__(NT, 2) k_mg_tile(TileArgs a) {
     const int gy = Y0 + r, gx = X0 + 4 * lane;
     float4 pv = make_float4(0.f, 0.f, 0.f, 0.f), fv = pv;
     uchar4 mv = make_uchar4(0, 0, 0, 0);
-    if (gy >= 0 && gy < h && gx >= 0 && gx < a.pitch) {
+    if (gy >= a.st_lo && gy < a.st_hi && gx >= 0 && gx < a.pitch) {
       const size_t o = (size_t)gy * a.pitch + gx;
       if (a.p_in) pv = *reinterpret_cast<const float4 *>(a.p_in + o);
       fv = __ldg(reinterpret_cast<const float4 *>(a.f + o));
@@ -243,9 +248,9 @@ __global__ void __launch_bounds__(NT, 2) k_mg_tile(TileArgs a) {
     const int xcb = X0 >> 1, ycb = Y0 >> 1;
     for (int j = warp; j < LH / 2; j += NW) {
       const int yc = ycb + j, y = 2 * yc;
-      if (yc < 0 || yc >= a.hc) continue;
-      const bool y_e = y >= 2 && y <= h - 2; // rows of the even-y loops (:140,:146)
-      const bool y_o = y + 1 <= h - 3;       // rows of the odd-y loops  (:153,:161)
+      if (yc < a.c_lo || yc >= a.c_hi) continue;
+      const bool y_e = y >= 2 && y <= h - 2;                  // rows of the even-y loops (:140,:146)
+      const bool y_o = y + 1 <= h - 3 && yc + 1 < a.c_hi;     // rows of the odd-y loops  (:153,:161)
       const float *ecr = a.ec + (size_t)yc * a.pc;
       const uint8_t *mcr = a.maskc + (size_t)yc * a.pc;
       for (int k = lane; k < HW; k += 32) {
@@ -357,7 +362,7 @@ __global__ void __launch_bounds__(NT, 2) k_mg_tile(TileArgs a) {
     const int xc0 = x0 >> 1, yc0 = y0 >> 1;
     for (int j = warp; j < TY / 2; j += NW) {
       const int yc = yc0 + j;
-      if (yc >= a.hc) break;
+      if (yc >= a.hc || 2 * yc >= a.own_hi) break;
       const int ly = 2 * yc - Y0;
       for (int i = lane; i < TX / 2; i += 32) {
         const int xc = xc0 + i;
@@ -378,7 +383,7 @@ __global__ void __launch_bounds__(NT, 2) k_mg_tile(TileArgs a) {
   // ---- write the tile back (p ping-pong buffer), 128-bit stores ----
   for (int ly = HALO + warp; ly < HALO + TY; ly += NW) {
     const int gy = Y0 + ly;
-    if (gy >= h) break;
+    if (gy >= a.own_hi) break;
     const int pr = ly & 1;
     for (int qd = lane; qd < TX / 4; qd += 32) {
       const int lx = HALO + 4 * qd, gx = X0 + lx;
@@ -394,7 +399,7 @@ __global__ void __launch_bounds__(NT, 2) k_mg_tile(TileArgs a) {
   // the zero-gradient copy of the (now final) interior neighbour or, without
   // that BC and at the four corners, the unchanged input value ----
   const bool bx0 = x0 == 0, bx1 = (w - 1 >= x0 && w - 1 < x0 + TX);
-  const bool by0 = y0 == 0, by1 = (h - 1 >= y0 && h - 1 < y0 + TY);
+  const bool by0 = y0 == 0, by1 = (h - 1 >= y0 && h - 1 < y0 + TY && h - 1 < a.own_hi);
   if (bx0 || bx1 || by0 || by1) {
     __syncthreads();
     const int t = threadIdx.x;
@@ -405,7 +410,7 @@ __global__ void __launch_bounds__(NT, 2) k_mg_tile(TileArgs a) {
       const bool corner = (gx == 0 || gx == w - 1) && (gy == 0 || gy == h - 1);
       a.p_out[(size_t)gy * a.pitch + gx] = (a.zgbc && !corner) ? cell(nx, ny) : orig(gx, gy);
     };
-    const int ty_hi = min(h, y0 + TY), tx_hi = min(w, x0 + TX);
+    const int ty_hi = min(a.own_hi, y0 + TY), tx_hi = min(w, x0 + TX);
     // columns first, rows second: at the corners both write orig()
     if (bx0)
       for (int gy = y0 + t; gy < ty_hi; gy += NT) put(0, gy, 1, gy);
@@ -421,14 +426,18 @@ __global__ void __launch_bounds__(NT, 2) k_mg_tile(TileArgs a) {
 // Stencil mask of a flag grid (layout: enum MB_* above; neighbours outside the
 // grid count as solid).  *nonbinary is raised if any flag is neither 0.0 nor 1.0
 // (then the bit form is not equivalent and the plain path is used).
-__global__ void k_make_mask(Grid flag, uint8_t *mask, int *nonbinary) {
+// Rows [r_lo, r_hi) are written; flag rows outside [st_lo, st_hi) are not stored
+// on this GPU and read as solid (the slab code refreshes those mask rows from
+// their owner afterwards).
+__global__ void k_make_mask(Grid flag, uint8_t *mask, int *nonbinary, int r_lo, int r_hi, int st_lo,
+                            int st_hi) {
   int x = blockIdx.x * blockDim.x + threadIdx.x;
-  int y = blockIdx.y * blockDim.y + threadIdx.y;
-  if (x >= flag.pitch || y >= flag.h) return;
+  int y = r_lo + blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= flag.pitch || y >= r_hi) return;
   unsigned m = 0;
   if (x < flag.w) {
     auto bit = [&](int xx, int yy) -> unsigned {
-      if (xx < 0 || yy < 0 || xx >= flag.w || yy >= flag.h) return 0u;
+      if (xx < 0 || yy < st_lo || xx >= flag.w || yy >= st_hi) return 0u;
       return flag.at(xx, yy) != 0.0f ? 1u : 0u;
     };
     float c = flag.at(x, y);
@@ -457,31 +466,46 @@ static void launch_tile(const TileArgs &a, cudaStream_t stream, LaunchCounter *l
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  dim3 grid(ceil_div(a.w, TX), ceil_div(a.h, TY));
+  dim3 grid(ceil_div(a.w, TX), ceil_div(a.own_hi - a.own_lo, TY));
   UBGL_LAUNCH(lc, kind, level, stream, k_mg_tile<S, MODE, LH, NT><<<grid, NT, smem, stream>>>(a));
 }
 
 constexpr int LH_MAIN = 80, NT_MAIN = 256;
 
+static void set_rows(TileArgs &a, const Rows *rows) {
+  if (rows) {
+    a.st_lo = rows->st_lo; a.st_hi = rows->st_hi; a.own_lo = rows->own_lo; a.own_hi = rows->own_hi;
+  } else {
+    a.st_lo = 0; a.st_hi = a.h; a.own_lo = 0; a.own_hi = a.h;
+  }
+  a.c_lo = 0; a.c_hi = a.hc;
+}
+
 void launch_mg_pre(const float *p_in, float *p_out, const Grid &f, const uint8_t *mask,
                    const Grid &rc, float hh, bool zgbc, cudaStream_t stream, LaunchCounter *lc,
-                   int level) {
+                   int level, const Rows *rows) {
   TileArgs a{};
   a.p_in = p_in; a.p_out = p_out; a.f = f.d; a.mask = mask;
   a.w = f.w; a.h = f.h; a.pitch = f.pitch;
   a.rc = rc.d; a.wc = rc.w; a.hc = rc.h; a.pc = rc.pitch;
   a.hh = hh; a.ihsq = 1.0f / hh / hh; a.zgbc = zgbc ? 1 : 0;
+  set_rows(a, rows);
   launch_tile<3, MODE_PRE, LH_MAIN, NT_MAIN>(a, stream, lc, K_MG_PRE, level);
 }
 
 void launch_mg_post(const float *p_in, float *p_out, const Grid &f, const uint8_t *mask,
                     const Grid &ec, const uint8_t *maskc, float hh, bool zgbc, cudaStream_t stream,
-                    LaunchCounter *lc, int level) {
+                    LaunchCounter *lc, int level, const Rows *rows, const Rows *crows) {
   TileArgs a{};
   a.p_in = p_in; a.p_out = p_out; a.f = f.d; a.mask = mask;
   a.w = f.w; a.h = f.h; a.pitch = f.pitch;
   a.ec = ec.d; a.maskc = maskc; a.wc = ec.w; a.hc = ec.h; a.pc = ec.pitch;
   a.hh = hh; a.ihsq = 1.0f / hh / hh; a.zgbc = zgbc ? 1 : 0;
+  set_rows(a, rows);
+  if (crows) {
+    a.c_lo = crows->st_lo;
+    a.c_hi = crows->st_hi;
+  }
   launch_tile<3, MODE_POST, LH_MAIN, NT_MAIN>(a, stream, lc, K_MG_POST, level);
 }
 
@@ -491,13 +515,16 @@ void launch_mg_smooth5(float *p_out, const Grid &f, const uint8_t *mask, float h
   a.p_in = nullptr; a.p_out = p_out; a.f = f.d; a.mask = mask;
   a.w = f.w; a.h = f.h; a.pitch = f.pitch;
   a.hh = hh; a.ihsq = 1.0f / hh / hh; a.zgbc = 0;
+  set_rows(a, nullptr);
   launch_tile<5, MODE_SMOOTH, LH_MAIN, NT_MAIN>(a, stream, lc, K_MG_COARSE, level);
 }
 
 void launch_make_mask(const Grid &flag, uint8_t *mask, int *d_nonbinary, cudaStream_t stream,
-                      LaunchCounter *lc, int level) {
-  dim3 b(32, 8), g(ceil_div(flag.pitch, 32), ceil_div(flag.h, 8));
-  UBGL_LAUNCH(lc, K_COARSEN, level, stream, k_make_mask<<<g, b, 0, stream>>>(flag, mask, d_nonbinary));
+                      LaunchCounter *lc, int level, const Rows *rows, const Rows *crows) {
+  const int r_lo = rows ? rows->own_lo : 0, r_hi = rows ? rows->own_hi : flag.h;
+  const int st_lo = rows ? rows->st_lo : 0, st_hi = rows ? rows->st_hi : flag.h;
+  dim3 b(32, 8), g(ceil_div(flag.pitch, 32), ceil_div(r_hi - r_lo, 8));
+  UBGL_LAUNCH(lc, K_COARSEN, level, stream, k_make_mask<<<g, b, 0, stream>>>(flag, mask, d_nonbinary, r_lo, r_hi, st_lo, st_hi));
 }
 
 } // namespace ubgl

@@ -2,6 +2,7 @@
 // simulation.hpp / interpolators.hpp of te42kyfo/ubootgl (file:line per kernel).
 #include "sim.cuh"
 #include "stencils.cuh"
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <utility>
@@ -117,12 +118,25 @@ __device__ __forceinline__ void cr_weights(float t, float &w0, float &w1, float 
 // bicubicSample (interpolators.hpp:92-206): clamp to [3, w-3] x [3, h-3]
 // (:94-97), truncate (:99-103), 4x4 taps at rows iy-1..iy+2 / cols ix-1..ix+2,
 // vertical Hermite per column first, then horizontal (:132-204).
+// Row-slab runs (csrc/slab.cu) store only rows [lo, hi) of a field: a back-trace
+// that leaves them raises *err and is pulled back inside (the result of that
+// face is then wrong, which the step reports as an error -- never silently).
+struct TapRows {
+  int lo, hi;
+  int *err; // nullptr: every row is stored (single GPU)
+};
+
 __device__ __forceinline__ float bicubic(const float *__restrict__ g, int pitch, int w, int h,
-                                         float cx, float cy) {
+                                         float cx, float cy, const TapRows &tr) {
   cx = fmaxf(fminf(cx, (float)w - 3.0f), 3.0f);
   cy = fmaxf(fminf(cy, (float)h - 3.0f), 3.0f);
-  const int icx = (int)cx, icy = (int)cy;
-  const float stx = __fsub_rn(cx, (float)icx), sty = __fsub_rn(cy, (float)icy);
+  const int icx = (int)cx;
+  int icy = (int)cy;
+  if (tr.err && (icy - 1 < tr.lo || icy + 2 >= min(tr.hi, h))) {
+    *tr.err = 1;
+    icy = max(tr.lo + 1, min(icy, min(tr.hi, h) - 3));
+  }
+  const float stx = __fsub_rn(cx, (float)icx), sty = __fsub_rn(cy, truncf(cy));
   float y0, y1, y2, y3, x0, x1, x2, x3;
   cr_weights(sty, y0, y1, y2, y3);
   cr_weights(stx, x0, x1, x2, x3);
@@ -146,11 +160,12 @@ __device__ __forceinline__ float bicubic(const float *__restrict__ g, int pitch,
 //  * octets exist only while x0 < vx.width - 8 (:248) -> last columns untouched;
 //  * whole-octet skip unless some lane has flag(x-1+i,y)+flag(x+i,y) == 2 (:254);
 //  * untouched entries keep whatever the back buffer holds.
-__global__ void k_advect_vx(Grid vx, Grid vy, Grid vxb, Grid flag, float half, float full) {
+__global__ void k_advect_vx(Grid vx, Grid vy, Grid vxb, Grid flag, float half, float full,
+                            int y_lo, int y_hi, TapRows tr) {
   const int lane = threadIdx.x;
   const int xi = 1 + blockIdx.x * 32 + lane;
-  const int y = 1 + blockIdx.y * blockDim.y + threadIdx.y;
-  const bool row_ok = y < vx.h - 1;
+  const int y = y_lo + blockIdx.y * blockDim.y + threadIdx.y; // y_lo >= 1, y_hi <= H-1
+  const bool row_ok = y < y_hi;
   const int x0 = xi - (lane & 7);
   const bool oct_ok = row_ok && (x0 < vx.w - 8);
   bool cond = false;
@@ -170,10 +185,10 @@ __global__ void k_advect_vx(Grid vx, Grid vy, Grid vxb, Grid flag, float half, f
                                   __fadd_rn(vy.at(xi + 1, y), vy.at(xi + 1, y - 1))),
                         0.25f);
   float midx = __fmaf_rn(-vx1, half, posx), midy = __fmaf_rn(-vy1, half, posy);
-  float vx2 = bicubic(vx.d, vx.pitch, vx.w, vx.h, __fsub_rn(midx, 0.5f), midy);
-  float vy2 = bicubic(vy.d, vy.pitch, vy.w, vy.h, midx, __fsub_rn(midy, 0.5f));
+  float vx2 = bicubic(vx.d, vx.pitch, vx.w, vx.h, __fsub_rn(midx, 0.5f), midy, tr);
+  float vy2 = bicubic(vy.d, vy.pitch, vy.w, vy.h, midx, __fsub_rn(midy, 0.5f), tr);
   float endx = __fmaf_rn(-vx2, full, posx), endy = __fmaf_rn(-vy2, full, posy);
-  float xvel = bicubic(vx.d, vx.pitch, vx.w, vx.h, __fsub_rn(endx, 0.5f), endy);
+  float xvel = bicubic(vx.d, vx.pitch, vx.w, vx.h, __fsub_rn(endx, 0.5f), endy, tr);
   vxb.at(xi, y) = __fmul_rn(__fmul_rn(xvel, f0), f1);
 }
 
@@ -188,12 +203,12 @@ __device__ __forceinline__ float vx_flat(const Grid &vx, int x, int y) {
   }
   return vx.at(x, y);
 }
-__global__ void k_advect_vy(Grid vx, Grid vy, Grid vyb, Grid flag, int rows, float half,
-                            float full) {
+__global__ void k_advect_vy(Grid vx, Grid vy, Grid vyb, Grid flag, float half, float full,
+                            int y_lo, int y_hi, TapRows tr) {
   const int lane = threadIdx.x;
   const int xi = 1 + blockIdx.x * 32 + lane;
-  const int y = 1 + blockIdx.y * blockDim.y + threadIdx.y;
-  const bool row_ok = y < rows - 1; // rows = vx.height: y in [1, H-2]
+  const int y = y_lo + blockIdx.y * blockDim.y + threadIdx.y;
+  const bool row_ok = y < y_hi; // y in [1, H-2] like the vx loop (simulation.cpp:247)
   const int x0 = xi - (lane & 7);
   const bool oct_ok = row_ok && (x0 < vy.w - 8);
   bool cond = false;
@@ -213,10 +228,10 @@ __global__ void k_advect_vy(Grid vx, Grid vy, Grid vyb, Grid flag, int rows, flo
                                   __fadd_rn(vx_flat(vx, xi + 1, y), vx_flat(vx, xi + 1, y - 1))),
                         0.25f);
   float midx = __fmaf_rn(-vx1, half, posx), midy = __fmaf_rn(-vy1, half, posy);
-  float vx2 = bicubic(vx.d, vx.pitch, vx.w, vx.h, __fsub_rn(midx, 0.5f), midy);
-  float vy2 = bicubic(vy.d, vy.pitch, vy.w, vy.h, midx, __fsub_rn(midy, 0.5f));
+  float vx2 = bicubic(vx.d, vx.pitch, vx.w, vx.h, __fsub_rn(midx, 0.5f), midy, tr);
+  float vy2 = bicubic(vy.d, vy.pitch, vy.w, vy.h, midx, __fsub_rn(midy, 0.5f), tr);
   float endx = __fmaf_rn(-vx2, full, posx), endy = __fmaf_rn(-vy2, full, posy);
-  float yvel = bicubic(vy.d, vy.pitch, vy.w, vy.h, endx, __fsub_rn(endy, 0.5f));
+  float yvel = bicubic(vy.d, vy.pitch, vy.w, vy.h, endx, __fsub_rn(endy, 0.5f), tr);
   vyb.at(xi, y) = __fmul_rn(__fmul_rn(yvel, f0), f1);
 }
 
@@ -231,15 +246,20 @@ __global__ void k_divergence(Grid vx, Grid vy, Grid f, float ih) {
 }
 
 // sinks (simulation.cpp:173-182): 3x3 stamps, in list order (later sinks win)
-__global__ void k_stamp_sinks(Grid f, const float *sinks, int n) {
+__global__ void k_stamp_sinks(Grid f, const float *sinks, int n, int y_lo, int y_hi) {
   int dx = (int)(threadIdx.x % 3) - 1, dy = (int)(threadIdx.x / 3) - 1;
   for (int k = 0; k < n; k++) {
     if (threadIdx.x < 9) {
       int ix = (int)sinks[3 * k], iy = (int)sinks[3 * k + 1];
-      f.at(ix + dx, iy + dy) = sinks[3 * k + 2];
+      if (iy + dy >= y_lo && iy + dy < y_hi) f.at(ix + dx, iy + dy) = sinks[3 * k + 2];
     }
     __syncthreads();
   }
+}
+
+void launch_stamp_sinks(const Grid &f, const float *d_sinks, int n, int y_lo, int y_hi,
+                        cudaStream_t stream, LaunchCounter *lc) {
+  UBGL_LAUNCH(lc, K_SINKS, LVL, stream, k_stamp_sinks<<<1, 32, 0, stream>>>(f, d_sinks, n, y_lo, y_hi));
 }
 
 // setPBC (simulation.cpp:36-45): columns for all y, then rows for all x.
@@ -408,13 +428,25 @@ void DeviceSim::diffuse() {
   }
 }
 
+void launch_advect(const Grid &vx, const Grid &vy, const Grid &vxbk, const Grid &vybk,
+                   const Grid &flag, float half, float full, int y_lo, int y_hi, int st_lo, int st_hi,
+                   int *err, cudaStream_t stream, LaunchCounter *lc) {
+  const int W = flag.w, H = flag.h;
+  y_lo = std::max(y_lo, 1);
+  y_hi = std::min(y_hi, H - 1);
+  if (y_hi <= y_lo) return;
+  TapRows tr{st_lo, st_hi, err};
+  dim3 b(32, 8);
+  dim3 g(ceil_div(W - 2, 32), ceil_div(y_hi - y_lo, 8));
+  UBGL_LAUNCH(lc, K_ADVECT, LVL, stream, k_advect_vx<<<g, b, 0, stream>>>(vx, vy, vxbk, flag, half, full, y_lo, y_hi, tr));
+  UBGL_LAUNCH(lc, K_ADVECT, LVL, stream, k_advect_vy<<<g, b, 0, stream>>>(vx, vy, vybk, flag, half, full, y_lo, y_hi, tr));
+}
+
 void DeviceSim::advect() {
   float ih = 1.0f / h;
   float half = 0.5f * dt * ih, full = dt * ih; // simulation.cpp:276,286
-  dim3 b(32, 8);
-  dim3 g(ceil_div(W - 2, 32), ceil_div(H - 2, 8));
-  UBGL_LAUNCH(&lc, K_ADVECT, LVL, stream, k_advect_vx<<<g, b, 0, stream>>>(vxb[ixf], vyb[iyf], vxb[ixb], flag, half, full));
-  UBGL_LAUNCH(&lc, K_ADVECT, LVL, stream, k_advect_vy<<<g, b, 0, stream>>>(vxb[ixf], vyb[iyf], vyb[iyb], flag, H, half, full));
+  launch_advect(vxb[ixf], vyb[iyf], vxb[ixb], vyb[iyb], flag, half, full, 1, H - 1, 0, H, nullptr,
+                stream, &lc);
   std::swap(ixf, ixb);
   std::swap(iyf, iyb);
 }
@@ -458,7 +490,7 @@ void DeviceSim::project_sinks() {
     UBGL_CUDA(cudaMemcpyAsync(d_sinks, stamps.data(), sizeof(float) * stamps.size(),
                               cudaMemcpyHostToDevice, stream));
     UBGL_CUDA(cudaStreamSynchronize(stream)); // stamps is a stack-lifetime staging buffer
-    UBGL_LAUNCH(&lc, K_SINKS, LVL, stream, k_stamp_sinks<<<1, 32, 0, stream>>>(f, d_sinks, n));
+    launch_stamp_sinks(f, d_sinks, n, 0, H, stream, &lc);
   }
 }
 

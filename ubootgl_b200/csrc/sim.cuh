@@ -12,6 +12,54 @@ enum { F_FLAG = 0, F_VX, F_VY, F_VXB, F_VYB, F_P, F_F, F_VX_ACCUM, F_VY_ACCUM, F
        F_VX_CURRENT, F_VY_CURRENT, F_COUNT };
 enum { ST_ACCUM = 0, ST_DIFFUSE, ST_ADVECT, ST_SETVBCS, ST_PROJECT, ST_SAVE, ST_COUNT };
 
+// ---- kernel argument blocks and launchers shared by DeviceSim and the slab
+// ---- driver (definitions in sim_fused.cu / sim.cu) ----
+struct PrestepArgs {
+  const float *A;   // front buffer (input)
+  const float *K;   // buffer whose BORDER cells are the "kept" values of the
+                    // first setVBCs after pass 1 (vx: the old back buffer)
+  float *acc;       // accumulator (read; zeroed later by k_divergence4)
+  float *B;         // old back buffer: receives the pass-1 result (interior)
+  float *Cout;      // receives the pass-2 result (interior) + border values
+  const uint8_t *mask;
+  int gw, gh;       // size of this staggered grid
+  int H;            // rows of the cell grid (mask)
+  int pitch;
+  float a, rden;
+  int bcLo, bcHi;   // BC of the column sides (W, E)
+  int bcS, bcN;
+  int st_lo, st_hi, own_lo, own_hi; // row slab (cell-grid rows), see common.cuh Rows
+};
+
+
+struct BorderArgs {
+  Grid xf, xb, yf, yb; // velocity front / back buffers (both are written)
+  Grid xc, yc;         // optional third copy (vx_current / vy_current), d == nullptr: none
+  Grid p;              // optional: setPBC on p, d == nullptr: none
+  int bcW, bcE, bcN, bcS;
+  int y_lo, y_hi;   // rows whose W/E border cells are set here
+  int do_s, do_n;   // this GPU owns the bottom / top border row
+};
+
+
+void launch_prestep(int comp, const PrestepArgs &g, cudaStream_t stream, LaunchCounter *lc);
+void launch_borders(const BorderArgs &g, cudaStream_t stream, LaunchCounter *lc);
+void launch_pbc(const Grid &p, int bcW, int bcE, int bcN, int bcS, int y_lo, int y_hi, bool do_s,
+                bool do_n, cudaStream_t stream, LaunchCounter *lc);
+void launch_divergence4(const Grid &vx, const Grid &vy, const Grid &f, const Grid &ax, const Grid &ay,
+                        float ih, int y_lo, int y_hi, cudaStream_t stream, LaunchCounter *lc);
+void launch_gradient_save(const Grid &vx, const Grid &vy, const Grid &p, const uint8_t *mask,
+                          const Grid &cx, const Grid &cy, float ih, int y_lo, int y_hi,
+                          cudaStream_t stream, LaunchCounter *lc);
+// advect (sim.cu): faces of rows [y_lo, y_hi); tap rows outside [st_lo, st_hi)
+// raise *err (slab mode: the back-trace left the halo)
+void launch_advect(const Grid &vx, const Grid &vy, const Grid &vxb, const Grid &vyb, const Grid &flag,
+                   float half, float full, int y_lo, int y_hi, int st_lo, int st_hi, int *err,
+                   cudaStream_t stream, LaunchCounter *lc);
+// sinks (sim.cu): 3x3 stamps restricted to rows [y_lo, y_hi)
+void launch_stamp_sinks(const Grid &f, const float *d_sinks, int n, int y_lo, int y_hi,
+                        cudaStream_t stream, LaunchCounter *lc);
+
 struct Sink {
   float x, y, z;
 };

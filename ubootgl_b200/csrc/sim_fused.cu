@@ -17,6 +17,7 @@
 // the plain path (tests/test_gpu_fused.py).
 #include "sim.cuh"
 #include "stencils.cuh"
+#include <algorithm>
 
 namespace ubgl {
 
@@ -31,22 +32,6 @@ constexpr int PTY = 32;        // tile height
 constexpr int PWH = PTY + 4;   // window height (halo 2)
 constexpr int PRS = PW + 8;    // shared row stride, data at column 4
 constexpr int PNT = 256;
-
-struct PrestepArgs {
-  const float *A;   // front buffer (input)
-  const float *K;   // buffer whose BORDER cells are the "kept" values of the
-                    // first setVBCs after pass 1 (vx: the old back buffer)
-  float *acc;       // accumulator (read; zeroed later by k_divergence4)
-  float *B;         // old back buffer: receives the pass-1 result (interior)
-  float *Cout;      // receives the pass-2 result (interior) + border values
-  const uint8_t *mask;
-  int gw, gh;       // size of this staggered grid
-  int H;            // rows of the cell grid (mask)
-  int pitch;
-  float a, rden;
-  int bcLo, bcHi;   // BC of the column sides (W, E)
-  int bcS, bcN;
-};
 
 struct PrestepSmem {
   float V[PWH][PRS]; // v0 = front + accum, later the pass-2 result
@@ -69,9 +54,10 @@ template <int COMP> __global__ void __launch_bounds__(PNT) k_prestep(PrestepArgs
   PrestepSmem &sm = *reinterpret_cast<PrestepSmem *>(smem_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int NW = PNT / 32;
-  const int x0 = blockIdx.x * PTX, y0 = blockIdx.y * PTY;
+  const int x0 = blockIdx.x * PTX, y0 = g.own_lo + blockIdx.y * PTY;
   const int X0 = x0 - 4, Y0 = y0 - 2;
   const int gw = g.gw, gh = g.gh;
+  const int s_hi = min(gh, g.st_hi), m_hi = min(g.H, g.st_hi), o_hi = min(gh, g.own_hi);
 
   auto interior = [&](int gx, int gy) { return gx >= 1 && gx <= gw - 2 && gy >= 1 && gy <= gh - 2; };
 
@@ -80,9 +66,9 @@ template <int COMP> __global__ void __launch_bounds__(PNT) k_prestep(PrestepArgs
     const int gy = Y0 + r, gx = X0 + 4 * lane;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f), k = v;
     uchar4 m = make_uchar4(0, 0, 0, 0);
-    if (gy >= 0 && gx >= 0 && gx < g.pitch) {
+    if (gy >= g.st_lo && gx >= 0 && gx < g.pitch) {
       const size_t o = (size_t)gy * g.pitch + gx;
-      if (gy < gh) {
+      if (gy < s_hi) {
         v = *reinterpret_cast<const float4 *>(g.A + o);
         const bool rowin = gy >= 1 && gy <= gh - 2;
         if (rowin) {
@@ -96,7 +82,7 @@ template <int COMP> __global__ void __launch_bounds__(PNT) k_prestep(PrestepArgs
         if (COMP == 0 && (!rowin || gx == 0 || (gw - 1 >= gx && gw - 1 <= gx + 3)))
           k = *reinterpret_cast<const float4 *>(g.K + o);
       }
-      if (gy < g.H) m = __ldg(reinterpret_cast<const uchar4 *>(g.mask + o));
+      if (gy < m_hi) m = __ldg(reinterpret_cast<const uchar4 *>(g.mask + o));
     }
     *reinterpret_cast<float4 *>(&sm.V[r][4 + 4 * lane]) = v;
     *reinterpret_cast<float4 *>(&sm.D[r][4 + 4 * lane]) = k;
@@ -222,7 +208,7 @@ template <int COMP> __global__ void __launch_bounds__(PNT) k_prestep(PrestepArgs
   for (int i = threadIdx.x; i < PTY * (PTX / 4); i += PNT) {
     const int r = 2 + i / (PTX / 4), c = 8 + 4 * (i % (PTX / 4));
     const int gy = Y0 + r, gx = X0 + c - 4;
-    if (gy >= gh || gx >= gw) continue;
+    if (gy >= o_hi || gx >= gw) continue;
     const size_t o = (size_t)gy * g.pitch + gx;
     const float4 d1 = *reinterpret_cast<const float4 *>(&sm.D[r][c]);
     const float4 d2 = *reinterpret_cast<const float4 *>(&sm.V[r][c]);
@@ -250,13 +236,6 @@ template <int COMP> __global__ void __launch_bounds__(PNT) k_prestep(PrestepArgs
 // separate launches: the row phase reads the column results at x = 0 / w-1 and
 // wins at the corners, exactly as the reference's loop order.
 // ---------------------------------------------------------------------------
-struct BorderArgs {
-  Grid xf, xb, yf, yb; // velocity front / back buffers (both are written)
-  Grid xc, yc;         // optional third copy (vx_current / vy_current), d == nullptr: none
-  Grid p;              // optional: setPBC on p, d == nullptr: none
-  int bcW, bcE, bcN, bcS;
-};
-
 __device__ __forceinline__ void put3(const Grid &a, const Grid &b, const Grid &c, int x, int y, float v) {
   a.at(x, y) = v;
   b.at(x, y) = v;
@@ -264,7 +243,8 @@ __device__ __forceinline__ void put3(const Grid &a, const Grid &b, const Grid &c
 }
 
 __global__ void k_vbc_cols(BorderArgs g) {
-  const int y = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = g.y_lo + blockIdx.x * blockDim.x + threadIdx.x;
+  if (y >= g.y_hi) return;
   if (y < g.xf.h) {
     const int w = g.xf.w;
     put3(g.xf, g.xb, g.xc, 0, y, vbc_par(g.bcW, g.xf.at(1, y), g.xf.at(0, y)));
@@ -285,17 +265,17 @@ __global__ void k_vbc_rows(BorderArgs g) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   if (x < g.xf.w) {
     const int h = g.xf.h;
-    put3(g.xf, g.xb, g.xc, x, 0, vbc_per(g.bcS, g.xf.at(x, 1), g.xf.at(x, 0)));
-    put3(g.xf, g.xb, g.xc, x, h - 1, vbc_per(g.bcN, g.xf.at(x, h - 2), g.xf.at(x, h - 1)));
+    if (g.do_s) put3(g.xf, g.xb, g.xc, x, 0, vbc_per(g.bcS, g.xf.at(x, 1), g.xf.at(x, 0)));
+    if (g.do_n) put3(g.xf, g.xb, g.xc, x, h - 1, vbc_per(g.bcN, g.xf.at(x, h - 2), g.xf.at(x, h - 1)));
   }
   if (x < g.yf.w) {
     const int h = g.yf.h;
-    put3(g.yf, g.yb, g.yc, x, 0, vbc_par(g.bcS, g.yf.at(x, 1), g.yf.at(x, 0)));
-    put3(g.yf, g.yb, g.yc, x, h - 1, vbc_par(g.bcN, g.yf.at(x, h - 2), g.yf.at(x, h - 1)));
+    if (g.do_s) put3(g.yf, g.yb, g.yc, x, 0, vbc_par(g.bcS, g.yf.at(x, 1), g.yf.at(x, 0)));
+    if (g.do_n) put3(g.yf, g.yb, g.yc, x, h - 1, vbc_par(g.bcN, g.yf.at(x, h - 2), g.yf.at(x, h - 1)));
   }
   if (g.p.d && x < g.p.w) {
-    g.p.at(x, 0) = single_pbc(g.bcS, g.p.at(x, 1));
-    g.p.at(x, g.p.h - 1) = single_pbc(g.bcN, g.p.at(x, g.p.h - 2));
+    if (g.do_s) g.p.at(x, 0) = single_pbc(g.bcS, g.p.at(x, 1));
+    if (g.do_n) g.p.at(x, g.p.h - 1) = single_pbc(g.bcN, g.p.at(x, g.p.h - 2));
   }
 }
 
@@ -303,11 +283,12 @@ __global__ void k_vbc_rows(BorderArgs g) {
 // divergence (simulation.cpp:166-171) + zeroing of the accumulator interiors
 // (:384,:392).  One thread = 4 consecutive cells of a row.
 // ---------------------------------------------------------------------------
-__global__ void k_divergence4(Grid vx, Grid vy, Grid f, Grid ax, Grid ay, float ih) {
+__global__ void k_divergence4(Grid vx, Grid vy, Grid f, Grid ax, Grid ay, float ih, int y_lo,
+                              int y_hi) {
   const int x = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
-  const int y = 1 + blockIdx.y * blockDim.y + threadIdx.y;
+  const int y = y_lo + blockIdx.y * blockDim.y + threadIdx.y; // y_lo >= 1, y_hi <= H-1
   const int W = f.w, H = f.h;
-  if (x >= W - 1 || y >= H - 1) return;
+  if (x >= W - 1 || y >= y_hi) return;
   const size_t o = (size_t)y * f.pitch + x; // all grids share the pitch
   const float4 a = *reinterpret_cast<const float4 *>(vx.d + o);
   const float aw = x > 0 ? vx.d[o - 1] : 0.0f;
@@ -321,14 +302,17 @@ __global__ void k_divergence4(Grid vx, Grid vy, Grid f, Grid ax, Grid ay, float 
   const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
   if (x >= 1 && x + 3 <= W - 3 && y <= H - 3) { // every cell interior in f, vx and vy
     *reinterpret_cast<float4 *>(f.d + o) = make_float4(r[0], r[1], r[2], r[3]);
-    *reinterpret_cast<float4 *>(ax.d + o) = z;
-    *reinterpret_cast<float4 *>(ay.d + o) = z;
+    if (ax.d) {
+      *reinterpret_cast<float4 *>(ax.d + o) = z;
+      *reinterpret_cast<float4 *>(ay.d + o) = z;
+    }
   } else {
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       const int xx = x + j;
       if (xx < 1 || xx > W - 2) continue;
       f.d[o + j] = r[j];
+      if (!ax.d) continue;
       if (xx <= W - 3) ax.d[o + j] = 0.0f; // vx interior: 1..W-3 x 1..H-2
       if (y <= H - 3) ay.d[o + j] = 0.0f;  // vy interior: 1..W-2 x 1..H-3
     }
@@ -341,11 +325,11 @@ __global__ void k_divergence4(Grid vx, Grid vy, Grid f, Grid ax, Grid ay, float 
 // are written by the setVBCs kernels that follow.
 // ---------------------------------------------------------------------------
 __global__ void k_gradient_save(Grid vx, Grid vy, Grid p, const uint8_t *mask, Grid cx, Grid cy,
-                                float ih) {
+                                float ih, int y_lo, int y_hi) {
   const int x = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
-  const int y = 1 + blockIdx.y * blockDim.y + threadIdx.y;
+  const int y = y_lo + blockIdx.y * blockDim.y + threadIdx.y; // y_lo >= 1, y_hi <= H-1
   const int W = p.w, H = p.h;
-  if (x >= W - 1 || y >= H - 1) return;
+  if (x >= W - 1 || y >= y_hi) return;
   const size_t o = (size_t)y * p.pitch + x;
   const float4 pc = *reinterpret_cast<const float4 *>(p.d + o);
   const float4 pn = *reinterpret_cast<const float4 *>(p.d + o + p.pitch);
@@ -393,11 +377,9 @@ __global__ void k_gradient_save(Grid vx, Grid vy, Grid p, const uint8_t *mask, G
 }
 
 // ---------------------------------------------------------------------------
-// launchers (DeviceSim members)
+// launchers
 // ---------------------------------------------------------------------------
-void DeviceSim::fused_prestep() {
-  const float a = dt * mu * ((float)W - 1.0f) / pwidth; // simulation.cpp:105
-  const float rden = 1.0f / (1.0f + 4.0f * a);
+void launch_prestep(int comp, const PrestepArgs &g, cudaStream_t stream, LaunchCounter *lc) {
   static bool attr_set = false;
   if (!attr_set) {
     UBGL_CUDA(cudaFuncSetAttribute(k_prestep<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -406,21 +388,81 @@ void DeviceSim::fused_prestep() {
                                    (int)sizeof(PrestepSmem)));
     attr_set = true;
   }
+  const int rows = std::min(g.gh, g.own_hi) - g.own_lo;
+  if (rows <= 0) return;
+  dim3 grid(ceil_div(g.gw, PTX), ceil_div(rows, PTY));
+  if (comp == 0)
+    UBGL_LAUNCH(lc, K_PRESTEP, 0, stream, k_prestep<0><<<grid, PNT, sizeof(PrestepSmem), stream>>>(g));
+  else
+    UBGL_LAUNCH(lc, K_PRESTEP, 0, stream, k_prestep<1><<<grid, PNT, sizeof(PrestepSmem), stream>>>(g));
+}
+
+void launch_borders(const BorderArgs &g, cudaStream_t stream, LaunchCounter *lc) {
+  if (g.y_hi > g.y_lo)
+    UBGL_LAUNCH(lc, K_VBC, 0, stream, k_vbc_cols<<<ceil_div(g.y_hi - g.y_lo, 128), 128, 0, stream>>>(g));
+  if (g.do_s || g.do_n)
+    UBGL_LAUNCH(lc, K_VBC, 0, stream, k_vbc_rows<<<ceil_div(g.yf.w, 128), 128, 0, stream>>>(g));
+}
+
+// setPBC alone (simulation.cpp:36-45) for the slab driver
+__global__ void k_pbc_cols(Grid p, int bcW, int bcE, int y_lo, int y_hi) {
+  const int y = y_lo + blockIdx.x * blockDim.x + threadIdx.x;
+  if (y >= y_hi || y >= p.h) return;
+  p.at(0, y) = single_pbc(bcW, p.at(1, y));
+  p.at(p.w - 1, y) = single_pbc(bcE, p.at(p.w - 2, y));
+}
+__global__ void k_pbc_rows(Grid p, int bcS, int bcN, int do_s, int do_n) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= p.w) return;
+  if (do_s) p.at(x, 0) = single_pbc(bcS, p.at(x, 1));
+  if (do_n) p.at(x, p.h - 1) = single_pbc(bcN, p.at(x, p.h - 2));
+}
+void launch_pbc(const Grid &p, int bcW, int bcE, int bcN, int bcS, int y_lo, int y_hi, bool do_s,
+                bool do_n, cudaStream_t stream, LaunchCounter *lc) {
+  if (y_hi > y_lo)
+    UBGL_LAUNCH(lc, K_PBC, 0, stream, k_pbc_cols<<<ceil_div(y_hi - y_lo, 128), 128, 0, stream>>>(p, bcW, bcE, y_lo, y_hi));
+  if (do_s || do_n)
+    UBGL_LAUNCH(lc, K_PBC, 0, stream, k_pbc_rows<<<ceil_div(p.w, 128), 128, 0, stream>>>(p, bcS, bcN, do_s, do_n));
+}
+
+void launch_divergence4(const Grid &vx, const Grid &vy, const Grid &f, const Grid &ax, const Grid &ay,
+                        float ih, int y_lo, int y_hi, cudaStream_t stream, LaunchCounter *lc) {
+  y_lo = std::max(y_lo, 1);
+  y_hi = std::min(y_hi, f.h - 1);
+  if (y_hi <= y_lo) return;
+  dim3 b(32, 8), g(ceil_div(ceil_div(f.w - 1, 4), 32), ceil_div(y_hi - y_lo, 8));
+  UBGL_LAUNCH(lc, K_DIVERGENCE, 0, stream, k_divergence4<<<g, b, 0, stream>>>(vx, vy, f, ax, ay, ih, y_lo, y_hi));
+}
+
+void launch_gradient_save(const Grid &vx, const Grid &vy, const Grid &p, const uint8_t *mask,
+                          const Grid &cx, const Grid &cy, float ih, int y_lo, int y_hi,
+                          cudaStream_t stream, LaunchCounter *lc) {
+  y_lo = std::max(y_lo, 1);
+  y_hi = std::min(y_hi, p.h - 1);
+  if (y_hi <= y_lo) return;
+  dim3 b(32, 8), g(ceil_div(ceil_div(p.w - 1, 4), 32), ceil_div(y_hi - y_lo, 8));
+  UBGL_LAUNCH(lc, K_FINISH, 0, stream, k_gradient_save<<<g, b, 0, stream>>>(vx, vy, p, mask, cx, cy, ih, y_lo, y_hi));
+}
+
+// ---------------------------------------------------------------------------
+// DeviceSim members (single GPU: every row is stored and owned)
+// ---------------------------------------------------------------------------
+void DeviceSim::fused_prestep() {
+  const float a = dt * mu * ((float)W - 1.0f) / pwidth; // simulation.cpp:105
   PrestepArgs g{};
   g.mask = mg->mask0_ptr();
-  g.H = H; g.pitch = pitch; g.a = a; g.rden = rden;
+  g.H = H; g.pitch = pitch; g.a = a; g.rden = 1.0f / (1.0f + 4.0f * a);
   g.bcLo = bcW; g.bcHi = bcE; g.bcS = bcS; g.bcN = bcN;
+  g.st_lo = 0; g.st_hi = H; g.own_lo = 0; g.own_hi = H;
   // vx: A = front, B = back, Cout = the vx_current buffer; afterwards the roles
   // rotate: front <- Cout, back stays, vx_current <- A (dead until save)
   g.A = vxb[ixf].d; g.K = vxb[ixb].d; g.acc = vx_accum.d; g.B = vxb[ixb].d; g.Cout = vxb[ixc].d;
   g.gw = W - 1; g.gh = H;
-  dim3 gx(ceil_div(g.gw, PTX), ceil_div(g.gh, PTY));
-  UBGL_LAUNCH(&lc, K_PRESTEP, 0, stream, k_prestep<0><<<gx, PNT, sizeof(PrestepSmem), stream>>>(g));
+  launch_prestep(0, g, stream, &lc);
   std::swap(ixf, ixc);
   g.A = vyb[iyf].d; g.K = vyb[iyf].d; g.acc = vy_accum.d; g.B = vyb[iyb].d; g.Cout = vyb[iyc].d;
   g.gw = W; g.gh = H - 1;
-  dim3 gy(ceil_div(g.gw, PTX), ceil_div(g.gh, PTY));
-  UBGL_LAUNCH(&lc, K_PRESTEP, 0, stream, k_prestep<1><<<gy, PNT, sizeof(PrestepSmem), stream>>>(g));
+  launch_prestep(1, g, stream, &lc);
   std::swap(iyf, iyc);
 }
 
@@ -433,18 +475,17 @@ void DeviceSim::fused_borders(bool with_p, bool with_current) {
   }
   if (with_p) g.p = p;
   g.bcW = bcW; g.bcE = bcE; g.bcN = bcN; g.bcS = bcS;
-  UBGL_LAUNCH(&lc, K_VBC, 0, stream, k_vbc_cols<<<ceil_div(H, 128), 128, 0, stream>>>(g));
-  UBGL_LAUNCH(&lc, K_VBC, 0, stream, k_vbc_rows<<<ceil_div(W, 128), 128, 0, stream>>>(g));
+  g.y_lo = 0; g.y_hi = H; g.do_s = 1; g.do_n = 1;
+  launch_borders(g, stream, &lc);
 }
 
 void DeviceSim::fused_divergence() {
-  dim3 b(32, 8), g(ceil_div(ceil_div(W - 1, 4), 32), ceil_div(H - 2, 8));
-  UBGL_LAUNCH(&lc, K_DIVERGENCE, 0, stream, k_divergence4<<<g, b, 0, stream>>>(vxb[ixf], vyb[iyf], f, vx_accum, vy_accum, 1.0f / h));
+  launch_divergence4(vxb[ixf], vyb[iyf], f, vx_accum, vy_accum, 1.0f / h, 1, H - 1, stream, &lc);
 }
 
 void DeviceSim::fused_gradient_save() {
-  dim3 b(32, 8), g(ceil_div(ceil_div(W - 1, 4), 32), ceil_div(H - 2, 8));
-  UBGL_LAUNCH(&lc, K_FINISH, 0, stream, k_gradient_save<<<g, b, 0, stream>>>(vxb[ixf], vyb[iyf], p, mg->mask0_ptr(), vxb[ixc], vyb[iyc], 1.0f / h));
+  launch_gradient_save(vxb[ixf], vyb[iyf], p, mg->mask0_ptr(), vxb[ixc], vyb[iyc], 1.0f / h, 1, H - 1,
+                       stream, &lc);
 }
 
 } // namespace ubgl
