@@ -325,7 +325,7 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         return run_reference(args)
-    if args.gpus == 1:
+    if args.gpus == 1 and int(os.environ.get("WORLD_SIZE", "1")) == 1:
         return run_single_gpu(args, args.workload or "channel8192")
     from ubootgl_b200 import slab_bench
     return slab_bench.run(args, args.workload or "channel32768")

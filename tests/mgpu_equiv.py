@@ -3,7 +3,7 @@ reproduce the single-GPU step BIT FOR BIT (same kernels, same per-cell
 arithmetic; only the tile origins and the halo plumbing differ).
 
     python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 \
-        --master-port 29533 tests/mgpu_equiv.py [W H steps]
+        --master-port 29533 tests/mgpu_equiv.py [W H steps dt]
 Rank 0 prints "MGPU_EQUIV OK ..." and exits 0 on success.
 """
 import os
@@ -30,7 +30,8 @@ def main():
     torch.cuda.set_device(dev)
 
     c = cases.sim_case(W, H, seed=11, ndiscs=9, radius=H / 17.0)
-    dt = 0.002
+    # dt = 0.02 is CFL ~ 25-75: back-traces leave the 16 ghost rows and are served by peer loads
+    dt = float(sys.argv[4]) if len(sys.argv) > 4 else 0.002
     sinks = [[0.4, 0.4 * H / W, 120.0], [0.2, 0.7 * H / W, 60.0]]
     plan = u.slab_plan(W, H, world, rank)
     S = u.SlabSimulation(c["flag"][plan["st_lo"]:plan["st_hi"]], W, H, rank, world,
@@ -75,7 +76,7 @@ def main():
         if abs(resn - res1) > 1e-5 * max(res1, 1e-30):
             ok = False
             print(f"MISMATCH residual norm: slabs {resn} single {res1}", flush=True)
-        print(f"MGPU_EQUIV {'OK' if ok else 'FAIL'} {W}x{H} ranks={world} steps={steps} "
+        print(f"MGPU_EQUIV {'OK' if ok else 'FAIL'} {W}x{H} ranks={world} steps={steps} dt={dt} "
               f"dist_levels={plan['dist_levels']} exchanges={ex} halo_MB={hb / 1e6:.1f} "
               f"residual={resn:.6g}", flush=True)
     okt = slab_boot.allreduce_max(0.0 if ok else 1.0)

@@ -113,12 +113,12 @@ def test_one_rank_slab_equals_simulation(ubgl, W, H):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("nranks", [2, 4])
-def test_slabs_equal_single_gpu(ubgl, nranks):
+@pytest.mark.parametrize("nranks,dt", [(2, "0.002"), (2, "0.02"), (4, "0.002"), (4, "0.02")])
+def test_slabs_equal_single_gpu(ubgl, nranks, dt):
     if ubgl.lib.ubgl_device_count() < nranks:
         pytest.skip(f"needs {nranks} GPUs (run under gpurun --gpus {nranks})")
     cmd = ["timeout", "600", sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
            f"--nproc-per-node={nranks}", "--master-addr", "127.0.0.1", "--master-port", str(29540 + nranks),
-           os.path.join(ROOT, "tests", "mgpu_equiv.py"), "1000", "1536", "3"]
+           os.path.join(ROOT, "tests", "mgpu_equiv.py"), "1000", "1536", "3", dt]
     out = subprocess.run(cmd, capture_output=True, text=True, cwd=ROOT)
     assert out.returncode == 0 and "MGPU_EQUIV OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]

@@ -16,7 +16,12 @@ Grid alloc_grid(int w, int h, int pitch, bool zero) {
   g.h = h;
   g.pitch = pitch;
   UBGL_CUDA(cudaMalloc(&g.d, g.bytes()));
-  if (zero) UBGL_CUDA(cudaMemset(g.d, 0, g.bytes()));
+  if (zero) {
+    // device memsets are asynchronous and the library's streams are non-blocking: finish it
+    // before any stream can touch the array
+    UBGL_CUDA(cudaMemset(g.d, 0, g.bytes()));
+    UBGL_CUDA(cudaDeviceSynchronize());
+  }
   return g;
 }
 void free_grid(Grid &g) {
@@ -233,6 +238,7 @@ DeviceMG::DeviceMG(int W, int H, int device_, cudaStream_t stream_, LaunchCounte
   UBGL_CUDA(cudaMalloc(&mask0, (size_t)lv[0].pitch * lv[0].h));
   UBGL_CUDA(cudaMalloc(&d_nonbinary, sizeof(int)));
   UBGL_CUDA(cudaMemset(d_nonbinary, 0, sizeof(int)));
+  UBGL_CUDA(cudaDeviceSynchronize());
   for (size_t l = 1; l + 1 < lv.size(); l++) // all-ones coarse flags of MG(int,int)
     launch_make_mask(lv[l].flagc, lv[l].mask, d_nonbinary, stream, lc, (int)l);
   dim3 g = grd2d(W, H);

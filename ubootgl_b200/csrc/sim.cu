@@ -118,30 +118,50 @@ __device__ __forceinline__ void cr_weights(float t, float &w0, float &w1, float 
 // bicubicSample (interpolators.hpp:92-206): clamp to [3, w-3] x [3, h-3]
 // (:94-97), truncate (:99-103), 4x4 taps at rows iy-1..iy+2 / cols ix-1..ix+2,
 // vertical Hermite per column first, then horizontal (:132-204).
-// Row-slab runs (csrc/slab.cu) store only rows [lo, hi) of a field: a back-trace
-// that leaves them raises *err and is pulled back inside (the result of that
-// face is then wrong, which the step reports as an error -- never silently).
+// Row-slab runs (csrc/slab.cu) store only rows [lo, hi) of a field.  A tap row
+// outside them is read straight from the NEIGHBOUR's slab through its
+// NVLink-mapped arena (peer loads; NVSwitch makes every peer uniform, SURVEY.md
+// 8e), so the halo depth bounds nothing: any CFL works, the rare far tap just
+// costs an NVLink round trip.  The neighbour's front buffers are complete when
+// this kernel starts (its halo push is stream-ordered after them and was waited
+// for) and are not rewritten before the next exchange.  Only a tap beyond the
+// neighbour's own rows (back-trace longer than a whole slab) raises *err.
 struct TapRows {
-  int lo, hi;
-  int *err; // nullptr: every row is stored (single GPU)
+  int lo = 0, hi = 0;             // rows stored locally
+  int plo = 0, phi = 0;           // rows reachable through the neighbours [plo, phi)
+  const float *x_lo = nullptr, *x_hi = nullptr; // vx front of the lower / upper neighbour (virtual row 0)
+  const float *y_lo = nullptr, *y_hi = nullptr; // vy front likewise
+  int *err = nullptr;
 };
 
+template <bool SLAB>
 __device__ __forceinline__ float bicubic(const float *__restrict__ g, int pitch, int w, int h,
-                                         float cx, float cy, const TapRows &tr) {
+                                         float cx, float cy, const TapRows &tr,
+                                         const float *g_lo, const float *g_hi) {
   cx = fmaxf(fminf(cx, (float)w - 3.0f), 3.0f);
   cy = fmaxf(fminf(cy, (float)h - 3.0f), 3.0f);
   const int icx = (int)cx;
   int icy = (int)cy;
-  if (tr.err && (icy - 1 < tr.lo || icy + 2 >= min(tr.hi, h))) {
-    *tr.err = 1;
-    icy = max(tr.lo + 1, min(icy, min(tr.hi, h) - 3));
-  }
   const float stx = __fsub_rn(cx, (float)icx), sty = __fsub_rn(cy, truncf(cy));
   float y0, y1, y2, y3, x0, x1, x2, x3;
   cr_weights(sty, y0, y1, y2, y3);
   cr_weights(stx, x0, x1, x2, x3);
-  const float *r0 = g + ((icy - 1) * pitch + (icx - 1));
-  const float *r1 = r0 + pitch, *r2 = r1 + pitch, *r3 = r2 + pitch;
+  const float *r0, *r1, *r2, *r3;
+  if (SLAB && (icy - 1 < tr.lo || icy + 2 >= min(tr.hi, h))) {
+    if (icy - 1 < tr.plo || icy + 2 >= min(tr.phi, h)) {
+      *tr.err = 1;
+      icy = max(tr.plo + 1, min(icy, min(tr.phi, h) - 3));
+    }
+    const int hi = min(tr.hi, h);
+    auto rowp = [&](int y) {
+      const float *b = y < tr.lo ? g_lo : (y >= hi ? g_hi : g);
+      return b + ((size_t)y * pitch + (icx - 1));
+    };
+    r0 = rowp(icy - 1); r1 = rowp(icy); r2 = rowp(icy + 1); r3 = rowp(icy + 2);
+  } else {
+    r0 = g + ((icy - 1) * pitch + (icx - 1));
+    r1 = r0 + pitch; r2 = r1 + pitch; r3 = r2 + pitch;
+  }
   auto col = [&](int j) {
     float c = __fmul_rn(y0, __ldg(r0 + j));
     c = __fmaf_rn(y1, __ldg(r1 + j), c);
@@ -160,6 +180,7 @@ __device__ __forceinline__ float bicubic(const float *__restrict__ g, int pitch,
 //  * octets exist only while x0 < vx.width - 8 (:248) -> last columns untouched;
 //  * whole-octet skip unless some lane has flag(x-1+i,y)+flag(x+i,y) == 2 (:254);
 //  * untouched entries keep whatever the back buffer holds.
+template <bool SLAB>
 __global__ void k_advect_vx(Grid vx, Grid vy, Grid vxb, Grid flag, float half, float full,
                             int y_lo, int y_hi, TapRows tr) {
   const int lane = threadIdx.x;
@@ -185,10 +206,10 @@ __global__ void k_advect_vx(Grid vx, Grid vy, Grid vxb, Grid flag, float half, f
                                   __fadd_rn(vy.at(xi + 1, y), vy.at(xi + 1, y - 1))),
                         0.25f);
   float midx = __fmaf_rn(-vx1, half, posx), midy = __fmaf_rn(-vy1, half, posy);
-  float vx2 = bicubic(vx.d, vx.pitch, vx.w, vx.h, __fsub_rn(midx, 0.5f), midy, tr);
-  float vy2 = bicubic(vy.d, vy.pitch, vy.w, vy.h, midx, __fsub_rn(midy, 0.5f), tr);
+  float vx2 = bicubic<SLAB>(vx.d, vx.pitch, vx.w, vx.h, __fsub_rn(midx, 0.5f), midy, tr, tr.x_lo, tr.x_hi);
+  float vy2 = bicubic<SLAB>(vy.d, vy.pitch, vy.w, vy.h, midx, __fsub_rn(midy, 0.5f), tr, tr.y_lo, tr.y_hi);
   float endx = __fmaf_rn(-vx2, full, posx), endy = __fmaf_rn(-vy2, full, posy);
-  float xvel = bicubic(vx.d, vx.pitch, vx.w, vx.h, __fsub_rn(endx, 0.5f), endy, tr);
+  float xvel = bicubic<SLAB>(vx.d, vx.pitch, vx.w, vx.h, __fsub_rn(endx, 0.5f), endy, tr, tr.x_lo, tr.x_hi);
   vxb.at(xi, y) = __fmul_rn(__fmul_rn(xvel, f0), f1);
 }
 
@@ -203,6 +224,7 @@ __device__ __forceinline__ float vx_flat(const Grid &vx, int x, int y) {
   }
   return vx.at(x, y);
 }
+template <bool SLAB>
 __global__ void k_advect_vy(Grid vx, Grid vy, Grid vyb, Grid flag, float half, float full,
                             int y_lo, int y_hi, TapRows tr) {
   const int lane = threadIdx.x;
@@ -228,10 +250,10 @@ __global__ void k_advect_vy(Grid vx, Grid vy, Grid vyb, Grid flag, float half, f
                                   __fadd_rn(vx_flat(vx, xi + 1, y), vx_flat(vx, xi + 1, y - 1))),
                         0.25f);
   float midx = __fmaf_rn(-vx1, half, posx), midy = __fmaf_rn(-vy1, half, posy);
-  float vx2 = bicubic(vx.d, vx.pitch, vx.w, vx.h, __fsub_rn(midx, 0.5f), midy, tr);
-  float vy2 = bicubic(vy.d, vy.pitch, vy.w, vy.h, midx, __fsub_rn(midy, 0.5f), tr);
+  float vx2 = bicubic<SLAB>(vx.d, vx.pitch, vx.w, vx.h, __fsub_rn(midx, 0.5f), midy, tr, tr.x_lo, tr.x_hi);
+  float vy2 = bicubic<SLAB>(vy.d, vy.pitch, vy.w, vy.h, midx, __fsub_rn(midy, 0.5f), tr, tr.y_lo, tr.y_hi);
   float endx = __fmaf_rn(-vx2, full, posx), endy = __fmaf_rn(-vy2, full, posy);
-  float yvel = bicubic(vy.d, vy.pitch, vy.w, vy.h, endx, __fsub_rn(endy, 0.5f), tr);
+  float yvel = bicubic<SLAB>(vy.d, vy.pitch, vy.w, vy.h, endx, __fsub_rn(endy, 0.5f), tr, tr.y_lo, tr.y_hi);
   vyb.at(xi, y) = __fmul_rn(__fmul_rn(yvel, f0), f1);
 }
 
@@ -429,24 +451,33 @@ void DeviceSim::diffuse() {
 }
 
 void launch_advect(const Grid &vx, const Grid &vy, const Grid &vxbk, const Grid &vybk,
-                   const Grid &flag, float half, float full, int y_lo, int y_hi, int st_lo, int st_hi,
-                   int *err, cudaStream_t stream, LaunchCounter *lc) {
+                   const Grid &flag, float half, float full, int y_lo, int y_hi, const AdvectPeers *peers,
+                   cudaStream_t stream, LaunchCounter *lc) {
   const int W = flag.w, H = flag.h;
   y_lo = std::max(y_lo, 1);
   y_hi = std::min(y_hi, H - 1);
   if (y_hi <= y_lo) return;
-  TapRows tr{st_lo, st_hi, err};
   dim3 b(32, 8);
   dim3 g(ceil_div(W - 2, 32), ceil_div(y_hi - y_lo, 8));
-  UBGL_LAUNCH(lc, K_ADVECT, LVL, stream, k_advect_vx<<<g, b, 0, stream>>>(vx, vy, vxbk, flag, half, full, y_lo, y_hi, tr));
-  UBGL_LAUNCH(lc, K_ADVECT, LVL, stream, k_advect_vy<<<g, b, 0, stream>>>(vx, vy, vybk, flag, half, full, y_lo, y_hi, tr));
+  if (!peers) {
+    TapRows tr{};
+    UBGL_LAUNCH(lc, K_ADVECT, LVL, stream, k_advect_vx<false><<<g, b, 0, stream>>>(vx, vy, vxbk, flag, half, full, y_lo, y_hi, tr));
+    UBGL_LAUNCH(lc, K_ADVECT, LVL, stream, k_advect_vy<false><<<g, b, 0, stream>>>(vx, vy, vybk, flag, half, full, y_lo, y_hi, tr));
+    return;
+  }
+  TapRows tr;
+  tr.lo = peers->st_lo; tr.hi = peers->st_hi; tr.plo = peers->peer_lo; tr.phi = peers->peer_hi;
+  tr.x_lo = peers->vx_lo; tr.x_hi = peers->vx_hi; tr.y_lo = peers->vy_lo; tr.y_hi = peers->vy_hi;
+  tr.err = peers->err;
+  UBGL_LAUNCH(lc, K_ADVECT, LVL, stream, k_advect_vx<true><<<g, b, 0, stream>>>(vx, vy, vxbk, flag, half, full, y_lo, y_hi, tr));
+  UBGL_LAUNCH(lc, K_ADVECT, LVL, stream, k_advect_vy<true><<<g, b, 0, stream>>>(vx, vy, vybk, flag, half, full, y_lo, y_hi, tr));
 }
 
 void DeviceSim::advect() {
   float ih = 1.0f / h;
   float half = 0.5f * dt * ih, full = dt * ih; // simulation.cpp:276,286
-  launch_advect(vxb[ixf], vyb[iyf], vxb[ixb], vyb[iyb], flag, half, full, 1, H - 1, 0, H, nullptr,
-                stream, &lc);
+  launch_advect(vxb[ixf], vyb[iyf], vxb[ixb], vyb[iyb], flag, half, full, 1, H - 1, nullptr, stream,
+                &lc);
   std::swap(ixf, ixb);
   std::swap(iyf, iyb);
 }

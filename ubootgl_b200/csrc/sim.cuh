@@ -51,10 +51,16 @@ void launch_divergence4(const Grid &vx, const Grid &vy, const Grid &f, const Gri
 void launch_gradient_save(const Grid &vx, const Grid &vy, const Grid &p, const uint8_t *mask,
                           const Grid &cx, const Grid &cy, float ih, int y_lo, int y_hi,
                           cudaStream_t stream, LaunchCounter *lc);
-// advect (sim.cu): faces of rows [y_lo, y_hi); tap rows outside [st_lo, st_hi)
-// raise *err (slab mode: the back-trace left the halo)
+// advect (sim.cu): faces of rows [y_lo, y_hi).  Slab mode (peers != nullptr): tap
+// rows outside the locally stored [st_lo, st_hi) are loaded from the neighbours'
+// front buffers over NVLink; rows outside [peer_lo, peer_hi) raise *err.
+struct AdvectPeers {
+  int st_lo, st_hi, peer_lo, peer_hi;
+  const float *vx_lo, *vx_hi, *vy_lo, *vy_hi; // neighbours' vx / vy fronts (virtual row 0); null at the ends
+  int *err;
+};
 void launch_advect(const Grid &vx, const Grid &vy, const Grid &vxb, const Grid &vyb, const Grid &flag,
-                   float half, float full, int y_lo, int y_hi, int st_lo, int st_hi, int *err,
+                   float half, float full, int y_lo, int y_hi, const AdvectPeers *peers,
                    cudaStream_t stream, LaunchCounter *lc);
 // sinks (sim.cu): 3x3 stamps restricted to rows [y_lo, y_hi)
 void launch_stamp_sinks(const Grid &f, const float *d_sinks, int n, int y_lo, int y_hi,

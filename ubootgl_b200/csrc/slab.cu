@@ -205,7 +205,10 @@ SlabSim::SlabSim(const float *flag_slab, int W_, int H_, float pwidth_, float mu
   for (int l = 1; l < plan.levels; l++) bytes += lvl_bytes(l, l < plan.ndist, 4);
   arena_bytes = bytes;
   UBGL_CUDA(cudaMalloc(&arena, arena_bytes));
-  UBGL_CUDA(cudaMemset(arena, 0, arena_bytes));
+  // on OUR stream: a legacy-stream cudaMemset is asynchronous and does not order with a
+  // non-blocking stream -- it would race with the uploads below and zero fresh data
+  UBGL_CUDA(cudaMemsetAsync(arena, 0, arena_bytes, stream));
+  UBGL_CUDA(cudaStreamSynchronize(stream));
   char *ctl = take(4096);
   sig = reinterpret_cast<unsigned *>(ctl);
   counter = reinterpret_cast<unsigned *>(ctl + 256);
@@ -384,7 +387,7 @@ void SlabSim::check_err() {
   if (e) {
     UBGL_CUDA(cudaMemsetAsync(err, 0, sizeof(int), stream));
     throw ArgError{e == 2 ? "slab: halo wait timed out (a peer rank stopped?)"
-                          : "slab: advect back-trace left the halo rows (CFL too large for ghost=16)"};
+                          : "slab: advect back-trace is longer than the neighbouring slab (CFL > rows per GPU)"};
   }
 }
 
@@ -596,8 +599,24 @@ void SlabSim::step(float dt_) {
   exchange({xf(vxb[ixf], 0), xf(vyb[iyf], 0)}, plan.ghost);
 
   // advect (reads the fronts incl. ghost rows, writes own rows of the backs)
-  launch_advect(vxb[ixf], vyb[iyf], vxb[ixb], vyb[iyb], flag, 0.5f * dt * ih, dt * ih, R.own_lo,
-                R.own_hi, R.st_lo, R.st_hi, err, stream, &lc);
+  {
+    AdvectPeers ap{};
+    ap.st_lo = R.st_lo; ap.st_hi = R.st_hi; ap.peer_lo = R.st_lo; ap.peer_hi = R.st_hi;
+    ap.err = err;
+    const size_t rb = sizeof(float) * (size_t)pitch;
+    if (!first) {
+      ap.peer_lo = plan.rows(0, plan.rank - 1).own_lo;
+      ap.vx_lo = peer_ptr(plan.rank - 1, vxb[ixf].d, 0, rb);
+      ap.vy_lo = peer_ptr(plan.rank - 1, vyb[iyf].d, 0, rb);
+    }
+    if (!last) {
+      ap.peer_hi = plan.rows(0, plan.rank + 1).own_hi;
+      ap.vx_hi = peer_ptr(plan.rank + 1, vxb[ixf].d, 0, rb);
+      ap.vy_hi = peer_ptr(plan.rank + 1, vyb[iyf].d, 0, rb);
+    }
+    launch_advect(vxb[ixf], vyb[iyf], vxb[ixb], vyb[iyb], flag, 0.5f * dt * ih, dt * ih, R.own_lo,
+                  R.own_hi, plan.nranks > 1 ? &ap : nullptr, stream, &lc);
+  }
   std::swap(ixf, ixb);
   std::swap(iyf, iyb);
   borders(false, false);
