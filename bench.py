@@ -294,11 +294,11 @@ KERNEL_BYTES = {
 }
 
 
-def dominant_roofline(kern, W, H, peak, peak_src, prof_ms_step):
+def dominant_roofline(kern, W, H, peak, peak_src, prof_ms_step, cells_scale=1.0):
     if not kern:
         return None
     ms, n, k, l = kern[0]
-    cells = (W >> l) * (H >> l)
+    cells = (W >> l) * (H >> l) * cells_scale  # slab runs: one rank's rows
     bpc = KERNEL_BYTES.get(k)
     if bpc is None:
         return {"bound": "hbm", "kernel": k, "level": l, "achieved": None, "peak": peak, "unit": "GB/s",

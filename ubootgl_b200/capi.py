@@ -101,6 +101,8 @@ def _load():
         "ubgl_slab_launch_count": (ll, [v]),
         "ubgl_slab_stream": (v, [v]),
         "ubgl_slab_stats": (i, [v, C.POINTER(ll), C.POINTER(ll)]),
+        "ubgl_slab_profile": (i, [v, i]),
+        "ubgl_slab_kernel_stats": (i, [v, i, i, C.POINTER(ll), C.POINTER(C.c_double)]),
         "ubgl_rbgs": (i, [FP, FP, FP, i, i, f, f, i]),
         "ubgl_residual": (i, [FP, FP, FP, FP, i, i, f, FP]),
         "ubgl_restrict": (i, [FP, i, i, FP]),
@@ -440,6 +442,20 @@ class SlabSimulation:
         a, b = C.c_longlong(), C.c_longlong()
         _ck(lib.ubgl_slab_stats(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def profile(self, on):
+        _ck(lib.ubgl_slab_profile(self._h, int(on)))
+
+    def kernel_stats(self):
+        """{(kind_name, level): (launches, total_ms)} of this rank's profiled region."""
+        out = {}
+        for k in range(lib.ubgl_num_kernel_kinds()):
+            for l in range(16):
+                n, ms = C.c_longlong(), C.c_double()
+                _ck(lib.ubgl_slab_kernel_stats(self._h, k, l, C.byref(n), C.byref(ms)))
+                if n.value:
+                    out[(lib.ubgl_kernel_kind_name(k).decode(), l)] = (n.value, ms.value)
+        return out
 
 
 # ---- pressure_solver.cpp free functions -------------------------------------

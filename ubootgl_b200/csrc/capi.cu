@@ -4,9 +4,11 @@
 #include "mg.cuh"
 #include "sim.cuh"
 #include "slab.cuh"
+#include <algorithm>
 #include <cstring>
 #include <memory>
 #include <new>
+#include <thread>
 #include <vector>
 
 namespace ubgl {
@@ -227,6 +229,32 @@ int ubgl_sim_stage(ubgl_sim_t *sim, int stage, float dt) {
   UBGL_CATCH
 }
 
+// Host side of applyAccumulatedVelocity's "accum = 0" (simulation.cpp:384,392):
+// interior rows 1..H-2 x cols 1..W-3 of vx_accum ((W-1) x H) and rows 1..H-3 x
+// cols 1..W-2 of vy_accum (W x (H-1)).  Large mirrors are cleared by a few
+// threads (a single core memsets ~10 GB/s; 8192^2 mirrors are 0.5 GB).
+static void zero_accum_mirrors(float *ax, float *ay, int W, int H) {
+  auto rows = [&](int y0, int y1) {
+    if (ax)
+      for (int y = std::max(y0, 1); y < std::min(y1, H - 1); y++)
+        std::memset(ax + (size_t)y * (W - 1) + 1, 0, sizeof(float) * (W - 3));
+    if (ay)
+      for (int y = std::max(y0, 1); y < std::min(y1, H - 2); y++)
+        std::memset(ay + (size_t)y * W + 1, 0, sizeof(float) * (W - 2));
+  };
+  const size_t bytes = sizeof(float) * (size_t)W * H * ((ax ? 1 : 0) + (ay ? 1 : 0));
+  unsigned nt = std::thread::hardware_concurrency();
+  nt = std::min(nt ? nt : 1u, 8u);
+  if (bytes < (size_t)(16 << 20) || nt < 2) {
+    rows(0, H);
+    return;
+  }
+  std::vector<std::thread> th;
+  for (unsigned t = 0; t < nt; t++)
+    th.emplace_back(rows, (int)((long long)H * t / nt), (int)((long long)H * (t + 1) / nt));
+  for (auto &t : th) t.join();
+}
+
 int ubgl_sim_step_host(ubgl_sim_t *sim, float dt, const ubgl_host_mirrors *m) {
   UBGL_TRY
   SIM(sim);
@@ -244,19 +272,12 @@ int ubgl_sim_step_host(ubgl_sim_t *sim, float dt, const ubgl_host_mirrors *m) {
     Grid g = S.field(F_VY_ACCUM);
     upload_grid(g, m->vy_accum, g.w, g.h, S.stream);
   }
+  cudaEvent_t uploaded = nullptr;
   if (m->vx_accum || m->vy_accum) {
-    // the reference zeroes the interior of the accumulators while applying
-    // them (simulation.cpp:384,392); the host mirrors follow once the upload
-    // has consumed them.
-    S.sync();
-    if (m->vx_accum)
-      for (int y = 1; y < S.H - 1; y++)
-        std::memset(m->vx_accum + (size_t)y * (S.W - 1) + 1, 0, sizeof(float) * (S.W - 3));
-    if (m->vy_accum)
-      for (int y = 1; y < S.H - 2; y++)
-        std::memset(m->vy_accum + (size_t)y * S.W + 1, 0, sizeof(float) * (S.W - 2));
+    UBGL_CUDA(cudaEventCreateWithFlags(&uploaded, cudaEventDisableTiming));
+    UBGL_CUDA(cudaEventRecord(uploaded, S.stream));
   }
-  S.step(dt);
+  S.step(dt); // asynchronous: every kernel of the step is now queued behind the uploads
   struct { int id; float *dst; } outs[] = {{F_VX, m->vx}, {F_VY, m->vy}, {F_P, m->p},
                                            {F_VX_CURRENT, m->vx_current},
                                            {F_VY_CURRENT, m->vy_current}};
@@ -265,6 +286,15 @@ int ubgl_sim_step_host(ubgl_sim_t *sim, float dt, const ubgl_host_mirrors *m) {
       Grid g = S.field(o.id);
       download_grid(g, o.dst, g.w, g.h, S.stream);
     }
+  if (uploaded) {
+    // the reference zeroes the interior of the accumulators while applying them
+    // (simulation.cpp:384,392); the host mirrors follow as soon as the upload has consumed
+    // them -- on host threads, while the GPU runs the step
+    cudaError_t e = cudaEventSynchronize(uploaded);
+    cudaEventDestroy(uploaded);
+    UBGL_CUDA(e);
+    zero_accum_mirrors(m->vx_accum, m->vy_accum, S.W, S.H);
+  }
   S.sync();
   UBGL_CATCH
 }
@@ -632,6 +662,28 @@ int ubgl_slab_stats(ubgl_slab_t *s, long long *exchanges, long long *halo_bytes)
   SLAB(s);
   if (exchanges) *exchanges = S.exchanges;
   if (halo_bytes) *halo_bytes = (long long)S.halo_bytes;
+  UBGL_CATCH
+}
+
+int ubgl_slab_profile(ubgl_slab_t *s, int on) {
+  UBGL_TRY
+  SLAB(s);
+  S.sync();
+  S.lc.collect();
+  if (on) S.lc.reset_stats();
+  S.lc.prof = on != 0;
+  UBGL_CATCH
+}
+
+int ubgl_slab_kernel_stats(ubgl_slab_t *s, int kind, int level, long long *count, double *ms) {
+  UBGL_TRY
+  SLAB(s);
+  UBGL_REQUIRE(kind >= 0 && kind < K_COUNT && level >= 0 && level < LaunchCounter::MAXLVL,
+               "bad kind/level");
+  S.sync();
+  S.lc.collect();
+  if (count) *count = S.lc.cnt[kind][level];
+  if (ms) *ms = S.lc.ms[kind][level];
   UBGL_CATCH
 }
 

@@ -181,7 +181,7 @@ __device__ __forceinline__ float bicubic(const float *__restrict__ g, int pitch,
 //  * whole-octet skip unless some lane has flag(x-1+i,y)+flag(x+i,y) == 2 (:254);
 //  * untouched entries keep whatever the back buffer holds.
 template <bool SLAB>
-__global__ void k_advect_vx(Grid vx, Grid vy, Grid vxb, Grid flag, float half, float full,
+__global__ void __launch_bounds__(256, 8) k_advect_vx(Grid vx, Grid vy, Grid vxb, Grid flag, float half, float full,
                             int y_lo, int y_hi, TapRows tr) {
   const int lane = threadIdx.x;
   const int xi = 1 + blockIdx.x * 32 + lane;
@@ -225,7 +225,7 @@ __device__ __forceinline__ float vx_flat(const Grid &vx, int x, int y) {
   return vx.at(x, y);
 }
 template <bool SLAB>
-__global__ void k_advect_vy(Grid vx, Grid vy, Grid vyb, Grid flag, float half, float full,
+__global__ void __launch_bounds__(256, 8) k_advect_vy(Grid vx, Grid vy, Grid vyb, Grid flag, float half, float full,
                             int y_lo, int y_hi, TapRows tr) {
   const int lane = threadIdx.x;
   const int xi = 1 + blockIdx.x * 32 + lane;

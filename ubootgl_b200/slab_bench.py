@@ -60,6 +60,23 @@ def run(args, name):
     value = N * K / (ms_total * 1e-3) / 1e6
     res_after = float(np.sqrt(slab_boot.allreduce_sum(sim.residual_sumsq())))
 
+    # ---- per-kernel profile of every rank (CUDA events around each launch) ----
+    sim.profile(True)
+    PK = min(K, 3)
+    for _ in range(PK):
+        sim.step(dt)
+    sim.sync()
+    stats = sim.kernel_stats()
+    sim.profile(False)
+    prof_total = sum(ms for _, ms in stats.values()) / PK
+    kern = sorted(((ms / PK, n // PK, k, l) for (k, l), (n, ms) in stats.items()), reverse=True)
+    wait_ms = sum(ms for ms, n, k, l in kern if k == "halo_wait")
+    push_ms = sum(ms for ms, n, k, l in kern if k == "halo_push")
+    wait_max, wait_min = slab_boot.allreduce_max(wait_ms), -slab_boot.allreduce_max(-wait_ms)
+    push_max = slab_boot.allreduce_max(push_ms)
+    compute_max = slab_boot.allreduce_max(prof_total - wait_ms - push_ms)
+    compute_min = -slab_boot.allreduce_max(-(prof_total - wait_ms - push_ms))
+
     # ---- end to end: each rank feeds its slab's accumulators from pinned host
     # memory and reads its rows of vx, vy, p, vx_current, vy_current back ----
     pin = lambda shape: torch.empty(shape, dtype=torch.float32, pin_memory=True).numpy()
@@ -106,10 +123,19 @@ def run(args, name):
                    "residual_after": res_after,
                    "note": "strong scaling is defined on this workload; the N=1 default of bench.py "
                            "is channel8192 (same generator, same MLUP/s definition)"},
-        "roofline": {"bound": "hbm", "kernel": "whole step (all ranks)", "achieved": step_gbs,
-                     "peak": peak * world, "unit": "GB/s", "frac": step_gbs / (peak * world), "traffic": None,
-                     "bytes_per_cell": bpc, "peak_source": peak_src + f" x {world} GPUs",
-                     "model": "stage-wise algorithmic bytes 152 + 186.7*k B/cell (SURVEY.md 8d), k=2"},
+        "roofline": bench.dominant_roofline([r for r in kern if not r[2].startswith("halo")], W, H, peak, peak_src,
+                                            prof_total, cells_scale=1.0 / world),
+        "roofline_step": {"bound": "hbm", "kernel": "whole step (all ranks)", "achieved": step_gbs,
+                          "peak": peak * world, "unit": "GB/s", "frac": step_gbs / (peak * world), "traffic": None,
+                          "bytes_per_cell": bpc, "peak_source": peak_src + f" x {world} GPUs",
+                          "model": "stage-wise algorithmic bytes 152 + 186.7*k B/cell (SURVEY.md 8d), k=2"},
+        "halo": {"wait_ms_per_step_max_rank": wait_max, "wait_ms_per_step_min_rank": wait_min,
+                 "push_ms_per_step_max_rank": push_max, "compute_ms_per_step_max_rank": compute_max,
+                 "compute_ms_per_step_min_rank": compute_min,
+                 "note": "profiled run (events around every launch); wait = k_halo_wait spinning on the "
+                         "neighbours' signals = load imbalance + NVLink latency"},
+        "kernels_ms_per_step_rank0": [{"kernel": k, "level": l, "launches": n, "ms": round(ms, 4)}
+                                      for ms, n, k, l in kern[:14]],
         "cpu_baseline": None,
         "e2e": {"value": N / t_e2e / 1e6, "unit": "MLUP/s", "h2d_bytes_per_step": int(h2d_all),
                 "d2h_bytes_per_step": int(d2h_all), "ms_per_step": t_e2e * 1e3,
