@@ -218,6 +218,18 @@ def run_single_gpu(args, name):
     value = N * K / (ms_total * 1e-3) / 1e6
     res_after = sim.residual()
 
+    # ---- MG V-cycle latency (BASELINE.json metric: "MG V-cycle ms"), resident p/f/flag ----
+    KV = 10  # mgtest.cpp:55-61 times 10 solves
+    sim.mg_solve(2)
+    sim.sync()
+    v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    v0.record(stream)
+    sim.mg_solve(KV)
+    v1.record(stream)
+    sim.sync()
+    torch.cuda.synchronize()
+    vc_ms = v0.elapsed_time(v1) / KV
+
     # ---- per-kernel profile (CUDA events around every launch, same stream) ----
     sim.profile(True)
     PK = min(K, 5)
@@ -229,7 +241,7 @@ def run_single_gpu(args, name):
     prof_total = sum(ms for _, ms in stats.values())
     kern = sorted(((ms / PK, n // PK, k, l) for (k, l), (n, ms) in stats.items()), reverse=True)
     peak, peak_src = peaks()
-    roof = dominant_roofline(kern, W, H, peak, peak_src, prof_total / PK)
+    roof = dominant_roofline(kern, W, H, peak, peak_src, prof_total / PK, workload=name)
 
     # ---- end to end through the host-mirror API (`e2e`) ----
     pin = lambda shape: torch.empty(shape, dtype=torch.float32, pin_memory=True).numpy()
@@ -272,6 +284,10 @@ def run_single_gpu(args, name):
                           "frac": step_gbs / peak, "bytes_per_cell": bpc,
                           "model": "stage-wise algorithmic bytes 152 + 186.7*k B/cell (SURVEY.md 8d), k=2",
                           "peak_source": peak_src},
+        "vcycle": {"ms": vc_ms, "algorithmic_gbs": N * B_VCYCLE / (vc_ms * 1e-3) / 1e9,
+                   "frac": N * B_VCYCLE / (vc_ms * 1e-3) / 1e9 / peak,
+                   "note": "one MG::solve V(3,3) on the resident level-0 fields, mean of 10 (mgtest.cpp:55-61); "
+                           "186.7 algorithmic B per level-0 cell"},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e, "unit": "MLUP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": t_e2e * 1e3, "api": "ubgl_sim_step_host (pinned host mirrors: accumulators in; vx, vy, p, vx_current, vy_current out)"},
@@ -294,7 +310,16 @@ KERNEL_BYTES = {
 }
 
 
-def dominant_roofline(kern, W, H, peak, peak_src, prof_ms_step, cells_scale=1.0):
+def ncu_traffic(workload, kind, level):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel from the
+    committed `ncu --set full` capture of the same workload (profiles/), else None."""
+    p = os.path.join(ROOT, "profiles", f"traffic_{workload}.json")
+    if not os.path.exists(p):
+        return None
+    return json.load(open(p)).get("traffic_bytes_per_launch", {}).get(f"{kind}:{level}")
+
+
+def dominant_roofline(kern, W, H, peak, peak_src, prof_ms_step, cells_scale=1.0, workload=None):
     if not kern:
         return None
     ms, n, k, l = kern[0]
@@ -310,7 +335,9 @@ def dominant_roofline(kern, W, H, peak, peak_src, prof_ms_step, cells_scale=1.0)
     return {"bound": "hbm", "kernel": k, "level": l, "launches_per_step": n,
             "avg_launch_ms": per_launch_ms, "share_of_step": ms / prof_ms_step if prof_ms_step else None,
             "algorithmic_bytes_per_launch": bytes_launch, "achieved": ach, "peak": peak, "unit": "GB/s",
-            "frac": ach / peak, "traffic": None, "peak_source": peak_src}
+            "frac": ach / peak, "traffic": ncu_traffic(workload, k, l) if cells_scale == 1.0 else None,
+            "traffic_source": f"profiles/traffic_{workload}.json (ncu --set full, DRAM read+write bytes per launch)",
+            "peak_source": peak_src}
 
 
 def main():

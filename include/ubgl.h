@@ -71,7 +71,9 @@ enum ubgl_option {
   UBGL_OPT_VCYCLES = 0,  /* V-cycles per project(); default 2 (simulation.cpp:189-190) */
   UBGL_OPT_FUSED = 1,    /* 1 (default): fused / temporally blocked kernels;
                             0: one plain kernel per reference stage (same results) */
-  UBGL_OPT_GRAPH = 2,    /* 1 (default): replay the step as a captured CUDA graph */
+  UBGL_OPT_GRAPH = 2,    /* reserved (accepted, no effect): the step is queued asynchronously on the
+                            handle's stream and is GPU-bound at every measured size, so it is
+                            not captured into a CUDA graph */
   UBGL_OPT_TIMING = 3    /* 1: record per-stage CUDA events (ubgl_sim_stage_ms) */
 };
 
@@ -127,6 +129,19 @@ typedef struct ubgl_host_mirrors {
   float *vy_current;   /* out, optional */
 } ubgl_host_mirrors;
 int ubgl_sim_step_host(ubgl_sim_t *sim, float dt, const ubgl_host_mirrors *m);
+/* Stop rule of the pressure solves inside step() / stage(PROJECT).  rel_tol <= 0
+ * (default): the reference's fixed UBGL_OPT_VCYCLES warm-started V-cycles, no
+ * convergence test (simulation.cpp:189-190).  rel_tol > 0: V-cycles until
+ * ||r||_2 <= rel_tol * ||f*flag||_2 (calculateResidualField norm,
+ * pressure_solver.cpp:91-116, relative to the residual of p = 0), or until a cycle
+ * leaves more than `stagnation` (e.g. 0.9) of the previous residual -- channel flows
+ * stagnate far above 1e-4 -- or max_cycles.  Costs one residual
+ * kernel + one host sync per cycle. */
+int ubgl_sim_set_tolerance(ubgl_sim_t *sim, float rel_tol, int max_cycles, float stagnation);
+/* what the last step()'s solves did: V-cycles run, ||f*flag||, and (tolerance mode)
+ * ||r|| before the first and after every cycle */
+int ubgl_sim_solve_info(ubgl_sim_t *sim, int *cycles_done, float *fnorm, float *res_hist, int cap,
+                        int *n_hist);
 int ubgl_sim_sync(ubgl_sim_t *sim);
 /* calculateResidualField(p, f, flag, r, h) (pressure_solver.cpp:91-116) on the
  * resident p/f/flag; r readable as field UBGL_R. */

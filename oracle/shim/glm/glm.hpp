@@ -91,5 +91,8 @@ inline float length(vec2 a) { return std::sqrt(dot(a, a)); }
 inline vec2 normalize(vec2 a) { return a / length(a); }
 inline float sign(float v) { return (float)((0.0f < v) - (v < 0.0f)); }
 inline float abs(float v) { return std::fabs(v); }
+inline vec2 abs(vec2 v) { return vec2(std::fabs(v.x), std::fabs(v.y)); }
+// glm::reflect (detail/func_geometric.inl): I - N * dot(N, I) * 2
+inline vec2 reflect(vec2 I, vec2 N) { return I - N * dot(N, I) * 2.0f; }
 
 } // namespace glm

@@ -71,6 +71,27 @@ int orc_sim_mg_levels(void *sim);
 void orc_sim_mg_level_size(void *sim, int level, int *w, int *h);
 void orc_sim_mg_get_flagc(void *sim, int level, float *dst);
 
+/* ---- callers either side of the step (ubgl_oracle_next.c) ---- */
+/* CoItem + CoKinematicsSimple (components.hpp:6-43), one record per item */
+typedef struct orc_item {
+  float size[2], pos[2], rotation;       /* CoItem */
+  float mass, vel[2], force[2], angVel, angForce; /* CoKinematicsSimple */
+  int bumpCount;
+} orc_item;
+void orc_colocate(const float *vx, const float *vy, int nx, int ny, float *vxy, float *mag);
+void orc_tracers_advect(float *points, unsigned *start, unsigned *end, float *ages, int ntracers,
+                        int npoints, float dt, float pdx, float pdy, unsigned rand_seed,
+                        const float *vxy, int tw, int th, const float *flagtex, int fw, int fh);
+void orc_tracers_shift(float *points, int ntracers, int npoints, float shift);
+void orc_items_advect_simple(orc_item *items, int n, float game_dt, const float *flag, const float *vx,
+                             const float *vy, const float *p, float *vx_accum, float *vy_accum, int W,
+                             int H, float pwidth);
+void orc_draw_circle(float *flag_full, float *flag_sim, int w, int h, float cx, float cy, int diam,
+                     float val);
+void orc_set_grids_all(float *flag, float *vx, float *vy, float *p, const float *newflag, int W, int H);
+void orc_shift_map(float *flag, float *vxf, float *vxb, float *vyf, float *vyb, float *p, float *vxc,
+                   float *vyc, const float *newflag, int W, int H);
+
 #ifdef __cplusplus
 }
 #endif

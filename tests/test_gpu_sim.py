@@ -146,3 +146,41 @@ def test_flag_update_rebuilds_pyramid(ubgl, port):
         assert (G.mg_flagc(l) == O.mg_flagc(l)).all()
     G.step(0.001); O.step(0.001)
     check(G, O, [ob.VX, ob.VY, ob.P], 3e-5, "step after flag edit")
+
+
+def test_tolerance_mode_matches_fixed_count_and_oracle_history(ubgl, port):
+    """Tolerance / stagnation stop rule of the pressure solves:
+    the cycles it runs are the reference's V-cycles -- same fields as a fixed-count
+    run of that many cycles, residual history within 1 % of the oracle's MG."""
+    W, H = 258, 131
+    G, O, c = make_pair(ubgl, port, W, H, seed=21)
+    G2, _, _ = make_pair(ubgl, port, W, H, seed=21)
+    dt = 0.001
+    G.set_tolerance(1e-4, max_cycles=12, stagnation=0.9)
+    G.step(dt)
+    n, fnorm, hist = G.solve_info()
+    assert 1 <= n <= 12 and len(hist) == n + 1 and fnorm > 0
+    # stop rule: every cycle but the last made progress and did not reach the target
+    for k in range(1, n):
+        assert hist[k] > 1e-4 * fnorm and hist[k] < 0.9 * hist[k - 1]
+    assert n == 12 or hist[n] <= 1e-4 * fnorm or hist[n] >= 0.9 * hist[n - 1]
+    G2.set_option(ubgl.capi.OPT_VCYCLES, n)
+    G2.step(dt)
+    for f in (ob.VX, ob.VY, ob.P):
+        assert (G.get(f) == G2.get(f)).all()
+    # oracle: MG::solve on the same rhs, warm start = the p the step began with
+    f = G.get(ob.F)
+    fl = c["flag"]
+    assert abs(np.sqrt(((f * fl)[1:-1, 1:-1].astype(np.float64) ** 2).sum()) - fnorm) <= 1e-5 * fnorm
+    M = port.MG(W, H)
+    M.update_fields(fl)
+    M.set(p=c["p"], f=f, flag=fl)
+    oh = [M.residual(float(O.dx))]
+    for _ in range(n):
+        M.solve(float(O.dx), zero_gradient_bc=True)
+        oh.append(M.residual(float(O.dx)))
+    assert np.allclose(hist, oh, rtol=1e-2), (hist, oh)
+    # rel_tol <= 0 restores the reference's fixed count
+    G.set_tolerance(0.0)
+    G.step(dt)
+    assert G.solve_info()[0] == 2

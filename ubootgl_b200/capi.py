@@ -57,6 +57,8 @@ def _load():
         "ubgl_sim_step": (i, [v, f]),
         "ubgl_sim_stage": (i, [v, i, f]),
         "ubgl_sim_step_host": (i, [v, f, C.POINTER(HostMirrors)]),
+        "ubgl_sim_set_tolerance": (i, [v, f, i, f]),
+        "ubgl_sim_solve_info": (i, [v, IP, FP, FP, i, IP]),
         "ubgl_sim_sync": (i, [v]),
         "ubgl_sim_residual": (i, [v, FP]),
         "ubgl_sim_mg_solve": (i, [v, i]),
@@ -226,6 +228,17 @@ class Simulation:
 
     def sync(self):
         _ck(lib.ubgl_sim_sync(self._h))
+
+    def set_tolerance(self, rel_tol, max_cycles=20, stagnation=0.9):
+        """rel_tol <= 0: the reference's fixed 2 V-cycles (simulation.cpp:189-190)."""
+        _ck(lib.ubgl_sim_set_tolerance(self._h, rel_tol, max_cycles, stagnation))
+
+    def solve_info(self):
+        """(cycles_done, ||f*flag||, [||r|| before the first / after every cycle])."""
+        n, c, fn = C.c_int(), C.c_int(), C.c_float()
+        hist = np.zeros(256, np.float32)
+        _ck(lib.ubgl_sim_solve_info(self._h, C.byref(c), C.byref(fn), _fp(hist), 256, C.byref(n)))
+        return c.value, fn.value, hist[:min(n.value, 256)].copy()
 
     def residual(self):
         l2 = C.c_float()

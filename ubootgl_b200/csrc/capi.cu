@@ -299,6 +299,30 @@ int ubgl_sim_step_host(ubgl_sim_t *sim, float dt, const ubgl_host_mirrors *m) {
   UBGL_CATCH
 }
 
+int ubgl_sim_set_tolerance(ubgl_sim_t *sim, float rel_tol, int max_cycles, float stagnation) {
+  UBGL_TRY
+  SIM(sim);
+  UBGL_REQUIRE(rel_tol <= 0.0f || (max_cycles >= 1 && stagnation > 0.0f && stagnation <= 1.0f),
+               "tolerance mode needs max_cycles >= 1 and 0 < stagnation <= 1");
+  S.tol = rel_tol;
+  if (rel_tol > 0.0f) {
+    S.max_cycles = max_cycles;
+    S.stag = stagnation;
+  }
+  UBGL_CATCH
+}
+
+int ubgl_sim_solve_info(ubgl_sim_t *sim, int *cycles_done, float *fnorm, float *res_hist, int cap,
+                        int *n_hist) {
+  UBGL_TRY
+  SIM(sim);
+  if (cycles_done) *cycles_done = S.cycles_done;
+  if (fnorm) *fnorm = S.fnorm;
+  if (n_hist) *n_hist = (int)S.res_hist.size();
+  for (int i = 0; res_hist && i < cap && i < (int)S.res_hist.size(); i++) res_hist[i] = S.res_hist[i];
+  UBGL_CATCH
+}
+
 int ubgl_sim_sync(ubgl_sim_t *sim) {
   UBGL_TRY
   SIM(sim);

@@ -361,6 +361,7 @@ DeviceSim::~DeviceSim() {
   free_grid(vx_accum); free_grid(vy_accum);
   free_grid(p); free_grid(f); free_grid(flag); free_grid(r);
   if (d_sinks) cudaFree(d_sinks);
+  if (d_fnorm) cudaFree(d_fnorm);
   if (stream) cudaStreamDestroy(stream);
 }
 
@@ -482,11 +483,63 @@ void DeviceSim::advect() {
   std::swap(iyf, iyb);
 }
 
+// sum over the interior of (f * flag)^2: the residual norm of p = 0, the
+// reference value of the relative residual in tolerance mode
+__global__ void k_fnorm_sq(Grid f, Grid flag, double *out) {
+  double acc = 0.0;
+  for (int y = 1 + blockIdx.x; y < f.h - 1; y += gridDim.x)
+    for (int x = 1 + threadIdx.x; x < f.w - 1; x += blockDim.x) {
+      float v = f.at(x, y) * flag.at(x, y);
+      acc += (double)v * (double)v;
+    }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+  __shared__ double part[32];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    acc = threadIdx.x < (blockDim.x >> 5) ? part[threadIdx.x] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if (threadIdx.x == 0) atomicAdd(out, acc);
+  }
+}
+
+// The pressure solves of project() (simulation.cpp:189-190).  Reference mode:
+// a fixed number of warm-started V-cycles, no convergence test.  Tolerance mode
+// (tol > 0): cycle until ||r|| <= tol * ||f*flag||, or the
+// residual stagnates (a cycle removes less than `stag` of it), or max_cycles.
+void DeviceSim::solve_cycles() {
+  cycles_done = 0;
+  res_hist.clear();
+  if (tol <= 0.0f) {
+    for (int c = 0; c < vcycles; c++) mg->solve(p, f, flag, h, true);
+    cycles_done = vcycles;
+    return;
+  }
+  if (!d_fnorm) UBGL_CUDA(cudaMalloc(&d_fnorm, sizeof(double)));
+  UBGL_CUDA(cudaMemsetAsync(d_fnorm, 0, sizeof(double), stream));
+  UBGL_LAUNCH(&lc, K_NORM, LVL, stream, k_fnorm_sq<<<std::min(H - 2, 148 * 8), 256, 0, stream>>>(f, flag, d_fnorm));
+  double fn = 0.0;
+  UBGL_CUDA(cudaMemcpyAsync(&fn, d_fnorm, sizeof(double), cudaMemcpyDeviceToHost, stream));
+  float r = residual(); // warm start (syncs the stream)
+  fnorm = (float)std::sqrt(fn);
+  res_hist.push_back(r);
+  const float target = tol * fnorm;
+  while (cycles_done < max_cycles && r > target) {
+    mg->solve(p, f, flag, h, true);
+    cycles_done++;
+    float rn = residual();
+    res_hist.push_back(rn);
+    const bool stalled = !(rn < stag * r);
+    r = rn;
+    if (stalled) break;
+  }
+}
+
 void DeviceSim::project() {
   float ih = 1.0f / h;
   UBGL_LAUNCH(&lc, K_DIVERGENCE, LVL, stream, k_divergence<<<grd2d(W - 2, H - 2), blk2d(), 0, stream>>>(vxb[ixf], vyb[iyf], f, ih));
   project_sinks();
-  for (int c = 0; c < vcycles; c++) mg->solve(p, f, flag, h, true);
+  solve_cycles();
 
   UBGL_LAUNCH(&lc, K_PBC, LVL, stream, k_set_pbc<<<1, 1024, 0, stream>>>(p, bcW, bcE, bcN, bcS));
   UBGL_LAUNCH(&lc, K_GRADIENT, LVL, stream, k_gradient<<<grd2d(W - 2, H - 2), blk2d(), 0, stream>>>(vxb[ixf], vyb[iyf], p, flag, ih));
@@ -566,7 +619,7 @@ void DeviceSim::step(float dt_) {
     mark();
     fused_divergence();
     project_sinks();
-    for (int c = 0; c < vcycles; c++) mg->solve(p, f, flag, h, true);
+    solve_cycles();
     fused_gradient_save(); // reads only interior p: independent of setPBC
     mark();
     fused_borders(true, true); // setPBC + setVBCs, also into vx_current / vy_current

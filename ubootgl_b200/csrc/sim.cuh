@@ -103,6 +103,10 @@ public:
   float pwidth, mu, h, dt = 0.0f;
   int bcW, bcE, bcN, bcS;
   int vcycles = 2;
+  // tolerance mode of the pressure solves (tol <= 0: the reference's fixed count)
+  float tol = 0.0f, stag = 0.9f, fnorm = 0.0f;
+  int max_cycles = 20, cycles_done = 0;
+  std::vector<float> res_hist; // ||r|| before the first and after every cycle (tolerance mode)
   bool fused = true, use_graph = true, timing = false;
   std::vector<Sink> sinks;
   int device;
@@ -120,6 +124,8 @@ private:
   int ixf = 0, ixb = 1, ixc = 2, iyf = 0, iyb = 1, iyc = 2;
   Grid vx_accum, vy_accum, p, f, flag, r;
   void project_sinks();
+  void solve_cycles();
+  double *d_fnorm = nullptr;
   // sim_fused.cu
   void fused_prestep();
   void fused_borders(bool with_p, bool with_current);
