@@ -238,6 +238,70 @@ int ubgl_slab_stats(ubgl_slab_t *s, long long *exchanges, long long *halo_bytes)
 int ubgl_slab_profile(ubgl_slab_t *s, int on);
 int ubgl_slab_kernel_stats(ubgl_slab_t *s, int kind, int level, long long *count, double *ms);
 
+/* ---- callers either side of the step, on the device ---------- */
+/* (1) Fluid tracers.  The reference runs them as GLSL compute shaders on
+ * GL textures built from vx_current / vy_current and the full-resolution flag
+ * (velocity_textures.cpp:63-101, draw_tracers_cs.cpp:131-156).  Sampling follows
+ * the OpenGL texture-object defaults those textures are created with: GL_LINEAR
+ * magnification, GL_REPEAT wrap, level 0, evaluated in exact fp32. */
+typedef struct ubgl_tracers ubgl_tracers_t;
+/* GLTracers::init(npoints, ntracers) (draw_tracers_cs.cpp:29-79): points and ring
+ * pointers zero, ages 2*3.1 (every tracer respawns on its first advect) */
+int ubgl_tracers_create(int ntracers, int npoints, int device, ubgl_tracers_t **out);
+int ubgl_tracers_destroy(ubgl_tracers_t *t);
+/* the SSBOs: points [ntracers][npoints] vec2, start/end ring pointers, ages; each optional */
+int ubgl_tracers_upload(ubgl_tracers_t *t, const float *points, const unsigned *start,
+                        const unsigned *end, const float *ages);
+int ubgl_tracers_download(ubgl_tracers_t *t, float *points, unsigned *start, unsigned *end,
+                          float *ages);
+/* VelocityTextures::uploadFlag (velocity_textures.cpp:95-101): the w x h flag texture the
+ * tracers test against (terrain.flagFullRes); NULL: use the simulation's own flag */
+int ubgl_tracers_set_flag_texture(ubgl_tracers_t *t, const float *flag, int w, int h);
+/* advect_tracer_points.cs:42-82 (RK2 midpoint through the co-located velocity
+ * texture of interp_shader.cs, freeze + age in terrain / out of bounds, wang-hash / LCG
+ * respawn) on the simulation's resident vx_current / vy_current; pdim = (pwidth,
+ * pwidth*H/W); rand_seed is the per-frame rand() of draw_tracers_cs.cpp:140.  Runs on the
+ * simulation's stream, asynchronously. */
+int ubgl_tracers_advect(ubgl_tracers_t *t, ubgl_sim_t *sim, float dt, unsigned rand_seed);
+int ubgl_tracers_shift(ubgl_tracers_t *t, float shift); /* shift_tracers.cs (points only) */
+/* interp_shader.cs:15-35 materialised: vxy is (2H-1) x (2W-1) x 2 floats (RG32F), mag
+ * (2H-1) x (2W-1); either host pointer may be NULL (device copy only) */
+int ubgl_sim_colocate_velocity(ubgl_sim_t *sim, float *vxy_host, float *mag_host);
+
+/* (2) Floating items, Simulation::advectFloatingItemsSimple
+ * (advect_floating_items.cpp:148-274).  One record = CoItem + CoKinematicsSimple
+ * (components.hpp:6-43); array order = the order the reference's view visits. */
+typedef struct ubgl_item {
+  float size[2], pos[2], rotation;                /* CoItem */
+  float mass, vel[2], force[2], angVel, angForce; /* CoKinematicsSimple */
+  int bumpCount;
+} ubgl_item;
+typedef struct ubgl_items ubgl_items_t;
+int ubgl_items_create(int device, ubgl_items_t **out);
+int ubgl_items_destroy(ubgl_items_t *it);
+int ubgl_items_upload(ubgl_items_t *it, const ubgl_item *items, int n);
+int ubgl_items_download(ubgl_items_t *it, ubgl_item *items, int cap, int *n);
+/* One game frame of every item against the simulation's resident flag / vx / vy / p;
+ * reaction forces are added to the DEVICE vx_accum / vy_accum with atomicAdd (the
+ * reference scatters serially under accum_mutex, :160), which removes the per-step
+ * upload of the accumulator grids.  Asynchronous on the simulation's stream. */
+int ubgl_items_advect_simple(ubgl_items_t *it, ubgl_sim_t *sim, float game_dt);
+
+/* (3) Terrain edits on the resident simulation-resolution mask (terrain scale 1).
+ * Terrain::drawCircle (terrain.cpp:213-234) for n circles (cx, cy, diam triples, grid
+ * coordinates) with one value, followed by MG::updateFields -- what
+ * explosion.cpp:60 + ubootgl_app.cpp:111-112 do through the host every frame. */
+int ubgl_sim_draw_circles(ubgl_sim_t *sim, const float *xyd, int n, float val);
+/* Simulation::setGrids(c, newflag(c)) for every cell (simulation.hpp:82-98 as called by
+ * ubootgl_app.cpp:274-278); newflag NULL: re-apply the resident flag.  Like the
+ * reference it does not rebuild the coarse flags. */
+int ubgl_sim_set_grids_all(ubgl_sim_t *sim, const float *newflag);
+/* The field part of UbootGlApp::shiftMap (ubootgl_app.cpp:252-296): scroll vx, vy
+ * (front and back), p and the flag one column to the left, enter new_last_column (H
+ * values from the host-side terrain generator, terrain.cpp:119-153) on the right, setGrids
+ * for every cell, reset the inlet column, saveCurrentVelocityFields, MG::updateFields. */
+int ubgl_sim_shift_map(ubgl_sim_t *sim, const float *new_last_column);
+
 /* ---- pressure_solver.cpp free functions, host grids in/out ---------------- */
 /* rbgs(p,f,flag,h,alpha) x sweeps, canonical red-black order
  * (pressure_solver.cpp:35-72; the pipelined path :73-87 is not reproduced) */

@@ -65,6 +65,14 @@ def mg_level_sizes(w, h):
     return out
 
 
+UP = C.POINTER(C.c_uint)
+# CoItem + CoKinematicsSimple (components.hpp:6-43) == orc_item == ubgl_item
+ITEM_DTYPE = np.dtype([("size", np.float32, 2), ("pos", np.float32, 2), ("rotation", np.float32),
+                       ("mass", np.float32), ("vel", np.float32, 2), ("force", np.float32, 2),
+                       ("angVel", np.float32), ("angForce", np.float32), ("bumpCount", np.int32)])
+assert ITEM_DTYPE.itemsize == 52
+
+
 class _SimBase:
     """Shared python face of a CPU Simulation handle (ref or port)."""
 
@@ -319,6 +327,21 @@ class Ref(_Checker):
         L.ref_terrain_size.argtypes = [v, IP, IP]
         L.ref_terrain_flag.argtypes = [v, FP]
         L.ref_terrain_draw_circle.argtypes = [v, f, f, i, f]
+        L.ref_items_advect_simple.argtypes = [v, v, i, f]
+        L.ref_items_view_order.argtypes = [i, IP]
+
+    def items_advect_simple(self, sim, items, game_dt):
+        """Unmodified Simulation::advectFloatingItemsSimple on sim's fields (in place on items)."""
+        assert items.dtype == ITEM_DTYPE and items.flags["C_CONTIGUOUS"]
+        self.lib.ref_items_advect_simple(sim.h, items.ctypes.data_as(C.c_void_p), len(items), game_dt)
+
+    def items_view_order(self, n):
+        o = np.zeros(n, np.int32)
+        self.lib.ref_items_view_order(n, o.ctypes.data_as(IP))
+        return o
+
+    def terrain(self, png, scale=1):
+        return _RefTerrain(self.lib, png, scale)
 
     def terrain_flag(self, png, scale=1):
         t = self.lib.ref_terrain_create(png.encode(), scale)
@@ -330,9 +353,89 @@ class Ref(_Checker):
         return a
 
 
+class _RefTerrain:
+    """The reference's Terrain object (terrain.hpp:9-32) for drawCircle fixtures."""
+
+    def __init__(self, lib, png, scale):
+        self.lib = lib
+        self.t = lib.ref_terrain_create(png.encode(), scale)
+
+    def flag(self):
+        w, h = C.c_int(), C.c_int()
+        self.lib.ref_terrain_size(self.t, C.byref(w), C.byref(h))
+        a = np.empty((h.value, w.value), np.float32)
+        self.lib.ref_terrain_flag(self.t, fp(a))
+        return a
+
+    def draw_circle(self, x, y, diam, val):
+        self.lib.ref_terrain_draw_circle(self.t, x, y, diam, val)
+
+    def __del__(self):
+        try:
+            self.lib.ref_terrain_destroy(self.t)
+        except Exception:
+            pass
+
+
 class Port(_Checker):
     prefix = "orc_"
     so = PORT_SO
+
+    def __init__(self):
+        super().__init__()
+        v, i, f, u = C.c_void_p, C.c_int, C.c_float, C.c_uint
+        L = self.lib
+        L.orc_colocate.argtypes = [FP, FP, i, i, FP, FP]
+        L.orc_tracers_advect.argtypes = [FP, UP, UP, FP, i, i, f, f, f, u, FP, i, i, FP, i, i]
+        L.orc_tracers_shift.argtypes = [FP, i, i, f]
+        L.orc_items_advect_simple.argtypes = [v, i, f, FP, FP, FP, FP, FP, FP, i, i, f]
+        L.orc_draw_circle.argtypes = [FP, FP, i, i, f, f, i, f]
+        L.orc_set_grids_all.argtypes = [FP, FP, FP, FP, FP, i, i]
+        L.orc_shift_map.argtypes = [FP] * 9 + [i, i]
+
+    # ---- SURVEY.md 8f "next" rows (oracle/ubgl_oracle_next.c) ----
+    def colocate(self, vx, vy):
+        """interp_shader.cs: staggered vx (H x W-1), vy (H-1 x W) -> vxy (2H-1, 2W-1, 2), mag."""
+        ny, nx = vx.shape[0], vy.shape[1]
+        vxy = np.empty((2 * ny - 1, 2 * nx - 1, 2), np.float32)
+        mag = np.empty((2 * ny - 1, 2 * nx - 1), np.float32)
+        self.lib.orc_colocate(fp(f32(vx)), fp(f32(vy)), nx, ny, fp(vxy), fp(mag))
+        return vxy, mag
+
+    def tracers_advect(self, st, dt, pdim, rand_seed, vxy, flagtex):
+        """advect_tracer_points.cs on st = dict(points (nt, np, 2) f32, start, end u32, ages f32), in place."""
+        nt, npts = st["points"].shape[:2]
+        th, tw = vxy.shape[:2]
+        fh, fw = flagtex.shape
+        self.lib.orc_tracers_advect(fp(st["points"]), st["start"].ctypes.data_as(UP),
+                                    st["end"].ctypes.data_as(UP), fp(st["ages"]), nt, npts, dt,
+                                    pdim[0], pdim[1], rand_seed & 0xFFFFFFFF, fp(f32(vxy)), tw, th,
+                                    fp(f32(flagtex)), fw, fh)
+
+    def tracers_shift(self, st, shift):
+        nt, npts = st["points"].shape[:2]
+        self.lib.orc_tracers_shift(fp(st["points"]), nt, npts, shift)
+
+    def items_advect_simple(self, items, game_dt, flag, vx, vy, p, vx_accum, vy_accum, pwidth=0.8):
+        """advectFloatingItemsSimple; items and the accumulators are updated in place."""
+        assert items.dtype == ITEM_DTYPE and items.flags["C_CONTIGUOUS"]
+        H, W = flag.shape
+        self.lib.orc_items_advect_simple(items.ctypes.data_as(C.c_void_p), len(items), game_dt,
+                                         fp(f32(flag)), fp(f32(vx)), fp(f32(vy)), fp(f32(p)),
+                                         fp(vx_accum), fp(vy_accum), W, H, pwidth)
+
+    def draw_circle(self, flag_full, flag_sim, cx, cy, diam, val):
+        h, w = flag_sim.shape
+        self.lib.orc_draw_circle(fp(flag_full), fp(flag_sim), w, h, cx, cy, diam, val)
+
+    def set_grids_all(self, flag, vx, vy, p, newflag):
+        H, W = flag.shape
+        self.lib.orc_set_grids_all(fp(flag), fp(vx), fp(vy), fp(p), fp(f32(newflag)), W, H)
+
+    def shift_map(self, flag, vxf, vxb, vyf, vyb, p, vxc, vyc, newflag):
+        H, W = flag.shape
+        self.lib.orc_shift_map(fp(flag), fp(vxf), fp(vxb), fp(vyf), fp(vyb), fp(p), fp(vxc), fp(vyc),
+                               fp(f32(newflag)), W, H)
 
 
 def have_ref():

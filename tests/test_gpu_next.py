@@ -1,0 +1,163 @@
+"""GPU parity of the callers either side of the step: tracers +
+co-located velocity, floating items with accumulator scatter, terrain edits and
+scrolling -- libubgl.so through the C ABI against the CPU oracle
+(oracle/ubgl_oracle_next.c) on identical seeded inputs."""
+import numpy as np
+import pytest
+
+from oracle import bind as ob
+from tests import cases, next_cases
+from tests.cases import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu_twin(ubgl, O, flag):
+    """A device Simulation holding exactly the oracle simulation's fields."""
+    G = ubgl.Simulation(flag)
+    for f in (ob.VX, ob.VY, ob.VXB, ob.VYB, ob.P, ob.VX_ACCUM, ob.VY_ACCUM, ob.VX_CURRENT, ob.VY_CURRENT):
+        G.set(f, O.get(f))
+    return G
+
+
+@pytest.mark.parametrize("W,H", [(70, 40), (130, 97), (258, 131)])
+def test_colocate_bit_exact(ubgl, port, W, H):
+    flag, O = next_cases.developed_flow(port, W, H, seed=W)
+    G = gpu_twin(ubgl, O, flag)
+    vxy, mag = G.colocate_velocity()
+    ovxy, omag = port.colocate(O.get(ob.VX_CURRENT), O.get(ob.VY_CURRENT))
+    assert (vxy.view(np.uint32) == ovxy.view(np.uint32)).all()
+    assert (mag.view(np.uint32) == omag.view(np.uint32)).all()
+
+
+@pytest.mark.parametrize("W,H,nt,scale", [(130, 97, 1000, 1), (258, 131, 5000, 1), (130, 97, 2000, 2)])
+def test_tracers_bit_exact(ubgl, port, W, H, nt, scale):
+    """60 frames incl. respawn, ring wrap-around, freezing in terrain: bit-exact
+    (the on-the-fly texel evaluation equals sampling the materialised texture)."""
+    flag, O = next_cases.developed_flow(port, W, H, seed=H)
+    G = gpu_twin(ubgl, O, flag)
+    flagtex = np.kron(flag, np.ones((scale, scale), np.float32))  # terrain.flagFullRes at `scale`
+    ovxy, _ = port.colocate(O.get(ob.VX_CURRENT), O.get(ob.VY_CURRENT))
+    T = ubgl.Tracers(nt, 30)
+    if scale != 1:
+        T.set_flag_texture(flagtex)
+    st = next_cases.tracer_state(nt, 30)
+    pd = (np.float32(0.8), np.float32(0.8) * np.float32(H) / np.float32(W))
+    g = cases.LCG(5)
+    for k in range(60):
+        seed = int(g.u() * 2 ** 31)
+        T.advect(G, 0.02, seed)
+        port.tracers_advect(st, 0.02, pd, seed, ovxy, flagtex)
+    gs = T.state()
+    for key in ("points", "ages"):
+        assert (gs[key].view(np.uint32) == st[key].view(np.uint32)).all(), key
+    assert (gs["start"] == st["start"]).all() and (gs["end"] == st["end"]).all()
+    assert (st["ages"] > 1.0).any() and (st["end"] > 20).any()
+    T.shift(-0.125)
+    port.tracers_shift(st, -0.125)
+    assert (T.state()["points"] == st["points"]).all()
+
+
+@pytest.mark.parametrize("W,H,n,dt", [(130, 97, 500, 0.004), (258, 131, 4000, 0.01), (70, 40, 64, 0.02)])
+def test_items_match_oracle(ubgl, port, W, H, n, dt):
+    flag, O = next_cases.developed_flow(port, W, H, seed=W + H)
+    G = gpu_twin(ubgl, O, flag)
+    items = next_cases.make_items(n, W, H, seed=3, flag=flag, cluster=0.2)
+    I = ubgl.Items(items)
+    o = items.copy()
+    ax, ay = O.get(ob.VX_ACCUM), O.get(ob.VY_ACCUM)
+    vx, vy, p = O.get(ob.VX), O.get(ob.VY), O.get(ob.P)
+    for k in range(3):
+        I.advect_simple(G, dt)
+        port.items_advect_simple(o, dt, flag, vx, vy, p, ax, ay)
+        g = I.get()
+        for name in ("pos", "vel", "rotation", "angVel", "force", "angForce", "size", "mass"):
+            assert rel_l2(g[name], o[name]) <= 1e-5, (k, name, rel_l2(g[name], o[name]))
+        assert (g["bumpCount"] == o["bumpCount"]).mean() >= 0.995
+    assert o["bumpCount"].sum() > 0
+    # force scatter: device atomicAdd vs the oracle's serial +=
+    assert np.abs(ax).sum() > 0
+    assert rel_l2(G.get(ob.VX_ACCUM), ax) <= 1e-5 and rel_l2(G.get(ob.VY_ACCUM), ay) <= 1e-5
+    # and the accumulators feed the next step exactly like host-uploaded ones
+    O.set(ob.VX_ACCUM, ax); O.set(ob.VY_ACCUM, ay)
+    G.step(0.001); O.step(0.001)
+    for f in (ob.VX, ob.VY, ob.P):
+        assert rel_l2(G.get(f), O.get(f)) <= 3e-5
+
+
+def test_items_empty_and_regrow(ubgl, port):
+    flag, O = next_cases.developed_flow(port, 70, 40, seed=1)
+    G = gpu_twin(ubgl, O, flag)
+    I = ubgl.Items()
+    I.set(np.zeros(0, ubgl.capi.ITEM_DTYPE))
+    I.advect_simple(G, 0.01)
+    assert len(I.get()) == 0
+    I.set(next_cases.make_items(10, 70, 40, seed=1))
+    I.advect_simple(G, 0.01)
+    I.set(next_cases.make_items(300, 70, 40, seed=2))
+    I.advect_simple(G, 0.01)
+    assert np.isfinite(I.get()["pos"]).all()
+
+
+def test_draw_circles_bit_exact_and_pyramid(ubgl, port):
+    W, H = 258, 131
+    flag, O = next_cases.developed_flow(port, W, H, seed=9)
+    G = gpu_twin(ubgl, O, flag)
+    g = cases.LCG(99)
+    full, simres = flag.copy(), flag.copy()
+    for val in (1.0, 0.0, 1.0):
+        circ = []
+        for _ in range(16):
+            d = 2 + int(g.u() * 10)
+            circ.append((d + 1 + g.u() * (W - 2 * d - 3), d + 1 + g.u() * (H - 2 * d - 3), d))
+        for cx, cy, d in circ:
+            port.draw_circle(full, simres, np.float32(cx), np.float32(cy), d, val)
+        G.draw_circles(circ, val)
+        assert (G.get(ob.FLAG) == simres).all()
+        O.update_flag(simres)
+        for l in range(G.mg_levels()):
+            assert (G.mg_flagc(l) == O.mg_flagc(l)).all(), l
+    assert (simres != flag).sum() > 200
+    G.step(0.001); O.step(0.001)
+    for f in (ob.VX, ob.VY, ob.P):
+        assert rel_l2(G.get(f), O.get(f)) <= 3e-5
+    with pytest.raises(ubgl.UbglError):
+        G.draw_circles([(3.0, 50.0, 10)], 1.0)  # box leaves the grid
+
+
+@pytest.mark.parametrize("W,H", [(70, 40), (258, 131), (1090, 436)])
+def test_shift_map_bit_exact(ubgl, port, W, H):
+    flag, O = next_cases.developed_flow(port, W, H, seed=W, steps=2)
+    G = gpu_twin(ubgl, O, flag)
+    rng = np.random.default_rng(W)
+    f = {k: O.get(i) for k, i in dict(vxf=ob.VX, vxb=ob.VXB, vyf=ob.VY, vyb=ob.VYB, p=ob.P,
+                                      vxc=ob.VX_CURRENT, vyc=ob.VY_CURRENT).items()}
+    cur = flag.copy()
+    for k in range(3):
+        col = (rng.random(H) > 0.4).astype(np.float32)
+        new = np.roll(cur, -1, axis=1)
+        new[:, -1] = col
+        port.shift_map(cur, f["vxf"], f["vxb"], f["vyf"], f["vyb"], f["p"], f["vxc"], f["vyc"], new)
+        G.shift_map(col)
+        assert (cur == new).all()
+    assert (G.get(ob.FLAG) == cur).all()
+    for k, i in dict(vxf=ob.VX, vxb=ob.VXB, vyf=ob.VY, vyb=ob.VYB, p=ob.P, vxc=ob.VX_CURRENT,
+                     vyc=ob.VY_CURRENT).items():
+        assert (G.get(i).view(np.uint32) == f[k].view(np.uint32)).all(), k
+    O.update_flag(cur)
+    for l in range(G.mg_levels()):
+        assert (G.mg_flagc(l) == O.mg_flagc(l)).all()
+
+
+def test_set_grids_all(ubgl, port):
+    W, H = 130, 97
+    flag, O = next_cases.developed_flow(port, W, H, seed=4)
+    G = gpu_twin(ubgl, O, flag)
+    new = flag.copy()
+    new[30:50, 40:70] = 0
+    new[60:70, 20:30] = 1
+    fl, vx, vy, p = flag.copy(), O.get(ob.VX), O.get(ob.VY), O.get(ob.P)
+    port.set_grids_all(fl, vx, vy, p, new)
+    G.set_grids_all(new)
+    assert (G.get(ob.FLAG) == new).all()
+    assert (G.get(ob.VX) == vx).all() and (G.get(ob.VY) == vy).all() and (G.get(ob.P) == p).all()

@@ -19,6 +19,11 @@ OPT_VCYCLES, OPT_FUSED, OPT_GRAPH, OPT_TIMING = range(4)
 
 FP = C.POINTER(C.c_float)
 IP = C.POINTER(C.c_int)
+UP = C.POINTER(C.c_uint)
+# struct ubgl_item (include/ubgl.h) = CoItem + CoKinematicsSimple (components.hpp:6-43)
+ITEM_DTYPE = np.dtype([("size", np.float32, 2), ("pos", np.float32, 2), ("rotation", np.float32),
+                       ("mass", np.float32), ("vel", np.float32, 2), ("force", np.float32, 2),
+                       ("angVel", np.float32), ("angForce", np.float32), ("bumpCount", np.int32)])
 
 
 class UbglError(RuntimeError):
@@ -105,6 +110,22 @@ def _load():
         "ubgl_slab_stats": (i, [v, C.POINTER(ll), C.POINTER(ll)]),
         "ubgl_slab_profile": (i, [v, i]),
         "ubgl_slab_kernel_stats": (i, [v, i, i, C.POINTER(ll), C.POINTER(C.c_double)]),
+        "ubgl_tracers_create": (i, [i, i, i, VP]),
+        "ubgl_tracers_destroy": (i, [v]),
+        "ubgl_tracers_upload": (i, [v, FP, UP, UP, FP]),
+        "ubgl_tracers_download": (i, [v, FP, UP, UP, FP]),
+        "ubgl_tracers_set_flag_texture": (i, [v, FP, i, i]),
+        "ubgl_tracers_advect": (i, [v, v, f, C.c_uint]),
+        "ubgl_tracers_shift": (i, [v, f]),
+        "ubgl_sim_colocate_velocity": (i, [v, FP, FP]),
+        "ubgl_items_create": (i, [i, VP]),
+        "ubgl_items_destroy": (i, [v]),
+        "ubgl_items_upload": (i, [v, v, i]),
+        "ubgl_items_download": (i, [v, v, i, IP]),
+        "ubgl_items_advect_simple": (i, [v, v, f]),
+        "ubgl_sim_draw_circles": (i, [v, FP, i, f]),
+        "ubgl_sim_set_grids_all": (i, [v, FP]),
+        "ubgl_sim_shift_map": (i, [v, FP]),
         "ubgl_rbgs": (i, [FP, FP, FP, i, i, f, f, i]),
         "ubgl_residual": (i, [FP, FP, FP, FP, i, i, f, FP]),
         "ubgl_restrict": (i, [FP, i, i, FP]),
@@ -287,6 +308,114 @@ class Simulation:
 
     def stream(self):
         return lib.ubgl_sim_stream(self._h)
+
+    # ---- callers either side of the step, on the device ----
+    def colocate_velocity(self, download=True):
+        """interp_shader.cs: (vxy (2H-1, 2W-1, 2), mag (2H-1, 2W-1)) from vx_current / vy_current."""
+        if not download:
+            _ck(lib.ubgl_sim_colocate_velocity(self._h, None, None))
+            return None
+        th, tw = 2 * self.height - 1, 2 * self.width - 1
+        vxy, mag = np.empty((th, tw, 2), np.float32), np.empty((th, tw), np.float32)
+        _ck(lib.ubgl_sim_colocate_velocity(self._h, _fp(vxy), _fp(mag)))
+        return vxy, mag
+
+    def draw_circles(self, xyd, val):
+        """Terrain::drawCircle (terrain.cpp:213-234) x n + MG::updateFields, on the device."""
+        xyd = _f32(np.asarray(xyd, np.float32).reshape(-1, 3))
+        _ck(lib.ubgl_sim_draw_circles(self._h, _fp(xyd), len(xyd), val))
+
+    def set_grids_all(self, newflag=None):
+        _ck(lib.ubgl_sim_set_grids_all(self._h, _fp(_f32(newflag)) if newflag is not None else None))
+
+    def shift_map(self, new_last_column):
+        col = _f32(new_last_column)
+        if col.shape != (self.height,):
+            raise UbglError("shift_map: the new column needs H values")
+        _ck(lib.ubgl_sim_shift_map(self._h, _fp(col)))
+
+
+class Tracers:
+    """DrawTracersCS::GLTracers (draw_tracers_cs.cpp:27-98) + advect_tracer_points.cs on the GPU."""
+
+    def __init__(self, ntracers=1000, npoints=30, device=0):
+        self.ntracers, self.npoints = ntracers, npoints
+        self._h = C.c_void_p()
+        _ck(lib.ubgl_tracers_create(ntracers, npoints, device, C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.ubgl_tracers_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_state(self, st):
+        _ck(lib.ubgl_tracers_upload(self._h, _fp(st["points"]), st["start"].ctypes.data_as(UP),
+                                    st["end"].ctypes.data_as(UP), _fp(st["ages"])))
+
+    def state(self):
+        st = dict(points=np.empty((self.ntracers, self.npoints, 2), np.float32),
+                  start=np.empty(self.ntracers, np.uint32), end=np.empty(self.ntracers, np.uint32),
+                  ages=np.empty(self.ntracers, np.float32))
+        _ck(lib.ubgl_tracers_download(self._h, _fp(st["points"]), st["start"].ctypes.data_as(UP),
+                                      st["end"].ctypes.data_as(UP), _fp(st["ages"])))
+        return st
+
+    def set_flag_texture(self, flag):
+        if flag is None:
+            _ck(lib.ubgl_tracers_set_flag_texture(self._h, None, 0, 0))
+        else:
+            flag = _f32(flag)
+            _ck(lib.ubgl_tracers_set_flag_texture(self._h, _fp(flag), flag.shape[1], flag.shape[0]))
+
+    def advect(self, sim, dt, rand_seed):
+        _ck(lib.ubgl_tracers_advect(self._h, sim._h, dt, rand_seed & 0xFFFFFFFF))
+
+    def shift(self, shift):
+        _ck(lib.ubgl_tracers_shift(self._h, shift))
+
+
+class Items:
+    """The CoItem + CoKinematicsSimple view of the reference's registry as one device array."""
+
+    def __init__(self, items=None, device=0):
+        self._h = C.c_void_p()
+        _ck(lib.ubgl_items_create(device, C.byref(self._h)))
+        if items is not None:
+            self.set(items)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.ubgl_items_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set(self, items):
+        items = np.ascontiguousarray(items)
+        if items.dtype.itemsize != ITEM_DTYPE.itemsize:
+            raise UbglError("items: need 52-byte ubgl_item records")
+        self.n = len(items)
+        _ck(lib.ubgl_items_upload(self._h, items.ctypes.data_as(C.c_void_p), len(items)))
+
+    def get(self):
+        a = np.zeros(self.n, ITEM_DTYPE)
+        n = C.c_int()
+        _ck(lib.ubgl_items_download(self._h, a.ctypes.data_as(C.c_void_p), self.n, C.byref(n)))
+        return a
+
+    def advect_simple(self, sim, game_dt):
+        """Simulation::advectFloatingItemsSimple (advect_floating_items.cpp:148-274)."""
+        _ck(lib.ubgl_items_advect_simple(self._h, sim._h, game_dt))
 
 
 class MG:

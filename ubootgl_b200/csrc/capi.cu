@@ -4,6 +4,7 @@
 #include "mg.cuh"
 #include "sim.cuh"
 #include "slab.cuh"
+#include "capi_internal.cuh"
 #include <algorithm>
 #include <cstring>
 #include <memory>
@@ -17,7 +18,8 @@ const char *kind_name(int k) {
       "other", "fill", "accum", "diffuse", "vbc", "advect", "divergence", "sinks", "rbgs_half",
       "zero_gradient_bc", "residual", "norm", "restrict", "prolong_correct", "coarsen_flag",
       "pbc", "gradient", "prestep_fused", "advect_div_fused", "mg_pre_fused", "mg_post_fused",
-      "mg_coarse_fused", "finish_fused", "halo_push", "halo_wait"};
+      "mg_coarse_fused", "finish_fused", "halo_push", "halo_wait", "colocate", "tracers", "items",
+      "terrain"};
   return (k >= 0 && k < K_COUNT) ? names[k] : "?";
 }
 static thread_local std::string g_err;
@@ -26,10 +28,6 @@ const char *get_error() { return g_err.c_str(); }
 } // namespace ubgl
 
 using namespace ubgl;
-
-struct ubgl_sim {
-  std::unique_ptr<DeviceSim> s;
-};
 
 struct ubgl_mg {
   int W = 0, H = 0, device = 0;
@@ -47,41 +45,6 @@ struct ubgl_mg {
     if (stream) cudaStreamDestroy(stream);
   }
 };
-
-#define UBGL_TRY try {
-#define UBGL_CATCH                                                             \
-  }                                                                            \
-  catch (const CudaError &e) {                                                 \
-    char buf[512];                                                             \
-    snprintf(buf, sizeof buf, "CUDA error %d (%s) at %s:%d", (int)e.code,      \
-             cudaGetErrorString(e.code), e.file, e.line);                      \
-    set_error(buf);                                                            \
-    cudaGetLastError();                                                        \
-    return e.code == cudaErrorMemoryAllocation ? UBGL_E_NOMEM : UBGL_E_CUDA;   \
-  }                                                                            \
-  catch (const ArgError &e) {                                                  \
-    set_error(e.msg);                                                          \
-    return UBGL_E_ARG;                                                         \
-  }                                                                            \
-  catch (const std::bad_alloc &) {                                             \
-    set_error("host allocation failed");                                       \
-    return UBGL_E_NOMEM;                                                       \
-  }                                                                            \
-  catch (...) {                                                                \
-    set_error("unknown internal error");                                       \
-    return UBGL_E_STATE;                                                       \
-  }                                                                            \
-  return UBGL_OK;
-
-#define NEED(ptr, what) UBGL_REQUIRE((ptr) != nullptr, what " must not be null")
-
-static void require_device(int device) {
-  int n = 0;
-  cudaError_t e = cudaGetDeviceCount(&n);
-  if (e != cudaSuccess) throw CudaError{e, __FILE__, __LINE__};
-  UBGL_REQUIRE(device >= 0 && device < n, "no such CUDA device (libubgl has no CPU fallback)");
-  UBGL_CUDA(cudaSetDevice(device));
-}
 
 extern "C" {
 
@@ -115,11 +78,6 @@ int ubgl_sim_destroy(ubgl_sim_t *sim) {
   delete sim;
   UBGL_CATCH
 }
-
-#define SIM(sim)                                                               \
-  NEED(sim, "sim");                                                            \
-  DeviceSim &S = *(sim)->s;                                                    \
-  UBGL_CUDA(cudaSetDevice(S.device));
 
 int ubgl_sim_set_option(ubgl_sim_t *sim, int option, int value) {
   UBGL_TRY

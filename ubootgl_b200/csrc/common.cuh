@@ -66,6 +66,8 @@ enum Kind {
   K_MG_PRE /* fused smooth+residual+restrict */, K_MG_POST /* fused prolong+correct+smooth */,
   K_MG_COARSE /* all coarse levels in one kernel */, K_FINISH /* fused pBC+gradient+vBC+save */,
   K_HALO_PUSH /* peer-store halo rows + signal */, K_HALO_WAIT,
+  K_COLOCATE /* staggered -> co-located velocity texture */, K_TRACERS, K_ITEMS /* floating items */,
+  K_TERRAIN /* flag edits, scroll */,
   K_COUNT
 };
 const char *kind_name(int kind);

@@ -362,6 +362,8 @@ DeviceSim::~DeviceSim() {
   free_grid(p); free_grid(f); free_grid(flag); free_grid(r);
   if (d_sinks) cudaFree(d_sinks);
   if (d_fnorm) cudaFree(d_fnorm);
+  if (d_vxy) cudaFree(d_vxy);
+  if (d_mag) cudaFree(d_mag);
   if (stream) cudaStreamDestroy(stream);
 }
 

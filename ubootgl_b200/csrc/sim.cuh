@@ -114,6 +114,8 @@ public:
   LaunchCounter lc;
   std::unique_ptr<DeviceMG> mg;
   float stage_ms[ST_COUNT] = {0, 0, 0, 0, 0, 0};
+  // co-located velocity texture of interp_shader.cs (next.cu), allocated on first use
+  float *d_vxy = nullptr, *d_mag = nullptr;
 
 private:
   // Three buffers per velocity component in the roles front / back
