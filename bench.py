@@ -11,6 +11,9 @@ A "step" is one Simulation::step (accumulate, diffuse, advect, divergence,
                (configs[2]; the config BASELINE.json's target is quoted on) -- default at N=1
   channel32768 32768x32768, same generator, row-slab decomposed (configs[3]) -- default at N>1
   game         1090x436-like game level (configs[1]) -- L2 resident, latency bound
+  explosion4096  configs[4]: 4096^2 channel; every step 16 craters (Terrain::drawCircle, diam 24)
+               carved on the device + coarse-flag rebuild + their pressure sinks, the fluid
+               step, 1 M fluid tracers and 1 M floating items
   channel<S>   any other square size S
 
 Prints ONE JSON line (rank 0).  See DESIGN.md section "Measurement".
@@ -51,6 +54,9 @@ def peaks():
 def workload_dims(name):
     if name == "game":
         return 1090, 436
+    if name.startswith("explosion"):
+        s = int(name[len("explosion"):])
+        return s, s
     if name.startswith("channel"):
         s = int(name[len("channel"):])
         return s, s
@@ -67,7 +73,7 @@ def make_inputs(name):
         vy = np.zeros((H - 1, W), np.float32)
         dt = 0.001
     else:
-        flag, _ = cases.channel_flag(W, H, seed=1234)
+        flag, _ = cases.channel_flag(W, H, seed=1234)  # explosion<S> shares the channel generator
         vx, vy = cases.uniform_stream(flag)
         dt = float(np.float32(PWIDTH) / np.float32(W - 1))  # dt = h, CFL ~ 1
     return W, H, flag, vx, vy, dt
@@ -298,6 +304,207 @@ def run_single_gpu(args, name):
     print(json.dumps(line), flush=True)
 
 
+# ---------------------------------------------------------------------------
+# configs[4]: explosion-heavy step -- terrain edits + step + tracers + items
+# ---------------------------------------------------------------------------
+N_PARTICLES = 1_000_000
+GAME_DT = 1.0 / 60.0          # one rendered frame (items sub-step up to 15x, advect_floating_items.cpp:183)
+CRATERS, CRATER_DIAM = 16, 24
+
+
+def explosion_inputs(name, n_particles):
+    from tests import next_cases
+    W, H, flag, vx, vy, dt = make_inputs(name)
+    items = next_cases.make_items(n_particles, W, H, seed=7, flag=None, cluster=0.0)
+    rng = np.random.default_rng(7)
+    st = next_cases.tracer_state(n_particles, 30)
+    ys, xs = np.nonzero(flag[2:-2, 2:-2])
+    pick = rng.integers(0, len(ys), n_particles)
+    cell = np.float32(PWIDTH) / np.float32(W)
+    st["points"][:, 0, 0] = (xs[pick] + 2.5) * cell      # uniformly in fluid cells
+    st["points"][:, 0, 1] = (ys[pick] + 2.5) * cell
+    st["ages"][:] = (rng.random(n_particles) * 6.0).astype(np.float32)
+    return W, H, flag, vx, vy, dt, items, st
+
+
+def crater_list(g, W, H):
+    out = []
+    for _ in range(CRATERS):
+        cx = CRATER_DIAM + 2 + g.u() * (W - 2 * CRATER_DIAM - 5)
+        cy = CRATER_DIAM + 2 + g.u() * (H - 2 * CRATER_DIAM - 5)
+        out.append((cx, cy, CRATER_DIAM))
+    return np.asarray(out, np.float32)
+
+
+def run_explosion(args, name):
+    import torch
+    import ubootgl_b200 as u
+    from ubootgl_b200 import capi
+
+    if u.lib.ubgl_device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device visible to libubgl.so (there is no CPU fallback)")
+    dev = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(dev)
+    W, H, flag, vx, vy, dt, items, st = explosion_inputs(name, N_PARTICLES)
+    N = W * H
+    h = float(np.float32(PWIDTH) / np.float32(W - 1))
+    sim = u.Simulation(flag, PWIDTH, MU, device=dev)
+    sim.set(capi.VX, vx)
+    sim.set(capi.VY, vy)
+    T = u.Tracers(N_PARTICLES, 30, device=dev)
+    T.set_state(st)
+    I = u.Items(items, device=dev)
+    stream = torch.cuda.ExternalStream(sim.stream(), device=dev)
+    g = cases.LCG(99)
+    K, Wm = args.steps, args.warmup
+    seed = [12345]
+
+    def frame(host_out=None):
+        circ = crater_list(g, W, H)
+        sim.draw_circles(circ, 1.0)                       # explosion.cpp:60 + ubootgl_app.cpp:111-112
+        new = np.concatenate([circ[:, :2] * np.float32(h), np.full((CRATERS, 1), 120.0, np.float32)], 1)
+        sim.set_sinks(np.concatenate([sim.sinks(), new]))  # explosion.cpp:33 (one sink per crater here)
+        if host_out is None:
+            sim.step(dt)
+        else:
+            sim.step_host(dt, **host_out)
+        seed[0] = (1103515245 * seed[0] + 12345) & 0x7FFFFFFF
+        T.advect(sim, GAME_DT, seed[0])
+        I.advect_simple(sim, GAME_DT)
+
+    for _ in range(Wm):
+        frame()
+    sim.sync()
+    torch.cuda.synchronize()
+    l0 = sim.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(dev) as clk:
+        e0.record(stream)
+        for _ in range(K):
+            frame()
+        e1.record(stream)
+        sim.sync()
+        torch.cuda.synchronize()
+    ms_step = e0.elapsed_time(e1) / K
+    launches = sim.launch_count() - l0
+
+    sim.profile(True)
+    PK = min(K, 5)
+    for _ in range(PK):
+        frame()
+    sim.sync()
+    stats = sim.kernel_stats()
+    sim.profile(False)
+    per = {}
+    for (k, l), (n, ms) in stats.items():
+        per[k] = per.get(k, 0.0) + ms / PK
+    kern = sorted(((ms / PK, n // PK, k, l) for (k, l), (n, ms) in stats.items()), reverse=True)
+    peak, peak_src = peaks()
+    fluid = [r for r in kern if r[2] not in ("tracers", "items", "terrain", "colocate", "coarsen_flag")]
+    roof = dominant_roofline(fluid, W, H, peak, peak_src, sum(per.values()))
+
+    # end to end: crater + sink lists in, fields + item records out, every frame
+    pin = lambda shape, dt_=torch.float32: torch.empty(shape, dtype=dt_, pin_memory=True).numpy()
+    outs = dict(vx=pin((H, W - 1)), vy=pin((H - 1, W)), p=pin((H, W)),
+                vx_current=pin((H, W - 1)), vy_current=pin((H - 1, W)))
+    KE = max(2, min(K, 5))
+    frame(outs); I.get()
+    t0 = time.perf_counter()
+    for _ in range(KE):
+        frame(outs)
+        rec = I.get()
+    t_e2e = (time.perf_counter() - t0) / KE
+    d2h = sum(a.nbytes for a in outs.values()) + rec.nbytes
+    h2d = CRATERS * 12 + len(sim.sinks()) * 12
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        cpu = explosion_cpu_baseline(name)
+    bpc = bytes_per_cell()
+    step_only = sum(ms for ms, n, k, l in fluid)
+    line = {
+        "metric": "fluid_step_throughput", "value": N / (ms_step * 1e-3) / 1e6, "unit": "MLUP/s", "n_gpus": 1,
+        "steps": K, "warmup": Wm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": name, "grid": [W, H], "vcycles_per_step": VCYCLES, "dt": dt,
+                   "per_step": f"{CRATERS} craters diam {CRATER_DIAM} + coarse-flag/mask rebuild, {CRATERS} sinks, "
+                               f"Simulation::step, {N_PARTICLES} tracers x30 ring, {N_PARTICLES} simple items "
+                               f"(game dt 1/60, up to 15 sub-steps, force scatter by atomicAdd)",
+                   "l2": f"state {12 * N * 4 / 1e6:.0f} MB per step vs 126 MB L2 (inputs larger than L2)"},
+        "particles": {"tracers_per_s": N_PARTICLES / (per.get("tracers", float("nan")) * 1e-3),
+                      "items_per_s": N_PARTICLES / (per.get("items", float("nan")) * 1e-3),
+                      "tracers_ms": per.get("tracers"), "items_ms": per.get("items"),
+                      "terrain_ms": per.get("terrain", 0.0) + per.get("coarsen_flag", 0.0) + per.get("other", 0.0),
+                      "fluid_step_ms": step_only,
+                      "fluid_step_mlups": N / (step_only * 1e-3) / 1e6},
+        "roofline": roof,
+        "roofline_step": {"bound": "hbm", "achieved": N * bpc / (step_only * 1e-3) / 1e9, "peak": peak,
+                          "unit": "GB/s", "frac": N * bpc / (step_only * 1e-3) / 1e9 / peak, "bytes_per_cell": bpc,
+                          "model": "fluid-step kernels only, 152 + 186.7*k B/cell, k=2", "peak_source": peak_src},
+        "cpu_baseline": cpu,
+        "e2e": {"value": N / t_e2e / 1e6, "unit": "MLUP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": t_e2e * 1e3,
+                "api": "draw_circles + set_sinks (host lists in), ubgl_sim_step_host (fields out), tracers/items "
+                       "advect, ubgl_items_download (item records out); no accumulator upload: items scatter on the device"},
+        "gpu_launches": int(launches),
+        "clocks": clk.summary(),
+        "kernels_ms_per_step": [{"kernel": k, "level": l, "launches": n, "ms": round(ms, 4)} for ms, n, k, l in kern[:14]],
+    }
+    print(json.dumps(line), flush=True)
+
+
+def explosion_cpu_baseline(name, n_items=50_000, n_tracers=50_000):
+    """The reference's CPU code for the same frame on a bounded sample: the fluid
+    step (unmodified reference, all cores), its own advectFloatingItemsSimple on
+    n_items, and the C restatement of the tracer shader on n_tracers."""
+    from oracle import bind as ob
+    from tests import next_cases
+    if not ob.have_port():
+        ob.build(ref=False)
+    port = ob.Port()
+    chk, kind = (ob.Ref(), "reference") if ob.have_ref() else (port, "port")
+    nproc = chk.num_procs()
+    chk.set_threads(nproc)
+    W, H, flag, vx, vy, dt, items, st = explosion_inputs(name, max(n_items, n_tracers))
+    sim = chk.Sim(flag, PWIDTH, MU)
+    sim.set(ob.VX, vx)
+    sim.set(ob.VY, vy)
+    sim.step(dt)
+    g = cases.LCG(99)
+    full, simres = flag.copy(), flag.copy()
+    t0 = time.perf_counter()
+    for cx, cy, d in crater_list(g, W, H):
+        port.draw_circle(full, simres, cx, cy, int(d), 1.0)
+    sim.update_flag(simres)
+    t_terrain = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    sim.step(dt)
+    t_step = time.perf_counter() - t0
+    it = np.ascontiguousarray(items[:n_items])
+    t0 = time.perf_counter()
+    if kind == "reference":
+        chk.items_advect_simple(sim, it, GAME_DT)
+    else:
+        ax, ay = np.zeros((H, W - 1), np.float32), np.zeros((H - 1, W), np.float32)
+        port.items_advect_simple(it, GAME_DT, simres, sim.get(ob.VX), sim.get(ob.VY), sim.get(ob.P), ax, ay)
+    t_items = time.perf_counter() - t0
+    # tracers: crop of the co-located texture is not possible (positions span the domain): build it once
+    S = 1024  # the tracer shader is timed against a 1024^2 member of the same generator (texture build is O(N))
+    fl2, _ = cases.channel_flag(S, S, seed=1234)
+    vx2, vy2 = cases.uniform_stream(fl2)
+    vxy, _ = port.colocate(vx2, vy2)
+    st2 = {k: np.ascontiguousarray(v[:n_tracers]) for k, v in st.items()}
+    t0 = time.perf_counter()
+    port.tracers_advect(st2, GAME_DT, (np.float32(PWIDTH), np.float32(PWIDTH)), 1, vxy, fl2)
+    t_tr = time.perf_counter() - t0
+    return {"value": W * H / t_step / 1e6, "unit": "MLUP/s", "cores": nproc, "kind": kind,
+            "sample": f"{name}: 1 warm-up + 1 timed Simulation::step ({t_step * 1e3:.0f} ms, {nproc} OMP threads); "
+                      f"16 craters + updateFields {t_terrain * 1e3:.1f} ms; advectFloatingItemsSimple on {n_items} items "
+                      f"{t_items * 1e3:.0f} ms serial ({n_items / t_items:.3g} items/s; cost grows ~N^2/100); tracer shader "
+                      f"restatement on {n_tracers} tracers {t_tr * 1e3:.1f} ms serial ({n_tracers / t_tr:.3g} tracers/s, port)",
+            "items_per_s": n_items / t_items, "tracers_per_s": n_tracers / t_tr}
+
+
 # algorithmic bytes per cell OF ITS LEVEL for each kernel kind (SURVEY.md 8d rule:
 # every distinct input array once, every output once, fp32)
 KERNEL_BYTES = {
@@ -336,7 +543,7 @@ def dominant_roofline(kern, W, H, peak, peak_src, prof_ms_step, cells_scale=1.0,
             "avg_launch_ms": per_launch_ms, "share_of_step": ms / prof_ms_step if prof_ms_step else None,
             "algorithmic_bytes_per_launch": bytes_launch, "achieved": ach, "peak": peak, "unit": "GB/s",
             "frac": ach / peak, "traffic": ncu_traffic(workload, k, l) if cells_scale == 1.0 else None,
-            "traffic_source": f"profiles/traffic_{workload}.json (ncu --set full, DRAM read+write bytes per launch)",
+            "traffic_source": None if workload is None else f"profiles/traffic_{workload}.json (ncu --set full, DRAM read+write bytes per launch)",
             "peak_source": peak_src}
 
 
@@ -353,6 +560,8 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
     if args.gpus == 1 and int(os.environ.get("WORLD_SIZE", "1")) == 1:
+        if (args.workload or "").startswith("explosion"):
+            return run_explosion(args, args.workload)
         return run_single_gpu(args, args.workload or "channel8192")
     from ubootgl_b200 import slab_bench
     return slab_bench.run(args, args.workload or "channel32768")

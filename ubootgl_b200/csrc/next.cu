@@ -13,6 +13,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <vector>
 
 namespace ubgl {
@@ -664,8 +665,10 @@ int ubgl_sim_draw_circles(ubgl_sim_t *sim, const float *xyd, int n, float val) {
   }
   float *d_xyd = nullptr;
   UBGL_CUDA(cudaMallocAsync(&d_xyd, sizeof(float) * 3 * n, S.stream));
-  UBGL_CUDA(cudaMemcpyAsync(d_xyd, xyd, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, S.stream));
-  UBGL_CUDA(cudaStreamSynchronize(S.stream)); // xyd is caller memory
+  float *hs = S.stage_host((size_t)3 * n); // xyd is caller memory: stage it, stay asynchronous
+  std::memcpy(hs, xyd, sizeof(float) * 3 * n);
+  UBGL_CUDA(cudaMemcpyAsync(d_xyd, hs, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, S.stream));
+  S.stage_done();
   UBGL_LAUNCH(&S.lc, K_TERRAIN, 0, S.stream, k_draw_circles<<<n, 256, 0, S.stream>>>(S.field(F_FLAG), d_xyd, n, val));
   UBGL_CUDA(cudaFreeAsync(d_xyd, S.stream));
   S.flag_changed(true); // MG::updateFields + stencil masks (ubootgl_app.cpp:111-112)
@@ -700,8 +703,10 @@ int ubgl_sim_shift_map(ubgl_sim_t *sim, const float *new_last_column) {
   NEED(new_last_column, "new_last_column");
   float *d_col = nullptr;
   UBGL_CUDA(cudaMallocAsync(&d_col, sizeof(float) * S.H, S.stream));
-  UBGL_CUDA(cudaMemcpyAsync(d_col, new_last_column, sizeof(float) * S.H, cudaMemcpyHostToDevice, S.stream));
-  UBGL_CUDA(cudaStreamSynchronize(S.stream));
+  float *hs = S.stage_host((size_t)S.H);
+  std::memcpy(hs, new_last_column, sizeof(float) * S.H);
+  UBGL_CUDA(cudaMemcpyAsync(d_col, hs, sizeof(float) * S.H, cudaMemcpyHostToDevice, S.stream));
+  S.stage_done();
   Grid none{};
   cudaStream_t st = S.stream;
   // velocities: front shifted, back receives the same values (ubootgl_app.cpp:254-266)

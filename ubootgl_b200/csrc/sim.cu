@@ -362,6 +362,8 @@ DeviceSim::~DeviceSim() {
   free_grid(p); free_grid(f); free_grid(flag); free_grid(r);
   if (d_sinks) cudaFree(d_sinks);
   if (d_fnorm) cudaFree(d_fnorm);
+  if (h_stage) cudaFreeHost(h_stage);
+  if (ev_stage) cudaEventDestroy(ev_stage);
   if (d_vxy) cudaFree(d_vxy);
   if (d_mag) cudaFree(d_mag);
   if (stream) cudaStreamDestroy(stream);
@@ -547,6 +549,20 @@ void DeviceSim::project() {
   UBGL_LAUNCH(&lc, K_GRADIENT, LVL, stream, k_gradient<<<grd2d(W - 2, H - 2), blk2d(), 0, stream>>>(vxb[ixf], vyb[iyf], p, flag, ih));
 }
 
+// Pinned host staging buffer for small per-step lists (sink stamps, crater lists).  One
+// buffer, reused: stage_host() waits until the previous copy out of it has completed.
+float *DeviceSim::stage_host(size_t nfloats) {
+  if (ev_stage) UBGL_CUDA(cudaEventSynchronize(ev_stage));
+  else UBGL_CUDA(cudaEventCreateWithFlags(&ev_stage, cudaEventDisableTiming));
+  if (nfloats > cap_stage) {
+    if (h_stage) UBGL_CUDA(cudaFreeHost(h_stage));
+    cap_stage = std::max<size_t>(nfloats * 2, 4096);
+    UBGL_CUDA(cudaMallocHost(&h_stage, sizeof(float) * cap_stage));
+  }
+  return h_stage;
+}
+void DeviceSim::stage_done() { UBGL_CUDA(cudaEventRecord(ev_stage, stream)); }
+
 void DeviceSim::project_sinks() {
   // sinks (simulation.cpp:173-187): grid position, border skip, decay and erase
   // are host-side list work exactly as in the reference; only the 3x3 stamps
@@ -573,9 +589,11 @@ void DeviceSim::project_sinks() {
       cap_sinks = n * 2;
       UBGL_CUDA(cudaMalloc(&d_sinks, sizeof(float) * 3 * cap_sinks));
     }
-    UBGL_CUDA(cudaMemcpyAsync(d_sinks, stamps.data(), sizeof(float) * stamps.size(),
-                              cudaMemcpyHostToDevice, stream));
-    UBGL_CUDA(cudaStreamSynchronize(stream)); // stamps is a stack-lifetime staging buffer
+    // pinned staging, so the copy is asynchronous and the host keeps running ahead of the GPU
+    float *hs = stage_host(stamps.size());
+    std::memcpy(hs, stamps.data(), sizeof(float) * stamps.size());
+    UBGL_CUDA(cudaMemcpyAsync(d_sinks, hs, sizeof(float) * stamps.size(), cudaMemcpyHostToDevice, stream));
+    stage_done();
     launch_stamp_sinks(f, d_sinks, n, 0, H, stream, &lc);
   }
 }

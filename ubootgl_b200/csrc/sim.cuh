@@ -116,6 +116,12 @@ public:
   float stage_ms[ST_COUNT] = {0, 0, 0, 0, 0, 0};
   // co-located velocity texture of interp_shader.cs (next.cu), allocated on first use
   float *d_vxy = nullptr, *d_mag = nullptr;
+  // pinned staging for small per-step host lists (see sim.cu)
+  float *stage_host(size_t nfloats);
+  void stage_done();
+  float *h_stage = nullptr;
+  size_t cap_stage = 0;
+  cudaEvent_t ev_stage = nullptr;
 
 private:
   // Three buffers per velocity component in the roles front / back
