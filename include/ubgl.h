@@ -69,8 +69,10 @@ enum ubgl_stage {
 /* tunables (ubgl_sim_set_option / ubgl_mg_set_option) */
 enum ubgl_option {
   UBGL_OPT_VCYCLES = 0,  /* V-cycles per project(); default 2 (simulation.cpp:189-190) */
-  UBGL_OPT_FUSED = 1,    /* 1 (default): fused / temporally blocked kernels;
-                            0: one plain kernel per reference stage (same results) */
+  UBGL_OPT_FUSED = 1,    /* non-zero (default 2): fused / temporally blocked kernels -- 2: multigrid
+                            passes with register-resident runs (k_mg_run), 1: the shared-memory
+                            tile schedule (k_mg_tile; the choice between 1 and 2 is process wide);
+                            0: one plain kernel per reference stage.  Same results in all three. */
   UBGL_OPT_GRAPH = 2,    /* reserved (accepted, no effect): the step is queued asynchronously on the
                             handle's stream and is GPU-bound at every measured size, so it is
                             not captured into a CUDA graph */

@@ -32,14 +32,15 @@ def test_vcycle_fused_equals_plain(ubgl, W, H, zg):
     p0 = rng.standard_normal((H, W)).astype(np.float32)
     hh = np.float32(0.8 / (W - 1))
     out = []
-    for fused in (1, 0):
+    for fused in (1, 2, 0):  # shared-memory tile kernels, register-run kernels (left selected), plain
         m = ubgl.MG(W, H)
         m.set_option(ubgl.capi.OPT_FUSED, fused)
         m.update_fields(flag)
         m.set(p0, f, flag)
         m.solve(hh, zg, 2)
         out.append(m.get_p())
-    assert same(out[0], out[1]), np.abs(out[0] - out[1]).max()
+    assert same(out[1], out[2]), ("run vs plain", np.abs(out[1] - out[2]).max())
+    assert same(out[0], out[2]), ("tile vs plain", np.abs(out[0] - out[2]).max())
 
 
 def test_nonbinary_flags_fall_back_to_plain(ubgl, port):
@@ -66,7 +67,7 @@ def test_step_fused_equals_plain(ubgl, W, H):
     from ubootgl_b200 import capi
     c = cases.sim_case(W, H, seed=W + H)
     outs = []
-    for fused in (1, 0):
+    for fused in (1, 2, 0):
         s = ubgl.Simulation(c["flag"])
         s.set_option(capi.OPT_FUSED, fused)
         s.set(capi.VX, c["vx"]); s.set(capi.VY, c["vy"])
@@ -76,5 +77,6 @@ def test_step_fused_equals_plain(ubgl, W, H):
             s.step(0.001)
         outs.append([s.get(f) for f in (capi.VX, capi.VY, capi.P, capi.F, capi.VXB, capi.VYB,
                                         capi.VX_CURRENT, capi.VY_CURRENT, capi.VX_ACCUM)])
-    for a, b in zip(*outs):
-        assert same(a, b), np.abs(a - b).max()
+    for a, b, c_ in zip(*outs):
+        assert same(b, c_), ("run vs plain", np.abs(b - c_).max())
+        assert same(a, c_), ("tile vs plain", np.abs(a - c_).max())

@@ -135,6 +135,31 @@ def test_step_host_mirrors(ubgl, port):
     assert (ax == O.get(ob.VX_ACCUM)).all() and (ay == O.get(ob.VY_ACCUM)).all()
 
 
+def test_step_host_banded_current_mirrors(ubgl):
+    """Above 16 MB per field the velocity mirrors come down in row bands and the
+    *_current mirrors are host copies of them (saveCurrentVelocityFields is a memcpy,
+    simulation.cpp:16-19): every mirror must equal the device field bit for bit."""
+    from ubootgl_b200 import capi
+    W, H = 2307, 2050
+    c = cases.sim_case(W, H, seed=11)
+    G = ubgl.Simulation(c["flag"], device=0)
+    G.set(capi.VX, c["vx"]); G.set(capi.VY, c["vy"])
+    ax, ay = c["vx_accum"].copy(), c["vy_accum"].copy()
+    out = {k: np.full(s, np.nan, np.float32) for k, s in
+           dict(vx=(H, W - 1), vy=(H - 1, W), p=(H, W), vx_current=(H, W - 1),
+                vy_current=(H - 1, W)).items()}
+    for _ in range(2):
+        G.step_host(0.0005, vx_accum=ax, vy_accum=ay, **out)
+    for name, fid in (("vx", capi.VX), ("vy", capi.VY), ("p", capi.P),
+                      ("vx_current", capi.VX_CURRENT), ("vy_current", capi.VY_CURRENT)):
+        assert np.array_equal(out[name], G.get(fid)), name
+    assert not ax[1:-1, 1:-2].any() and not ay[1:-2, 1:-1].any()
+    # only one of the pair requested: plain downloads
+    only = np.full((H, W - 1), np.nan, np.float32)
+    G.step_host(0.0005, vx_current=only)
+    assert np.array_equal(only, G.get(capi.VX_CURRENT))
+
+
 def test_flag_update_rebuilds_pyramid(ubgl, port):
     W, H = 130, 97
     G, O, c = make_pair(ubgl, port, W, H, seed=2)

@@ -87,7 +87,7 @@ int ubgl_sim_set_option(ubgl_sim_t *sim, int option, int value) {
     UBGL_REQUIRE(value >= 0, "vcycles must be >= 0");
     S.vcycles = value;
     break;
-  case UBGL_OPT_FUSED: S.fused = value != 0; S.mg->fused = value != 0; break;
+  case UBGL_OPT_FUSED: S.fused = value != 0; S.mg->fused = value != 0; if (value) set_tile_variant(value); break;
   case UBGL_OPT_GRAPH: S.use_graph = value != 0; break;
   case UBGL_OPT_TIMING: S.timing = value != 0; break;
   default: throw ArgError{"unknown option"};
@@ -187,30 +187,63 @@ int ubgl_sim_stage(ubgl_sim_t *sim, int stage, float dt) {
   UBGL_CATCH
 }
 
-// Host side of applyAccumulatedVelocity's "accum = 0" (simulation.cpp:384,392):
-// interior rows 1..H-2 x cols 1..W-3 of vx_accum ((W-1) x H) and rows 1..H-3 x
-// cols 1..W-2 of vy_accum (W x (H-1)).  Large mirrors are cleared by a few
-// threads (a single core memsets ~10 GB/s; 8192^2 mirrors are 0.5 GB).
-static void zero_accum_mirrors(float *ax, float *ay, int W, int H) {
-  auto rows = [&](int y0, int y1) {
-    if (ax)
-      for (int y = std::max(y0, 1); y < std::min(y1, H - 1); y++)
-        std::memset(ax + (size_t)y * (W - 1) + 1, 0, sizeof(float) * (W - 3));
-    if (ay)
-      for (int y = std::max(y0, 1); y < std::min(y1, H - 2); y++)
-        std::memset(ay + (size_t)y * W + 1, 0, sizeof(float) * (W - 2));
-  };
-  const size_t bytes = sizeof(float) * (size_t)W * H * ((ax ? 1 : 0) + (ay ? 1 : 0));
+// Host side of ubgl_sim_step_host.  Two jobs run on a few host threads while the
+// GPU steps and the DMA engines copy:
+//  * applyAccumulatedVelocity's "accum = 0" (simulation.cpp:384,392): interior rows
+//    1..H-2 x cols 1..W-3 of vx_accum ((W-1) x H) and rows 1..H-3 x cols 1..W-2 of
+//    vy_accum (W x (H-1)), as soon as the upload has consumed the mirrors;
+//  * saveCurrentVelocityFields (simulation.cpp:16-19) for the mirrors: vx_current /
+//    vy_current are byte copies of the final front vx / vy, so they are filled from
+//    the freshly downloaded vx / vy mirror band by band (a host memcpy behind the
+//    D->H copy) instead of crossing PCIe a second time.
+struct HostBand {
+  cudaEvent_t ready = nullptr; // the D->H copy of this band has landed
+  const float *src = nullptr;
+  float *dst = nullptr;
+  size_t bytes = 0;
+};
+
+static void host_side_work(int device, cudaEvent_t uploaded, float *ax, float *ay, int W, int H,
+                           std::vector<HostBand> &bands, cudaError_t *first_err) {
+  const size_t big = (size_t)(16 << 20);
+  size_t total = 0;
+  for (auto &b : bands) total += b.bytes;
+  if (uploaded) total += sizeof(float) * (size_t)W * H * ((ax ? 1 : 0) + (ay ? 1 : 0));
   unsigned nt = std::thread::hardware_concurrency();
   nt = std::min(nt ? nt : 1u, 8u);
-  if (bytes < (size_t)(16 << 20) || nt < 2) {
-    rows(0, H);
-    return;
+  if (total < big) nt = 1;
+  std::vector<cudaError_t> errs(nt, cudaSuccess);
+  auto work = [&](unsigned t) {
+    cudaSetDevice(device);
+    if (uploaded) {
+      cudaError_t e = cudaEventSynchronize(uploaded);
+      if (e != cudaSuccess) errs[t] = e;
+      const int y0 = (int)((long long)H * t / nt), y1 = (int)((long long)H * (t + 1) / nt);
+      if (ax)
+        for (int y = std::max(y0, 1); y < std::min(y1, H - 1); y++)
+          std::memset(ax + (size_t)y * (W - 1) + 1, 0, sizeof(float) * (W - 3));
+      if (ay)
+        for (int y = std::max(y0, 1); y < std::min(y1, H - 2); y++)
+          std::memset(ay + (size_t)y * W + 1, 0, sizeof(float) * (W - 2));
+    }
+    for (size_t b = t; b < bands.size(); b += nt) {
+      cudaError_t e = cudaEventSynchronize(bands[b].ready);
+      if (e != cudaSuccess) {
+        errs[t] = e;
+        continue;
+      }
+      std::memcpy(bands[b].dst, bands[b].src, bands[b].bytes);
+    }
+  };
+  if (nt < 2) {
+    work(0);
+  } else {
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; t++) th.emplace_back(work, t);
+    for (auto &t : th) t.join();
   }
-  std::vector<std::thread> th;
-  for (unsigned t = 0; t < nt; t++)
-    th.emplace_back(rows, (int)((long long)H * t / nt), (int)((long long)H * (t + 1) / nt));
-  for (auto &t : th) t.join();
+  for (auto e : errs)
+    if (e != cudaSuccess && *first_err == cudaSuccess) *first_err = e;
 }
 
 int ubgl_sim_step_host(ubgl_sim_t *sim, float dt, const ubgl_host_mirrors *m) {
@@ -231,29 +264,64 @@ int ubgl_sim_step_host(ubgl_sim_t *sim, float dt, const ubgl_host_mirrors *m) {
     upload_grid(g, m->vy_accum, g.w, g.h, S.stream);
   }
   cudaEvent_t uploaded = nullptr;
-  if (m->vx_accum || m->vy_accum) {
-    UBGL_CUDA(cudaEventCreateWithFlags(&uploaded, cudaEventDisableTiming));
-    UBGL_CUDA(cudaEventRecord(uploaded, S.stream));
-  }
-  S.step(dt); // asynchronous: every kernel of the step is now queued behind the uploads
-  struct { int id; float *dst; } outs[] = {{F_VX, m->vx}, {F_VY, m->vy}, {F_P, m->p},
-                                           {F_VX_CURRENT, m->vx_current},
-                                           {F_VY_CURRENT, m->vy_current}};
-  for (auto &o : outs)
-    if (o.dst) {
-      Grid g = S.field(o.id);
-      download_grid(g, o.dst, g.w, g.h, S.stream);
+  std::vector<HostBand> bands;
+  auto cleanup = [&]() {
+    if (uploaded) cudaEventDestroy(uploaded);
+    for (auto &b : bands)
+      if (b.ready) cudaEventDestroy(b.ready);
+  };
+  try {
+    if (m->vx_accum || m->vy_accum) {
+      UBGL_CUDA(cudaEventCreateWithFlags(&uploaded, cudaEventDisableTiming));
+      UBGL_CUDA(cudaEventRecord(uploaded, S.stream));
     }
-  if (uploaded) {
-    // the reference zeroes the interior of the accumulators while applying them
-    // (simulation.cpp:384,392); the host mirrors follow as soon as the upload has consumed
-    // them -- on host threads, while the GPU runs the step
-    cudaError_t e = cudaEventSynchronize(uploaded);
-    cudaEventDestroy(uploaded);
-    UBGL_CUDA(e);
-    zero_accum_mirrors(m->vx_accum, m->vy_accum, S.W, S.H);
+    S.step(dt); // asynchronous: every kernel of the step is now queued behind the uploads
+    // velocity mirrors first: a component whose *_current mirror is wanted too comes down
+    // in row bands, each followed by an event the host copy threads wait on; p last, so
+    // the host copies of the final bands hide behind its transfer
+    struct { int id, cur_id; float *dst, *cur; } vel[] = {{F_VX, F_VX_CURRENT, m->vx, m->vx_current},
+                                                          {F_VY, F_VY_CURRENT, m->vy, m->vy_current}};
+    for (auto &o : vel) {
+      if (o.dst && o.cur) {
+        Grid g = S.field(o.id);
+        const size_t row = sizeof(float) * (size_t)g.w;
+        const int nb = (size_t)g.h * row >= (size_t)(16 << 20) ? std::min(32, g.h) : 1;
+        for (int b = 0; b < nb; b++) {
+          const int y0 = (int)((long long)g.h * b / nb), y1 = (int)((long long)g.h * (b + 1) / nb);
+          UBGL_CUDA(cudaMemcpy2DAsync(o.dst + (size_t)y0 * g.w, row, g.d + (size_t)y0 * g.pitch,
+                                      sizeof(float) * g.pitch, row, y1 - y0, cudaMemcpyDeviceToHost,
+                                      S.stream));
+          HostBand hb;
+          UBGL_CUDA(cudaEventCreateWithFlags(&hb.ready, cudaEventDisableTiming));
+          bands.push_back(hb);
+          HostBand &k = bands.back();
+          UBGL_CUDA(cudaEventRecord(k.ready, S.stream));
+          k.src = o.dst + (size_t)y0 * g.w;
+          k.dst = o.cur + (size_t)y0 * g.w;
+          k.bytes = row * (size_t)(y1 - y0);
+        }
+      } else if (o.dst) {
+        Grid g = S.field(o.id);
+        download_grid(g, o.dst, g.w, g.h, S.stream);
+      } else if (o.cur) {
+        Grid g = S.field(o.cur_id);
+        download_grid(g, o.cur, g.w, g.h, S.stream);
+      }
+    }
+    if (m->p) {
+      Grid g = S.field(F_P);
+      download_grid(g, m->p, g.w, g.h, S.stream);
+    }
+    cudaError_t herr = cudaSuccess;
+    if (uploaded || !bands.empty())
+      host_side_work(S.device, uploaded, m->vx_accum, m->vy_accum, S.W, S.H, bands, &herr);
+    UBGL_CUDA(herr);
+    S.sync();
+  } catch (...) {
+    cleanup();
+    throw;
   }
-  S.sync();
+  cleanup();
   UBGL_CATCH
 }
 
@@ -398,7 +466,7 @@ int ubgl_mg_set_option(ubgl_mg_t *mg, int option, int value) {
   UBGL_TRY
   MGH(mg);
   switch (option) {
-  case UBGL_OPT_FUSED: M.mg->fused = value != 0; break;
+  case UBGL_OPT_FUSED: M.mg->fused = value != 0; if (value) set_tile_variant(value); break;
   case UBGL_OPT_GRAPH: case UBGL_OPT_TIMING: case UBGL_OPT_VCYCLES: break;
   default: throw ArgError{"unknown option"};
   }

@@ -80,6 +80,8 @@ void launch_mg_post(const float *p_in, float *p_out, const Grid &f, const uint8_
                     const Grid &ec, const uint8_t *maskc, float hh, bool zgbc, cudaStream_t stream,
                     LaunchCounter *lc, int level, const Rows *rows = nullptr,
                     const Rows *crows = nullptr);
+void set_tile_variant(int v); // 2: k_mg_run (default), 1: k_mg_tile
+int tile_variant();
 void launch_mg_smooth5(float *p_out, const Grid &f, const uint8_t *mask, float hh,
                        cudaStream_t stream, LaunchCounter *lc, int level);
 void launch_make_mask(const Grid &flag, uint8_t *mask, int *d_nonbinary, cudaStream_t stream,

@@ -36,6 +36,8 @@
 // (solveLevel).
 #include "mg.cuh"
 #include "stencils.cuh"
+#include <cstdlib>
+#include <type_traits>
 
 namespace ubgl {
 
@@ -423,6 +425,387 @@ __global__ void __launch_bounds__(NT, 2) k_mg_tile(TileArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------
+// k_mg_run -- the same PRE / POST passes (S = 3) with the thread's cells held in
+// REGISTERS.  k_mg_tile above is bound by the shared-memory pipe (ncu: L1/shared
+// 70 %, issue 50 %, DRAM 19 %): every 4-cell update re-reads f, the weight table
+// and three rows of the other colour from shared memory.  Here a thread owns a
+// run of R consecutive window rows x 8 consecutive cells (4 of each colour):
+//  * f*h*h and the smoothing weights of its 8R cells are loaded from HBM ONCE into
+//    registers and reused by all 6 half-sweeps (no F / weight traffic in the loop);
+//  * a half-sweep walks the run top to bottom, so the other colour's rows r-1, r,
+//    r+1 are a rolling register window: (R+2)/R instead of 3 128-bit loads per row;
+//  * the W / E neighbour outside the thread's 8 cells comes from the adjacent lane
+//    by shuffle instead of an unaligned 32-bit shared load.
+// Shared-memory traffic per 4-cell update drops from 26 to ~11 crossbar cycles and
+// the instruction count from ~50 to ~30.  R is even and window rows start even, so
+// the colour of every register slot is known at compile time.  Per-cell arithmetic
+// (order of additions, table weights) is unchanged: results are bit-identical to
+// k_mg_tile and to the plain path (tests/test_gpu_fused.py).
+// ---------------------------------------------------------------------------
+constexpr int RUN_R = 4;                 // rows per thread
+constexpr int RUN_NCH = 16;              // row chunks per window
+constexpr int RUN_LH = RUN_R * RUN_NCH;  // 64 window rows
+constexpr int RUN_NT = 16 * RUN_NCH;     // 16 column groups x 16 chunks = 256 threads
+constexpr int RUN_HX = 8;                // x halo: whole 8-cell column groups
+
+template <int MODE> struct RunGeom {
+  static constexpr int S = 3;
+  static constexpr int HY = (MODE == MODE_PRE) ? 8 : 6; // 2S (+2: residual, restriction)
+  static constexpr int TX = LW - 2 * RUN_HX;
+  static constexpr int TY = RUN_LH - 2 * HY;
+  static constexpr size_t p_floats = 2 * (RUN_LH + 2) * RS; // one pad row above and below
+  static constexpr size_t r_floats = (MODE == MODE_PRE) ? 2 * RUN_LH * RS : 0;
+  static constexpr size_t smem = sizeof(float) * (p_floats + r_floats + 8) + 2 * RUN_LH * RS;
+};
+
+__device__ __forceinline__ float4 lds4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+
+template <int MODE>
+__global__ void __launch_bounds__(RUN_NT, 2) k_mg_run(TileArgs a) {
+  using G = RunGeom<MODE>;
+  constexpr int S = G::S, R = RUN_R, LH = RUN_LH, NT = RUN_NT, HX = RUN_HX, HY = G::HY;
+  constexpr int TX = G::TX, TY = G::TY, NW = NT / 32;
+  static_assert(R % 2 == 0 && HY % 2 == 0 && TX % 8 == 0 && TY % 2 == 0, "run geometry");
+
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float *sP = reinterpret_cast<float *>(smem_raw);
+  float *sR = sP + G::p_floats;
+  float *rcpt = sR + G::r_floats;
+  uint8_t *sM = reinterpret_cast<uint8_t *>(rcpt + 8);
+  auto P = [&](int pl, int r) -> float * { return sP + (pl * (LH + 2) + r + 1) * RS; };
+  auto Rr = [&](int pl, int r) -> float * { return sR + (pl * LH + r) * RS; };
+  auto M = [&](int pl, int r) -> uint8_t * { return sM + (pl * LH + r) * RS; };
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tg = lane & 15, chunk = 2 * warp + (lane >> 4);
+  const int r0 = R * chunk, ci = XO + 4 * tg;
+  const unsigned hmask = 0xFFFFu << (lane & 16); // the 16 lanes that share this row chunk
+  const int x0 = blockIdx.x * TX, y0 = a.own_lo + blockIdx.y * TY;
+  const int X0 = x0 - HX, Y0 = y0 - HY; // X0 % 8 == 0, Y0 even: local parity == global parity
+  const int w = a.w, h = a.h;
+  const int gx8 = X0 + 8 * tg;
+
+  if (threadIdx.x < 8) rcpt[threadIdx.x] = rcp_count(threadIdx.x);
+
+  // ---- stage: p and the mask go to shared memory (colour planes), f*h*h stays in
+  // registers; slot E = the thread's cells 0,2,4,6, slot O = cells 1,3,5,7 ----
+  float4 FE[R], FO[R], WE[R], WO[R];
+  {
+    unsigned ME[R], MO[R];
+#pragma unroll
+    for (int i = 0; i < R; i++) {
+      const int r = r0 + i, gy = Y0 + r;
+      float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0, f0 = p0, f1 = p0;
+      uint2 mv = make_uint2(0u, 0u);
+      if (gy >= a.st_lo && gy < a.st_hi && gx8 >= 0 && gx8 < a.pitch) {
+        const size_t o = (size_t)gy * a.pitch + gx8;
+        if (a.p_in) {
+          p0 = *reinterpret_cast<const float4 *>(a.p_in + o);
+          p1 = *reinterpret_cast<const float4 *>(a.p_in + o + 4);
+        }
+        f0 = __ldg(reinterpret_cast<const float4 *>(a.f + o));
+        f1 = __ldg(reinterpret_cast<const float4 *>(a.f + o + 4));
+        mv = __ldg(reinterpret_cast<const uint2 *>(a.mask + o));
+      }
+      ME[i] = __byte_perm(mv.x, mv.y, 0x6420);
+      MO[i] = __byte_perm(mv.x, mv.y, 0x7531);
+      const float4 pe = make_float4(sel0(ME[i], MB_C, p0.x), sel0(ME[i] >> 8, MB_C, p0.z),
+                                    sel0(ME[i] >> 16, MB_C, p1.x), sel0(ME[i] >> 24, MB_C, p1.z));
+      const float4 po = make_float4(sel0(MO[i], MB_C, p0.y), sel0(MO[i] >> 8, MB_C, p0.w),
+                                    sel0(MO[i] >> 16, MB_C, p1.y), sel0(MO[i] >> 24, MB_C, p1.w));
+      // cell j of row r has colour (j + r) & 1 = (j + i) & 1
+      *reinterpret_cast<float4 *>(P(i & 1, r) + ci) = pe;
+      *reinterpret_cast<float4 *>(P((i & 1) ^ 1, r) + ci) = po;
+      *reinterpret_cast<unsigned *>(M(i & 1, r) + ci) = ME[i];
+      *reinterpret_cast<unsigned *>(M((i & 1) ^ 1, r) + ci) = MO[i];
+      FE[i] = make_float4(fh2_of(f0.x, a.hh), fh2_of(f0.z, a.hh), fh2_of(f1.x, a.hh), fh2_of(f1.z, a.hh));
+      FO[i] = make_float4(fh2_of(f0.y, a.hh), fh2_of(f0.w, a.hh), fh2_of(f1.y, a.hh), fh2_of(f1.w, a.hh));
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < R; i++) {
+      WE[i] = make_float4(rcpt[(ME[i] >> 2) & 7u], rcpt[(ME[i] >> 10) & 7u], rcpt[(ME[i] >> 18) & 7u],
+                          rcpt[(ME[i] >> 26) & 7u]);
+      WO[i] = make_float4(rcpt[(MO[i] >> 2) & 7u], rcpt[(MO[i] >> 10) & 7u], rcpt[(MO[i] >> 18) & 7u],
+                          rcpt[(MO[i] >> 26) & 7u]);
+    }
+  }
+
+  // Per-thread 4-bit masks over its 4 cells of slot q (bits 4q .. 4q+3):
+  // fz: cells on the global W/E border column (never updated); in: 1 <= gx <= w-2.
+  unsigned fzb = 0, inb = 0;
+#pragma unroll
+  for (int q = 0; q < 2; q++) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int gx = gx8 + 2 * j + q;
+      if (gx == 0 || gx == w - 1) fzb |= 1u << (4 * q + j);
+      if (gx >= 1 && gx <= w - 2) inb |= 1u << (4 * q + j);
+    }
+  }
+
+  auto lo = [](int origin, int k) { return max(1, origin + k); };
+  auto hi = [](int origin, int len, int n, int k) { return min(n - 1, origin + len - k); };
+
+  // W / E neighbours of the 4 cells of slot q, given the other colour's 4 cells A of
+  // the same row: q == 0: W = (left lane's A.w, A.x, A.y, A.z), E = A;
+  //               q == 1: W = A, E = (A.y, A.z, A.w, right lane's A.x).
+  // The window edge reads 0 (the cell beyond it is outside the valid trapezoid anyway).
+  auto edge = [&](const float4 &A, int q) {
+    float e = q == 0 ? __shfl_up_sync(hmask, A.w, 1, 16) : __shfl_down_sync(hmask, A.x, 1, 16);
+    return (tg == (q == 0 ? 0 : 15)) ? 0.0f : e;
+  };
+
+  // one colour of one sweep over the rows of this thread's run that are still exact at time k
+  auto half_sweep = [&](int k, auto cpar_tag) {
+    constexpr int CPAR = decltype(cpar_tag)::value;
+    const int r_lo = lo(Y0, k) - Y0, r_hi = hi(Y0, LH, h, k) - Y0;
+    if (r0 + R <= r_lo || r0 >= r_hi) return;
+    const float *po = P(CPAR ^ 1, r0 - 1) + ci;
+    float *pd = P(CPAR, r0) + ci;
+    float4 Sv = lds4(po), A = lds4(po + RS);
+#pragma unroll
+    for (int i = 0; i < R; i++) {
+      const float4 Nv = lds4(po + (i + 2) * RS);
+      const int q = (CPAR + i) & 1;
+      const float ed = edge(A, q);
+      if (r0 + i >= r_lo && r0 + i < r_hi) {
+        const float4 Wv = q == 0 ? make_float4(ed, A.x, A.y, A.z) : A;
+        const float4 Ev = q == 0 ? A : make_float4(A.y, A.z, A.w, ed);
+        const float4 Fv = q == 0 ? FE[i] : FO[i];
+        const float4 Wt = q == 0 ? WE[i] : WO[i];
+        auto upd = [&](float pw, float pe, float ps, float pn, float f, float wt) {
+          float v = __fadd_rn(__fadd_rn(__fadd_rn(pw, pe), ps), pn);
+          return __fmul_rn(__fadd_rn(v, f), wt);
+        };
+        float4 v;
+        v.x = upd(Wv.x, Ev.x, Sv.x, Nv.x, Fv.x, Wt.x);
+        v.y = upd(Wv.y, Ev.y, Sv.y, Nv.y, Fv.y, Wt.y);
+        v.z = upd(Wv.z, Ev.z, Sv.z, Nv.z, Fv.z, Wt.z);
+        v.w = upd(Wv.w, Ev.w, Sv.w, Nv.w, Fv.w, Wt.w);
+        float *d = pd + i * RS;
+        const unsigned z = (fzb >> (4 * q)) & 15u;
+        if (z == 0) {
+          *reinterpret_cast<float4 *>(d) = v;
+        } else {
+          if (!(z & 1)) d[0] = v.x;
+          if (!(z & 2)) d[1] = v.y;
+          if (!(z & 4)) d[2] = v.z;
+          if (!(z & 8)) d[3] = v.w;
+        }
+      }
+      Sv = A;
+      A = Nv;
+    }
+  };
+
+  auto cell = [&](int gx, int gy) -> float & {
+    const int lx = gx - X0, ly = gy - Y0;
+    return P((lx + ly) & 1, ly)[XO + (lx >> 1)];
+  };
+  auto mbyte = [&](int gx, int gy) -> unsigned {
+    const int lx = gx - X0, ly = gy - Y0;
+    return M((lx + ly) & 1, ly)[XO + (lx >> 1)];
+  };
+
+  // setZeroGradientBC on the border cells whose interior neighbour is still exact at
+  // time k (see k_mg_tile)
+  auto zero_gradient = [&](int k) {
+    const int gx_lo = lo(X0, k), gx_hi = hi(X0, LW, w, k);
+    const int gy_lo = lo(Y0, k), gy_hi = hi(Y0, LH, h, k);
+    const int t = threadIdx.x;
+    if (X0 <= 0 && gx_lo == 1)
+      for (int gy = gy_lo + t; gy < gy_hi; gy += NT) cell(0, gy) = sel0(mbyte(0, gy), MB_C, cell(1, gy));
+    if (w - 1 < X0 + LW && gx_hi == w - 1)
+      for (int gy = gy_lo + t; gy < gy_hi; gy += NT)
+        cell(w - 1, gy) = sel0(mbyte(w - 1, gy), MB_C, cell(w - 2, gy));
+    if (Y0 <= 0 && gy_lo == 1)
+      for (int gx = gx_lo + t; gx < gx_hi; gx += NT) cell(gx, 0) = sel0(mbyte(gx, 0), MB_C, cell(gx, 1));
+    if (h - 1 < Y0 + LH && gy_hi == h - 1)
+      for (int gx = gx_lo + t; gx < gx_hi; gx += NT)
+        cell(gx, h - 1) = sel0(mbyte(gx, h - 1), MB_C, cell(gx, h - 2));
+  };
+
+  if (MODE == MODE_POST) {
+    // prolongate + correct (pressure_solver.cpp:134-181), one thread per COARSE cell,
+    // exactly as in k_mg_tile
+    const int xcb = X0 >> 1, ycb = Y0 >> 1;
+    for (int j = warp; j < LH / 2; j += NW) {
+      const int yc = ycb + j, y = 2 * yc;
+      if (yc < a.c_lo || yc >= a.c_hi) continue;
+      const bool y_e = y >= 2 && y <= h - 2;
+      const bool y_o = y + 1 <= h - 3 && yc + 1 < a.c_hi;
+      const float *ecr = a.ec + (size_t)yc * a.pc;
+      const uint8_t *mcr = a.maskc + (size_t)yc * a.pc;
+      float *P0e = P(0, 2 * j), *P1e = P(1, 2 * j), *P0o = P(0, 2 * j + 1), *P1o = P(1, 2 * j + 1);
+      const uint8_t *M0e = M(0, 2 * j), *M1e = M(1, 2 * j), *M0o = M(0, 2 * j + 1), *M1o = M(1, 2 * j + 1);
+      for (int k = lane; k < HW; k += 32) {
+        const int xc = xcb + k, x = 2 * xc;
+        if (xc < 0 || xc >= a.wc) continue;
+        const bool x_e = x >= 2 && x <= w - 2, x_o = x + 1 <= w - 3;
+        const float e00 = __ldg(ecr + xc);
+        const float e10 = x_o ? __ldg(ecr + xc + 1) : 0.0f;
+        const float e01 = y_o ? __ldg(ecr + a.pc + xc) : 0.0f;
+        const float e11 = (x_o && y_o) ? __ldg(ecr + a.pc + xc + 1) : 0.0f;
+        const unsigned mc = __ldg(mcr + xc);
+        const unsigned mn = y_o ? __ldg(mcr + a.pc + xc) : 0u;
+        const int fC = mc & 1, fE = (mc >> 5) & 1, fN = (mc >> 7) & 1, fNE = (mn >> 5) & 1;
+        const int c = XO + k;
+        if (y_e) {
+          if (x_e) {
+            const float e = sel0(M0e[c], MB_C, e00);
+            P0e[c] = __fadd_rn(P0e[c], e);
+          }
+          if (x_o) {
+            const float e = __fmul_rn(sel0(M1e[c], MB_C, __fadd_rn(e00, e10)), prolong_rcp(fC + fE));
+            P1e[c] = __fadd_rn(P1e[c], e);
+          }
+        }
+        if (y_o) {
+          if (x_e) {
+            const float e = __fmul_rn(sel0(M1o[c], MB_C, __fadd_rn(e00, e01)), prolong_rcp(fC + fN));
+            P1o[c] = __fadd_rn(P1o[c], e);
+          }
+          if (x_o) {
+            const float es = __fadd_rn(__fadd_rn(__fadd_rn(e00, e11), e10), e01);
+            const float e = __fmul_rn(sel0(M0o[c], MB_C, es), prolong_rcp(fC + fNE + fE + fN));
+            P0o[c] = __fadd_rn(P0o[c], e);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    if (a.zgbc) {
+      zero_gradient(0);
+      __syncthreads();
+    }
+  }
+
+#pragma unroll 1
+  for (int s = 0; s < S; s++) {
+    half_sweep(2 * s + 1, std::integral_constant<int, 1>()); // "red":   (x+y) odd,  pressure_solver.cpp:35-40
+    __syncthreads();
+    half_sweep(2 * s + 2, std::integral_constant<int, 0>()); // "black": (x+y) even, pressure_solver.cpp:42-47
+    __syncthreads();
+    if (a.zgbc) {
+      zero_gradient(2 * s + 2);
+      __syncthreads();
+    }
+  }
+
+  if (MODE == MODE_PRE) {
+    // residual (pressure_solver.cpp:101-111, binary flags) of the thread's own cells on
+    // rows [HY-1, HY+TY+1), both colours, into the R planes; raw f is re-read (L2 hit)
+    const int rr_lo = HY - 1, rr_hi = HY + TY + 1;
+    if (r0 + R > rr_lo && r0 < rr_hi) {
+      const bool col_ok = gx8 >= 0 && gx8 < a.pitch;
+#pragma unroll
+      for (int cpar = 0; cpar < 2; cpar++) {
+        const float *po = P(cpar ^ 1, r0 - 1) + ci;
+        float4 Sv = lds4(po), A = lds4(po + RS);
+#pragma unroll
+        for (int i = 0; i < R; i++) {
+          const float4 Nv = lds4(po + (i + 2) * RS);
+          const int q = (cpar + i) & 1;
+          const float ed = edge(A, q);
+          const int r = r0 + i, gy = Y0 + r;
+          if (r >= rr_lo && r < rr_hi) {
+            const float4 Wv = q == 0 ? make_float4(ed, A.x, A.y, A.z) : A;
+            const float4 Ev = q == 0 ? A : make_float4(A.y, A.z, A.w, ed);
+            const float4 Cv = lds4(P(cpar, r) + ci);
+            const unsigned mw = *reinterpret_cast<const unsigned *>(M(cpar, r) + ci);
+            float4 f0 = make_float4(0.f, 0.f, 0.f, 0.f), f1 = f0;
+            if (col_ok && gy >= a.st_lo && gy < a.st_hi) {
+              const size_t o = (size_t)gy * a.pitch + gx8;
+              f0 = __ldg(reinterpret_cast<const float4 *>(a.f + o));
+              f1 = __ldg(reinterpret_cast<const float4 *>(a.f + o + 4));
+            }
+            const float4 Fv = q == 0 ? make_float4(f0.x, f0.z, f1.x, f1.z) : make_float4(f0.y, f0.w, f1.y, f1.w);
+            const bool rowin = gy >= 1 && gy <= h - 2;
+            const unsigned in = rowin ? (inb >> (4 * q)) & 15u : 0u;
+            auto res = [&](float pc_, float pw, float pe, float ps, float pn, float f, int j) {
+              const unsigned m = mw >> (8 * j);
+              float val = (m & MB_W) ? pw : pc_;
+              val = __fadd_rn(val, (m & MB_E) ? pe : pc_);
+              val = __fadd_rn(val, (m & MB_S) ? ps : pc_);
+              val = __fadd_rn(val, (m & MB_N) ? pn : pc_);
+              val = __fmaf_rn(-4.0f, pc_, val);
+              val = __fmul_rn(val, a.ihsq);
+              val = __fadd_rn(f, val);
+              return ((m & MB_C) && ((in >> j) & 1u)) ? val : 0.0f;
+            };
+            float4 v;
+            v.x = res(Cv.x, Wv.x, Ev.x, Sv.x, Nv.x, Fv.x, 0);
+            v.y = res(Cv.y, Wv.y, Ev.y, Sv.y, Nv.y, Fv.y, 1);
+            v.z = res(Cv.z, Wv.z, Ev.z, Sv.z, Nv.z, Fv.z, 2);
+            v.w = res(Cv.w, Wv.w, Ev.w, Sv.w, Nv.w, Fv.w, 3);
+            *reinterpret_cast<float4 *>(Rr(cpar, r) + ci) = v;
+          }
+          Sv = A;
+          A = Nv;
+        }
+      }
+    }
+    __syncthreads();
+    // full-weighting restriction of the coarse cells whose fine centre (2xc,2yc) lies in
+    // this tile; coarse border = 0 (rc.fill(0.0), pressure_solver.cpp:222)
+    const int xc0 = x0 >> 1, yc0 = y0 >> 1;
+    for (int j = warp; j < TY / 2; j += NW) {
+      const int yc = yc0 + j;
+      if (yc >= a.hc || 2 * yc >= a.own_hi) break;
+      const int ly = 2 * yc - Y0;
+      const float *F0m = Rr(0, ly - 1), *F1m = Rr(1, ly - 1), *F0c = Rr(0, ly), *F1c = Rr(1, ly),
+                  *F0p = Rr(0, ly + 1), *F1p = Rr(1, ly + 1);
+      for (int i = lane; i < TX / 2; i += 32) {
+        const int xc = xc0 + i;
+        if (xc >= a.wc) break;
+        float v = 0.0f;
+        if (xc >= 1 && yc >= 1 && xc < a.wc - 1 && yc < a.hc - 1) {
+          const int c = XO + ((2 * xc - X0) >> 1); // column of the (even,even) centre
+          v = fw9(F0m[c - 1], F1m[c], F0m[c], F1c[c - 1], F0c[c], F1c[c], F0p[c - 1], F1p[c], F0p[c]);
+        }
+        a.rc[(size_t)yc * a.pc + xc] = v;
+      }
+    }
+  }
+
+  // ---- write the thread's own tile cells back (p ping-pong buffer), 128-bit stores ----
+  if (tg >= HX / 8 && tg < (HX + TX) / 8) {
+#pragma unroll
+    for (int i = 0; i < R; i++) {
+      const int r = r0 + i, gy = Y0 + r;
+      if (r < HY || r >= HY + TY || gy >= a.own_hi || gx8 >= w) continue;
+      const float4 e = lds4(P(i & 1, r) + ci), o = lds4(P((i & 1) ^ 1, r) + ci);
+      float *dst = a.p_out + (size_t)gy * a.pitch + gx8;
+      *reinterpret_cast<float4 *>(dst) = make_float4(e.x, o.x, e.y, o.y);
+      if (gx8 + 4 < w) *reinterpret_cast<float4 *>(dst + 4) = make_float4(e.z, o.z, e.w, o.w);
+    }
+  }
+
+  // ---- border cells of this tile (see k_mg_tile) ----
+  const bool bx0 = x0 == 0, bx1 = (w - 1 >= x0 && w - 1 < x0 + TX);
+  const bool by0 = y0 == 0, by1 = (h - 1 >= y0 && h - 1 < y0 + TY && h - 1 < a.own_hi);
+  if (bx0 || bx1 || by0 || by1) {
+    __syncthreads();
+    const int t = threadIdx.x;
+    auto orig = [&](int gx, int gy) { return a.p_in ? a.p_in[(size_t)gy * a.pitch + gx] : 0.0f; };
+    auto put = [&](int gx, int gy, int nx, int ny) {
+      const bool corner = (gx == 0 || gx == w - 1) && (gy == 0 || gy == h - 1);
+      a.p_out[(size_t)gy * a.pitch + gx] = (a.zgbc && !corner) ? cell(nx, ny) : orig(gx, gy);
+    };
+    const int ty_hi = min(a.own_hi, y0 + TY), tx_hi = min(w, x0 + TX);
+    if (bx0)
+      for (int gy = y0 + t; gy < ty_hi; gy += NT) put(0, gy, 1, gy);
+    if (bx1)
+      for (int gy = y0 + t; gy < ty_hi; gy += NT) put(w - 1, gy, w - 2, gy);
+    if (by0)
+      for (int gx = x0 + t; gx < tx_hi; gx += NT) put(gx, 0, gx, 1);
+    if (by1)
+      for (int gx = x0 + t; gx < tx_hi; gx += NT) put(gx, h - 1, gx, h - 2);
+  }
+}
+
 // Stencil mask of a flag grid (layout: enum MB_* above; neighbours outside the
 // grid count as solid).  *nonbinary is raised if any flag is neither 0.0 nor 1.0
 // (then the bit form is not equivalent and the plain path is used).
@@ -472,6 +855,29 @@ static void launch_tile(const TileArgs &a, cudaStream_t stream, LaunchCounter *l
 
 constexpr int LH_MAIN = 80, NT_MAIN = 256;
 
+// 2 (default): k_mg_run (register runs); 1: k_mg_tile (shared-memory tiles).  Process
+// wide; set through UBGL_OPT_FUSED so the tests can compare the two schedules.
+static int env_tile_variant() {
+  const char *e = getenv("UBGL_TILE_VARIANT"); // A/B runs of bench.py; tests use UBGL_OPT_FUSED
+  return (e && e[0] == '1') ? 1 : 2;
+}
+static int g_tile_variant = env_tile_variant();
+void set_tile_variant(int v) { g_tile_variant = (v == 1) ? 1 : 2; }
+int tile_variant() { return g_tile_variant; }
+
+template <int MODE>
+static void launch_run(const TileArgs &a, cudaStream_t stream, LaunchCounter *lc, int kind, int level) {
+  using G = RunGeom<MODE>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    UBGL_CUDA(cudaFuncSetAttribute(k_mg_run<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)G::smem));
+    attr_set = true;
+  }
+  dim3 grid(ceil_div(a.w, G::TX), ceil_div(a.own_hi - a.own_lo, G::TY));
+  UBGL_LAUNCH(lc, kind, level, stream, k_mg_run<MODE><<<grid, RUN_NT, G::smem, stream>>>(a));
+}
+
 static void set_rows(TileArgs &a, const Rows *rows) {
   if (rows) {
     a.st_lo = rows->st_lo; a.st_hi = rows->st_hi; a.own_lo = rows->own_lo; a.own_hi = rows->own_hi;
@@ -490,7 +896,10 @@ void launch_mg_pre(const float *p_in, float *p_out, const Grid &f, const uint8_t
   a.rc = rc.d; a.wc = rc.w; a.hc = rc.h; a.pc = rc.pitch;
   a.hh = hh; a.ihsq = 1.0f / hh / hh; a.zgbc = zgbc ? 1 : 0;
   set_rows(a, rows);
-  launch_tile<3, MODE_PRE, LH_MAIN, NT_MAIN>(a, stream, lc, K_MG_PRE, level);
+  if (g_tile_variant == 2)
+    launch_run<MODE_PRE>(a, stream, lc, K_MG_PRE, level);
+  else
+    launch_tile<3, MODE_PRE, LH_MAIN, NT_MAIN>(a, stream, lc, K_MG_PRE, level);
 }
 
 void launch_mg_post(const float *p_in, float *p_out, const Grid &f, const uint8_t *mask,
@@ -506,7 +915,10 @@ void launch_mg_post(const float *p_in, float *p_out, const Grid &f, const uint8_
     a.c_lo = crows->st_lo;
     a.c_hi = crows->st_hi;
   }
-  launch_tile<3, MODE_POST, LH_MAIN, NT_MAIN>(a, stream, lc, K_MG_POST, level);
+  if (g_tile_variant == 2)
+    launch_run<MODE_POST>(a, stream, lc, K_MG_POST, level);
+  else
+    launch_tile<3, MODE_POST, LH_MAIN, NT_MAIN>(a, stream, lc, K_MG_POST, level);
 }
 
 void launch_mg_smooth5(float *p_out, const Grid &f, const uint8_t *mask, float hh,

@@ -216,29 +216,55 @@ __device__ __forceinline__ void bilinear_scatter(const Grid &g, float cx, float 
 
 // One thread per SORTED slot, so the lanes of a warp share a bin: the repulsion
 // loop (:167-181) walks the bin's positions in array order (stable sort == the
-// reference's push_back order) with warp-uniform broadcast loads.
-__global__ void __launch_bounds__(128) k_items_advect(Item *items, const int *order, const unsigned char *sbin,
-                                                      const int *off, const float2 *spos, int n, float game_dt,
-                                                      Grid flag, Grid vx, Grid vy, Grid p, Grid ax, Grid ay,
-                                                      float pwidth, float h) {
+// reference's push_back order).  It is the O(N^2/100) part of the reference
+// algorithm (10^10 pair tests for 10^6 items), so the positions of the bin(s) a
+// block touches are streamed through shared memory in tiles and every thread
+// reads them as warp-uniform broadcasts; each thread still visits exactly its own
+// bin's entries, in order, so the sums round as before.
+constexpr int ITEMS_NT = 128, ITEMS_TILE = 512;
+__global__ void __launch_bounds__(ITEMS_NT) k_items_advect(Item *items, const int *order, const unsigned char *sbin,
+                                                           const int *off, const float2 *spos, int n, float game_dt,
+                                                           Grid flag, Grid vx, Grid vy, Grid p, Grid ax, Grid ay,
+                                                           float pwidth, float h) {
+  __shared__ float2 tile[ITEMS_TILE];
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n) return;
-  Item it = items[order[k]];
-  const int b = sbin[k];
+  const bool live = k < n;
+  Item it;
+  int qs = 0, qe = 0;
+  if (live) {
+    it = items[order[k]];
+    const int b = sbin[k];
+    qs = off[b];
+    qe = off[b + 1];
+  }
   float rfx = 0.0f, rfy = 0.0f;
   int contacts = 0;
-  const float r2 = it.size[0] * it.size[1] * 0.4f, lmin = 0.1f * it.size[0];
-  for (int q = off[b], qe = off[b + 1]; q < qe; q++) {
-    const float2 o = __ldg(&spos[q]);
-    const float dx = it.pos[0] - o.x, dy = it.pos[1] - o.y;
-    const float d2 = dx * dx + dy * dy;
-    if (d2 < r2) {
-      const float len = fmaxf(lmin, sqrtf(d2));
-      rfx += 0.0001f * (dx / len / len);
-      rfy += 0.0001f * (dy / len / len);
-      contacts++;
+  const float r2 = live ? it.size[0] * it.size[1] * 0.4f : 0.0f, lmin = live ? 0.1f * it.size[0] : 0.0f;
+  const float px0 = live ? it.pos[0] : 0.0f, py0 = live ? it.pos[1] : 0.0f;
+  {
+    const int kf = blockIdx.x * blockDim.x, kl = min(kf + (int)blockDim.x, n) - 1;
+    const int qlo = off[sbin[kf]], qhi = off[sbin[kl] + 1]; // slots any thread of this block visits
+    for (int base = qlo; base < qhi; base += ITEMS_TILE) {
+      __syncthreads();
+      for (int t = threadIdx.x; t < ITEMS_TILE; t += ITEMS_NT)
+        tile[t] = base + t < qhi ? __ldg(&spos[base + t]) : make_float2(0.0f, 0.0f);
+      __syncthreads();
+      const int j1 = min(qe, base + ITEMS_TILE) - base;
+#pragma unroll 8
+      for (int j = max(qs, base) - base; j < j1; j++) {
+        const float2 o = tile[j];
+        const float dx = px0 - o.x, dy = py0 - o.y;
+        const float d2 = dx * dx + dy * dy;
+        if (d2 < r2) {
+          const float len = fmaxf(lmin, sqrtf(d2));
+          rfx += 0.0001f * (dx / len / len);
+          rfy += 0.0001f * (dy / len / len);
+          contacts++;
+        }
+      }
     }
   }
+  if (!live) return;
   const float cden = (float)max(contacts, 1);
   rfx /= cden;
   rfy /= cden;
