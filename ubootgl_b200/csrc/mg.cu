@@ -371,13 +371,21 @@ void DeviceMG::solve_fused(const Grid &p, const Grid &f, const Grid &flag, float
   hh[0] = hh0;
   for (int l = 0; l < L; l++) // :229
     hh[l + 1] = hh[l] * ((float)lv[l].w - 1.0f) / ((float)lv[l + 1].w - 1.0f);
-  for (int l = 0; l < L; l++) {
+  // levels t..L run in one launch (k_mg_tail) when they fit a CTA's shared memory
+  std::vector<TailLevel> tv;
+  for (auto &V : lv) tv.push_back(TailLevel{V.w, V.h, V.pitch, V.mask});
+  const int t = mg_tail_first_level(tv, 1);
+  const int Ld = t ? t : L; // levels [0, Ld) use the PRE / POST passes
+  for (int l = 0; l < Ld; l++) {
     const Grid &fl = (l == 0) ? f : lv[l].rc;
     launch_mg_pre(l == 0 ? p.d : nullptr, l == 0 ? scratch0.d : lv[l].eb.d, fl,
                   l == 0 ? mask0 : lv[l].mask, lv[l + 1].rc, hh[l], zgbc && l == 0, stream, lc, l);
   }
-  launch_mg_smooth5(lv[L].ec.d, lv[L].rc, lv[L].mask, hh[L], stream, lc, L);
-  for (int l = L - 1; l >= 0; l--) {
+  if (t)
+    launch_mg_tail(tv, t, hh.data(), lv[t].rc.d, lv[t].ec.d, stream, lc);
+  else
+    launch_mg_smooth5(lv[L].ec.d, lv[L].rc, lv[L].mask, hh[L], stream, lc, L);
+  for (int l = Ld - 1; l >= 0; l--) {
     const Grid &fl = (l == 0) ? f : lv[l].rc;
     launch_mg_post(l == 0 ? scratch0.d : lv[l].eb.d, l == 0 ? p.d : lv[l].ec.d, fl,
                    l == 0 ? mask0 : lv[l].mask, lv[l + 1].ec, lv[l + 1].mask, hh[l],

@@ -84,6 +84,14 @@ void set_tile_variant(int v); // 2: k_mg_run (default), 1: k_mg_tile
 int tile_variant();
 void launch_mg_smooth5(float *p_out, const Grid &f, const uint8_t *mask, float hh,
                        cudaStream_t stream, LaunchCounter *lc, int level);
+// k_mg_tail: levels t..L of the V-cycle in one single-CTA launch (shared-memory resident)
+struct TailLevel {
+  int w, h, pitch;
+  const uint8_t *mask;
+};
+int mg_tail_first_level(const std::vector<TailLevel> &lv, int t_min); // 0: none fits
+void launch_mg_tail(const std::vector<TailLevel> &lv, int t, const float *hh, const float *rhs,
+                    float *out, cudaStream_t stream, LaunchCounter *lc);
 void launch_make_mask(const Grid &flag, uint8_t *mask, int *d_nonbinary, cudaStream_t stream,
                       LaunchCounter *lc, int level, const Rows *rows = nullptr,
                     const Rows *crows = nullptr);

@@ -64,6 +64,7 @@ struct TileArgs {
   // indices), rows [own_lo, own_hi) are computed and written.  Single GPU: 0, h.
   int st_lo, st_hi, own_lo, own_hi;
   int c_lo, c_hi; // MODE_POST: rows of the coarse level stored here (single GPU: 0, hc)
+  int pf_dist;    // k_mg_run: L2-prefetch the window this many CTAs ahead (0: off)
 };
 
 constexpr int LW = 128;    // staged window width in cells
@@ -519,6 +520,10 @@ __global__ void __launch_bounds__(RUN_NT, 2) k_mg_run(TileArgs a) {
       *reinterpret_cast<float4 *>(P((i & 1) ^ 1, r) + ci) = po;
       *reinterpret_cast<unsigned *>(M(i & 1, r) + ci) = ME[i];
       *reinterpret_cast<unsigned *>(M((i & 1) ^ 1, r) + ci) = MO[i];
+      if (MODE == MODE_PRE) { // raw f waits in the (still unused) residual planes for the residual pass
+        *reinterpret_cast<float4 *>(Rr(i & 1, r) + ci) = make_float4(f0.x, f0.z, f1.x, f1.z);
+        *reinterpret_cast<float4 *>(Rr((i & 1) ^ 1, r) + ci) = make_float4(f0.y, f0.w, f1.y, f1.w);
+      }
       FE[i] = make_float4(fh2_of(f0.x, a.hh), fh2_of(f0.z, a.hh), fh2_of(f1.x, a.hh), fh2_of(f1.z, a.hh));
       FO[i] = make_float4(fh2_of(f0.y, a.hh), fh2_of(f0.w, a.hh), fh2_of(f1.y, a.hh), fh2_of(f1.w, a.hh));
     }
@@ -529,6 +534,30 @@ __global__ void __launch_bounds__(RUN_NT, 2) k_mg_run(TileArgs a) {
                           rcpt[(ME[i] >> 26) & 7u]);
       WO[i] = make_float4(rcpt[(MO[i] >> 2) & 7u], rcpt[(MO[i] >> 10) & 7u], rcpt[(MO[i] >> 18) & 7u],
                           rcpt[(MO[i] >> 26) & 7u]);
+    }
+  }
+
+  // L2 prefetch of the window the CTA that follows this one on the SM will stage (about one
+  // generation of resident CTAs ahead in launch order): with 2 CTAs x 8 warps per SM the
+  // staging loads are the largest stall of the kernel (ncu: long_sb 28 %), an L2 hit
+  // instead of an HBM miss shortens it.  No extra DRAM traffic: each line is still
+  // fetched once and used within ~one CTA lifetime (296 windows x 72 KB << 126 MB L2).
+  if (a.pf_dist > 0) {
+    const long long lb = (long long)blockIdx.y * gridDim.x + blockIdx.x + a.pf_dist;
+    if (lb < (long long)gridDim.x * gridDim.y) {
+      const int by = (int)(lb / gridDim.x), bx = (int)(lb - (long long)by * gridDim.x);
+      const int pgx = bx * TX - HX + 8 * tg, pY0 = a.own_lo + by * TY - HY;
+      if (pgx >= 0 && pgx < a.pitch) {
+#pragma unroll
+        for (int i = 0; i < R; i++) {
+          const int gy = pY0 + r0 + i;
+          if (gy < a.st_lo || gy >= a.st_hi) continue;
+          const size_t o = (size_t)gy * a.pitch + pgx;
+          if (a.p_in) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.p_in + o));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(a.f + o));
+          if ((tg & 3) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.mask + o));
+        }
+      }
     }
   }
 
@@ -696,10 +725,9 @@ __global__ void __launch_bounds__(RUN_NT, 2) k_mg_run(TileArgs a) {
 
   if (MODE == MODE_PRE) {
     // residual (pressure_solver.cpp:101-111, binary flags) of the thread's own cells on
-    // rows [HY-1, HY+TY+1), both colours, into the R planes; raw f is re-read (L2 hit)
+    // rows [HY-1, HY+TY+1), both colours, written over the raw f parked in the R planes
     const int rr_lo = HY - 1, rr_hi = HY + TY + 1;
     if (r0 + R > rr_lo && r0 < rr_hi) {
-      const bool col_ok = gx8 >= 0 && gx8 < a.pitch;
 #pragma unroll
       for (int cpar = 0; cpar < 2; cpar++) {
         const float *po = P(cpar ^ 1, r0 - 1) + ci;
@@ -715,13 +743,7 @@ __global__ void __launch_bounds__(RUN_NT, 2) k_mg_run(TileArgs a) {
             const float4 Ev = q == 0 ? A : make_float4(A.y, A.z, A.w, ed);
             const float4 Cv = lds4(P(cpar, r) + ci);
             const unsigned mw = *reinterpret_cast<const unsigned *>(M(cpar, r) + ci);
-            float4 f0 = make_float4(0.f, 0.f, 0.f, 0.f), f1 = f0;
-            if (col_ok && gy >= a.st_lo && gy < a.st_hi) {
-              const size_t o = (size_t)gy * a.pitch + gx8;
-              f0 = __ldg(reinterpret_cast<const float4 *>(a.f + o));
-              f1 = __ldg(reinterpret_cast<const float4 *>(a.f + o + 4));
-            }
-            const float4 Fv = q == 0 ? make_float4(f0.x, f0.z, f1.x, f1.z) : make_float4(f0.y, f0.w, f1.y, f1.w);
+            const float4 Fv = lds4(Rr(cpar, r) + ci); // raw f of these cells, parked at staging
             const bool rowin = gy >= 1 && gy <= h - 2;
             const unsigned in = rowin ? (inb >> (4 * q)) & 15u : 0u;
             auto res = [&](float pc_, float pw, float pe, float ps, float pn, float f, int j) {
@@ -806,6 +828,181 @@ __global__ void __launch_bounds__(RUN_NT, 2) k_mg_run(TileArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------
+// k_mg_tail -- the bottom of the V-cycle in ONE launch.  Below ~128^2 cells a level
+// is a single window and every PRE / POST launch costs its ~12 us latency chain
+// (staging, 6 barriers-separated half-sweeps, write-back) whatever the size: at
+// 8192^2 levels 6-10 take 117 us of a 1.66 ms V-cycle, on the 1090x436 game level
+// a third of the step.  Here one CTA keeps levels t..L (L = levels-2, the coarsest
+// one solveLevel uses) entirely in shared memory -- p, the rhs and the stencil mask
+// of each level, 9 B/cell -- and runs solveLevel(t) (pressure_solver.cpp:201-248)
+// from the zero initial guess: 3 sweeps, residual + full weighting (residuals are
+// evaluated inside the restriction stencil, never stored), recursion, prolongation
+// + correction, 3 sweeps; 5 sweeps on level L.  The only HBM traffic is the rhs of
+// level t in, its solution out.  Per-cell arithmetic is the tile kernels' (solid
+// cells stored as 0, table weights, same order of additions): bit-identical.
+// ---------------------------------------------------------------------------
+constexpr int TAIL_MAXLV = 8, TAIL_NT = 1024;
+struct TailArgs {
+  int n;                       // levels t .. t+n-1
+  int w[TAIL_MAXLV], h[TAIL_MAXLV], gp[TAIL_MAXLV]; // size and GLOBAL pitch of each level
+  int sp[TAIL_MAXLV];          // shared-memory row pitch: w rounded up to 4 cells
+  int off[TAIL_MAXLV];         // first cell of the level in the shared arrays
+  int cells;                   // total (padded) cells of all tail levels
+  float hh[TAIL_MAXLV];
+  const uint8_t *mask[TAIL_MAXLV];
+  const float *rhs;            // rc of level t
+  float *out;                  // ec of level t
+};
+
+__global__ void __launch_bounds__(TAIL_NT, 1) k_mg_tail(TailArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float *sPa = reinterpret_cast<float *>(smem_raw);
+  float *sFa = sPa + a.cells;
+  uint8_t *sMa = reinterpret_cast<uint8_t *>(sFa + a.cells);
+  __shared__ float rcpt[8], prt[8];
+  const int tid = threadIdx.x;
+  constexpr int NT = TAIL_NT, UB = 4; // staging keeps UB rows per warp in flight
+  if (tid < 8) {
+    rcpt[tid] = rcp_count(tid);
+    prt[tid] = prolong_rcp(tid);
+  }
+  // ---- stage: masks of every level, rhs of level t, p = 0 everywhere; 4 cells per access
+  // (shared rows are padded to a multiple of 4 cells, global rows to 32) ----
+  const int lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = NT / 32;
+  for (int l = 0; l < a.n; l++) {
+    const int sp = a.sp[l], wq = sp >> 2, h = a.h[l];
+    for (int y0 = warp; y0 < h; y0 += UB * NW)
+      for (int xq = lane; xq < wq; xq += 32) {
+        unsigned m[UB];
+        float4 f[UB];
+#pragma unroll
+        for (int k = 0; k < UB; k++) {
+          const int y = y0 + k * NW;
+          m[k] = 0u;
+          f[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (y < h) {
+            m[k] = __ldg(reinterpret_cast<const unsigned *>(a.mask[l] + (size_t)y * a.gp[l] + 4 * xq));
+            if (l == 0) f[k] = __ldg(reinterpret_cast<const float4 *>(a.rhs + (size_t)y * a.gp[0] + 4 * xq));
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < UB; k++) {
+          const int y = y0 + k * NW;
+          if (y < h) {
+            const int i = a.off[l] + y * sp + 4 * xq;
+            *reinterpret_cast<unsigned *>(sMa + i) = m[k];
+            *reinterpret_cast<float4 *>(sFa + i) = f[k];
+            *reinterpret_cast<float4 *>(sPa + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+      }
+  }
+  __syncthreads();
+
+  // `count` red-black sweeps of level l: a warp per row, lanes over the row's cells of one colour
+  auto sweeps = [&](int l, int count) {
+    const int w = a.w[l], h = a.h[l], sp = a.sp[l];
+    float *P = sPa + a.off[l];
+    const float *F = sFa + a.off[l];
+    const uint8_t *M = sMa + a.off[l];
+    const float hh = a.hh[l];
+    for (int s = 0; s < 2 * count; s++) {
+      const int cpar = (s & 1) ^ 1; // red (x+y odd) first, pressure_solver.cpp:35-47
+      for (int y = 1 + warp; y < h - 1; y += NW)
+        for (int x = 1 + ((y + cpar + 1) & 1) + 2 * lane; x < w - 1; x += 64) {
+          const int i = y * sp + x;
+          float v = __fadd_rn(__fadd_rn(__fadd_rn(P[i - 1], P[i + 1]), P[i - sp]), P[i + sp]);
+          v = __fadd_rn(v, fh2_of(F[i], hh));
+          P[i] = __fmul_rn(v, rcpt[(M[i] >> 2) & 7u]);
+        }
+      __syncthreads();
+    }
+  };
+  // residual_cell with binary flags (see k_mg_tile); 0 outside the interior
+  auto residual = [&](const float *P, const float *F, const uint8_t *M, int w, int h, int sp, int x,
+                      int y, float ihsq) {
+    if (x < 1 || y < 1 || x > w - 2 || y > h - 2) return 0.0f;
+    const int i = y * sp + x;
+    const unsigned m = M[i];
+    const float pc = P[i];
+    float val = (m & MB_W) ? P[i - 1] : pc;
+    val = __fadd_rn(val, (m & MB_E) ? P[i + 1] : pc);
+    val = __fadd_rn(val, (m & MB_S) ? P[i - sp] : pc);
+    val = __fadd_rn(val, (m & MB_N) ? P[i + sp] : pc);
+    val = __fmaf_rn(-4.0f, pc, val);
+    val = __fmul_rn(val, ihsq);
+    val = __fadd_rn(F[i], val);
+    return (m & MB_C) ? val : 0.0f;
+  };
+
+  // ---- down ----
+  for (int l = 0; l + 1 < a.n; l++) {
+    sweeps(l, 3);
+    const int w = a.w[l], h = a.h[l], sp = a.sp[l], wc = a.w[l + 1], hc = a.h[l + 1], spc = a.sp[l + 1];
+    const float *P = sPa + a.off[l], *F = sFa + a.off[l];
+    const uint8_t *M = sMa + a.off[l];
+    float *Fc = sFa + a.off[l + 1];
+    const float ihsq = 1.0f / a.hh[l] / a.hh[l];
+    for (int yc = 1 + warp; yc < hc - 1; yc += NW)
+      for (int xc = 1 + lane; xc < wc - 1; xc += 32) {
+        const int x = 2 * xc, y = 2 * yc;
+        auto r = [&](int dx, int dy) { return residual(P, F, M, w, h, sp, x + dx, y + dy, ihsq); };
+        Fc[yc * spc + xc] = fw9(r(-1, -1), r(0, -1), r(1, -1), r(-1, 0), r(0, 0), r(1, 0), r(-1, 1), r(0, 1), r(1, 1));
+      }
+    __syncthreads();
+  }
+  sweeps(a.n - 1, 5); // level L: 5 sweeps, pressure_solver.cpp:203-206
+  // ---- up ----
+  for (int l = a.n - 2; l >= 0; l--) {
+    const int w = a.w[l], h = a.h[l], sp = a.sp[l], wc = a.w[l + 1], hc = a.h[l + 1], spc = a.sp[l + 1];
+    float *P = sPa + a.off[l];
+    const uint8_t *M = sMa + a.off[l];
+    const float *E = sPa + a.off[l + 1];
+    const uint8_t *Mc = sMa + a.off[l + 1];
+    // prolongate + correct, one thread per coarse cell (as in k_mg_tile)
+    for (int yc = warp; yc < hc; yc += NW)
+    for (int xc = lane; xc < wc; xc += 32) {
+      const int x = 2 * xc, y = 2 * yc;
+      const bool y_e = y >= 2 && y <= h - 2, y_o = y + 1 <= h - 3 && yc + 1 < hc;
+      const bool x_e = x >= 2 && x <= w - 2, x_o = x + 1 <= w - 3;
+      const int ic = yc * spc + xc;
+      const float e00 = E[ic];
+      const float e10 = x_o ? E[ic + 1] : 0.0f;
+      const float e01 = y_o ? E[ic + spc] : 0.0f;
+      const float e11 = (x_o && y_o) ? E[ic + spc + 1] : 0.0f;
+      const unsigned mc = Mc[ic];
+      const unsigned mn = y_o ? Mc[ic + spc] : 0u;
+      const int fC = mc & 1, fE = (mc >> 5) & 1, fN = (mc >> 7) & 1, fNE = (mn >> 5) & 1;
+      const int i = y * sp + x;
+      if (y_e) {
+        if (x_e) P[i] = __fadd_rn(P[i], sel0(M[i], MB_C, e00));
+        if (x_o)
+          P[i + 1] = __fadd_rn(P[i + 1], __fmul_rn(sel0(M[i + 1], MB_C, __fadd_rn(e00, e10)), prt[fC + fE]));
+      }
+      if (y_o) {
+        if (x_e)
+          P[i + sp] = __fadd_rn(P[i + sp], __fmul_rn(sel0(M[i + sp], MB_C, __fadd_rn(e00, e01)), prt[fC + fN]));
+        if (x_o) {
+          const float es = __fadd_rn(__fadd_rn(__fadd_rn(e00, e11), e10), e01);
+          P[i + sp + 1] = __fadd_rn(P[i + sp + 1], __fmul_rn(sel0(M[i + sp + 1], MB_C, es), prt[fC + fNE + fE + fN]));
+        }
+      }
+    }
+    __syncthreads();
+    sweeps(l, 3);
+  }
+  // ---- solution of level t (whole padded rows: the pad columns hold 0) ----
+  {
+    const int sp = a.sp[0], wq = sp >> 2, h = a.h[0];
+    for (int y = warp; y < h; y += NW)
+      for (int xq = lane; xq < wq; xq += 32)
+        *reinterpret_cast<float4 *>(a.out + (size_t)y * a.gp[0] + 4 * xq) =
+            *reinterpret_cast<const float4 *>(sPa + y * sp + 4 * xq);
+  }
+}
+
 // Stencil mask of a flag grid (layout: enum MB_* above; neighbours outside the
 // grid count as solid).  *nonbinary is raised if any flag is neither 0.0 nor 1.0
 // (then the bit form is not equivalent and the plain path is used).
@@ -862,6 +1059,16 @@ static int env_tile_variant() {
   return (e && e[0] == '1') ? 1 : 2;
 }
 static int g_tile_variant = env_tile_variant();
+static int env_prefetch_dist() {
+  const char *e = getenv("UBGL_MG_PREFETCH"); // CTAs ahead; default one generation of 148 SMs x 2
+  return e ? atoi(e) : 296;
+}
+static int g_prefetch_dist = env_prefetch_dist();
+static size_t env_tail_cells() {
+  const char *e = getenv("UBGL_MG_TAIL_CELLS");
+  return e ? (size_t)atoll(e) : 8192;
+}
+static size_t g_tail_max_cells = env_tail_cells();
 void set_tile_variant(int v) { g_tile_variant = (v == 1) ? 1 : 2; }
 int tile_variant() { return g_tile_variant; }
 
@@ -875,7 +1082,9 @@ static void launch_run(const TileArgs &a, cudaStream_t stream, LaunchCounter *lc
     attr_set = true;
   }
   dim3 grid(ceil_div(a.w, G::TX), ceil_div(a.own_hi - a.own_lo, G::TY));
-  UBGL_LAUNCH(lc, kind, level, stream, k_mg_run<MODE><<<grid, RUN_NT, G::smem, stream>>>(a));
+  TileArgs b = a;
+  b.pf_dist = g_prefetch_dist;
+  UBGL_LAUNCH(lc, kind, level, stream, k_mg_run<MODE><<<grid, RUN_NT, G::smem, stream>>>(b));
 }
 
 static void set_rows(TileArgs &a, const Rows *rows) {
@@ -929,6 +1138,47 @@ void launch_mg_smooth5(float *p_out, const Grid &f, const uint8_t *mask, float h
   a.hh = hh; a.ihsq = 1.0f / hh / hh; a.zgbc = 0;
   set_rows(a, nullptr);
   launch_tile<5, MODE_SMOOTH, LH_MAIN, NT_MAIN>(a, stream, lc, K_MG_COARSE, level);
+}
+
+// First level t >= max(1, t_min) from which levels t..L fit one CTA's shared memory (0: none).
+constexpr size_t TAIL_SMEM_MAX = 220 * 1024;
+int mg_tail_first_level(const std::vector<TailLevel> &lv, int t_min) {
+  const int L = (int)lv.size() - 2;
+  if (g_tile_variant != 2 || L < 1) return 0;
+  for (int t = t_min > 1 ? t_min : 1; t <= L; t++) {
+    size_t cells = 0;
+    for (int l = t; l <= L; l++) cells += (size_t)round_up(lv[l].w, 4) * lv[l].h;
+    // one SM runs the tail: above ~8K cells on its first level the multi-CTA passes are faster
+    if (L - t + 1 <= TAIL_MAXLV && cells * 9 + 16 <= TAIL_SMEM_MAX && (size_t)lv[t].w * lv[t].h <= g_tail_max_cells)
+      return t;
+  }
+  return 0;
+}
+
+// solveLevel(t) from the zero guess: rhs = rc of level t, solution -> ec of level t
+void launch_mg_tail(const std::vector<TailLevel> &lv, int t, const float *hh, const float *rhs,
+                    float *out, cudaStream_t stream, LaunchCounter *lc) {
+  const int L = (int)lv.size() - 2;
+  TailArgs a{};
+  a.n = L - t + 1;
+  int cells = 0;
+  for (int i = 0; i < a.n; i++) {
+    const TailLevel &V = lv[t + i];
+    a.w[i] = V.w; a.h[i] = V.h; a.gp[i] = V.pitch; a.sp[i] = round_up(V.w, 4); a.off[i] = cells;
+    a.hh[i] = hh[t + i];
+    a.mask[i] = V.mask;
+    cells += a.sp[i] * V.h;
+  }
+  a.cells = cells;
+  a.rhs = rhs;
+  a.out = out;
+  const size_t smem = (size_t)cells * 9 + 16;
+  static bool attr_set = false;
+  if (!attr_set) {
+    UBGL_CUDA(cudaFuncSetAttribute(k_mg_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TAIL_SMEM_MAX));
+    attr_set = true;
+  }
+  UBGL_LAUNCH(lc, K_MG_COARSE, t, stream, k_mg_tail<<<1, TAIL_NT, smem, stream>>>(a));
 }
 
 void launch_make_mask(const Grid &flag, uint8_t *mask, int *d_nonbinary, cudaStream_t stream,

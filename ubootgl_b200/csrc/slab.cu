@@ -497,7 +497,13 @@ void SlabSim::mg_solve() {
   hh[0] = h;
   for (int l = 0; l < L; l++) // :229
     hh[l + 1] = hh[l] * ((float)lv[l].w - 1.0f) / ((float)lv[l + 1].w - 1.0f);
-  for (int l = 0; l < L; l++) {
+  // replicated levels t..L that fit one CTA's shared memory run in one launch (k_mg_tail),
+  // identically on every rank
+  std::vector<TailLevel> tv;
+  for (auto &V : lv) tv.push_back(TailLevel{V.w, V.h, V.pitch, V.mask});
+  const int t = mg_tail_first_level(tv, nd > 1 ? nd : 1);
+  const int Ld = t ? t : L;
+  for (int l = 0; l < Ld; l++) {
     const Grid &fl = (l == 0) ? f : lv[l].rc;
     const Grid &pout = (l == 0) ? scratch0 : lv[l].eb;
     const Rows *rows = lv[l].dist ? &lv[l].rows : nullptr;
@@ -512,8 +518,11 @@ void SlabSim::mg_solve() {
       }
     }
   }
-  launch_mg_smooth5(lv[L].ec.d, lv[L].rc, lv[L].mask, hh[L], stream, &lc, L);
-  for (int l = L - 1; l >= 0; l--) {
+  if (t)
+    launch_mg_tail(tv, t, hh.data(), lv[t].rc.d, lv[t].ec.d, stream, &lc);
+  else
+    launch_mg_smooth5(lv[L].ec.d, lv[L].rc, lv[L].mask, hh[L], stream, &lc, L);
+  for (int l = Ld - 1; l >= 0; l--) {
     const Grid &fl = (l == 0) ? f : lv[l].rc;
     const Grid &pin = (l == 0) ? scratch0 : lv[l].eb;
     const Grid &pout = (l == 0) ? p : lv[l].ec;
