@@ -457,7 +457,7 @@ template <int MODE> struct RunGeom {
   static constexpr int TY = RUN_LH - 2 * HY;
   static constexpr size_t p_floats = 2 * (RUN_LH + 2) * RS; // one pad row above and below
   static constexpr size_t r_floats = (MODE == MODE_PRE) ? 2 * RUN_LH * RS : 0;
-  static constexpr size_t smem = sizeof(float) * (p_floats + r_floats + 8) + 2 * RUN_LH * RS;
+  static constexpr size_t smem = sizeof(float) * (p_floats + r_floats + 16) + 2 * RUN_LH * RS;
 };
 
 __device__ __forceinline__ float4 lds4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
@@ -473,7 +473,8 @@ __global__ void __launch_bounds__(RUN_NT, 2) k_mg_run(TileArgs a) {
   float *sP = reinterpret_cast<float *>(smem_raw);
   float *sR = sP + G::p_floats;
   float *rcpt = sR + G::r_floats;
-  uint8_t *sM = reinterpret_cast<uint8_t *>(rcpt + 8);
+  float *prt = rcpt + 8;
+  uint8_t *sM = reinterpret_cast<uint8_t *>(rcpt + 16);
   auto P = [&](int pl, int r) -> float * { return sP + (pl * (LH + 2) + r + 1) * RS; };
   auto Rr = [&](int pl, int r) -> float * { return sR + (pl * LH + r) * RS; };
   auto M = [&](int pl, int r) -> uint8_t * { return sM + (pl * LH + r) * RS; };
@@ -487,7 +488,35 @@ __global__ void __launch_bounds__(RUN_NT, 2) k_mg_run(TileArgs a) {
   const int w = a.w, h = a.h;
   const int gx8 = X0 + 8 * tg;
 
-  if (threadIdx.x < 8) rcpt[threadIdx.x] = rcp_count(threadIdx.x);
+  if (threadIdx.x < 8) {
+    rcpt[threadIdx.x] = rcp_count(threadIdx.x);
+    prt[threadIdx.x] = prolong_rcp(threadIdx.x);
+  }
+
+  // MODE_POST: the coarse error and coarse stencil mask under this thread's cells -- coarse
+  // rows ycb .. ycb+2, columns xcb .. xcb+4 -- for prolongation + correction
+  // (pressure_solver.cpp:134-181), applied to p in registers on its way into shared memory
+  float ecr[3][5];
+  unsigned mcr[3];
+  const int ycb = (Y0 + r0) >> 1;
+  if (MODE == MODE_POST) {
+    const int xcb = gx8 >> 1;
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      const int yc = ycb + j;
+#pragma unroll
+      for (int k = 0; k < 5; k++) ecr[j][k] = 0.0f;
+      mcr[j] = 0u;
+      if (yc >= a.c_lo && yc < a.c_hi && gx8 >= 0 && xcb < a.pc) {
+        const size_t oc = (size_t)yc * a.pc + xcb;
+        const float4 t = __ldg(reinterpret_cast<const float4 *>(a.ec + oc));
+        ecr[j][0] = t.x; ecr[j][1] = t.y; ecr[j][2] = t.z; ecr[j][3] = t.w;
+        if (xcb + 4 < a.pc) ecr[j][4] = __ldg(a.ec + oc + 4);
+        mcr[j] = __ldg(reinterpret_cast<const unsigned *>(a.maskc + oc));
+      }
+    }
+    __syncthreads(); // prt[] is read while staging
+  }
 
   // ---- stage: p and the mask go to shared memory (colour planes), f*h*h stays in
   // registers; slot E = the thread's cells 0,2,4,6, slot O = cells 1,3,5,7 ----
@@ -511,10 +540,41 @@ __global__ void __launch_bounds__(RUN_NT, 2) k_mg_run(TileArgs a) {
       }
       ME[i] = __byte_perm(mv.x, mv.y, 0x6420);
       MO[i] = __byte_perm(mv.x, mv.y, 0x7531);
-      const float4 pe = make_float4(sel0(ME[i], MB_C, p0.x), sel0(ME[i] >> 8, MB_C, p0.z),
-                                    sel0(ME[i] >> 16, MB_C, p1.x), sel0(ME[i] >> 24, MB_C, p1.z));
-      const float4 po = make_float4(sel0(MO[i], MB_C, p0.y), sel0(MO[i] >> 8, MB_C, p0.w),
-                                    sel0(MO[i] >> 16, MB_C, p1.y), sel0(MO[i] >> 24, MB_C, p1.w));
+      float4 pe = make_float4(sel0(ME[i], MB_C, p0.x), sel0(ME[i] >> 8, MB_C, p0.z),
+                              sel0(ME[i] >> 16, MB_C, p1.x), sel0(ME[i] >> 24, MB_C, p1.z));
+      float4 po = make_float4(sel0(MO[i], MB_C, p0.y), sel0(MO[i] >> 8, MB_C, p0.w),
+                              sel0(MO[i] >> 16, MB_C, p1.y), sel0(MO[i] >> 24, MB_C, p1.w));
+      if (MODE == MODE_POST) {
+        // same per-cell rounding sequence as prolong_cell (stencils.cuh) + correct; the coarse
+        // flag sums come from the coarse mask (C, E, N bits of (xc,yc), E bit of (xc,yc+1))
+        const int j = i >> 1, yc = ycb + j, y = 2 * yc;
+        const bool row_ok = yc >= a.c_lo && yc < a.c_hi;
+        const bool y_o = y + 1 <= h - 3 && yc + 1 < a.c_hi;
+        const bool act = row_ok && ((i & 1) ? y_o : (y >= 2 && y <= h - 2));
+        float pev[4] = {pe.x, pe.y, pe.z, pe.w}, pov[4] = {po.x, po.y, po.z, po.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const int x = gx8 + 2 * k;
+          const bool x_e = x >= 2 && x <= w - 2, x_o = x + 1 <= w - 3 && gx8 >= 0;
+          const unsigned mc = mcr[j] >> (8 * k), mn = mcr[j + 1] >> (8 * k);
+          const int fC = mc & 1, fE = (mc >> 5) & 1, fN = (mc >> 7) & 1, fNE = (mn >> 5) & 1;
+          const float e00 = ecr[j][k], e10 = ecr[j][k + 1], e01 = ecr[j + 1][k], e11 = ecr[j + 1][k + 1];
+          if ((i & 1) == 0) {
+            if (act && x_e) pev[k] = __fadd_rn(pev[k], sel0(ME[i] >> (8 * k), MB_C, e00));
+            if (act && x_o)
+              pov[k] = __fadd_rn(pov[k], __fmul_rn(sel0(MO[i] >> (8 * k), MB_C, __fadd_rn(e00, e10)), prt[fC + fE]));
+          } else {
+            if (act && x_e)
+              pev[k] = __fadd_rn(pev[k], __fmul_rn(sel0(ME[i] >> (8 * k), MB_C, __fadd_rn(e00, e01)), prt[fC + fN]));
+            if (act && x_o) {
+              const float es = __fadd_rn(__fadd_rn(__fadd_rn(e00, e11), e10), e01);
+              pov[k] = __fadd_rn(pov[k], __fmul_rn(sel0(MO[i] >> (8 * k), MB_C, es), prt[fC + fNE + fE + fN]));
+            }
+          }
+        }
+        pe = make_float4(pev[0], pev[1], pev[2], pev[3]);
+        po = make_float4(pov[0], pov[1], pov[2], pov[3]);
+      }
       // cell j of row r has colour (j + r) & 1 = (j + i) & 1
       *reinterpret_cast<float4 *>(P(i & 1, r) + ci) = pe;
       *reinterpret_cast<float4 *>(P((i & 1) ^ 1, r) + ci) = po;
@@ -656,59 +716,9 @@ __global__ void __launch_bounds__(RUN_NT, 2) k_mg_run(TileArgs a) {
         cell(gx, h - 1) = sel0(mbyte(gx, h - 1), MB_C, cell(gx, h - 2));
   };
 
-  if (MODE == MODE_POST) {
-    // prolongate + correct (pressure_solver.cpp:134-181), one thread per COARSE cell,
-    // exactly as in k_mg_tile
-    const int xcb = X0 >> 1, ycb = Y0 >> 1;
-    for (int j = warp; j < LH / 2; j += NW) {
-      const int yc = ycb + j, y = 2 * yc;
-      if (yc < a.c_lo || yc >= a.c_hi) continue;
-      const bool y_e = y >= 2 && y <= h - 2;
-      const bool y_o = y + 1 <= h - 3 && yc + 1 < a.c_hi;
-      const float *ecr = a.ec + (size_t)yc * a.pc;
-      const uint8_t *mcr = a.maskc + (size_t)yc * a.pc;
-      float *P0e = P(0, 2 * j), *P1e = P(1, 2 * j), *P0o = P(0, 2 * j + 1), *P1o = P(1, 2 * j + 1);
-      const uint8_t *M0e = M(0, 2 * j), *M1e = M(1, 2 * j), *M0o = M(0, 2 * j + 1), *M1o = M(1, 2 * j + 1);
-      for (int k = lane; k < HW; k += 32) {
-        const int xc = xcb + k, x = 2 * xc;
-        if (xc < 0 || xc >= a.wc) continue;
-        const bool x_e = x >= 2 && x <= w - 2, x_o = x + 1 <= w - 3;
-        const float e00 = __ldg(ecr + xc);
-        const float e10 = x_o ? __ldg(ecr + xc + 1) : 0.0f;
-        const float e01 = y_o ? __ldg(ecr + a.pc + xc) : 0.0f;
-        const float e11 = (x_o && y_o) ? __ldg(ecr + a.pc + xc + 1) : 0.0f;
-        const unsigned mc = __ldg(mcr + xc);
-        const unsigned mn = y_o ? __ldg(mcr + a.pc + xc) : 0u;
-        const int fC = mc & 1, fE = (mc >> 5) & 1, fN = (mc >> 7) & 1, fNE = (mn >> 5) & 1;
-        const int c = XO + k;
-        if (y_e) {
-          if (x_e) {
-            const float e = sel0(M0e[c], MB_C, e00);
-            P0e[c] = __fadd_rn(P0e[c], e);
-          }
-          if (x_o) {
-            const float e = __fmul_rn(sel0(M1e[c], MB_C, __fadd_rn(e00, e10)), prolong_rcp(fC + fE));
-            P1e[c] = __fadd_rn(P1e[c], e);
-          }
-        }
-        if (y_o) {
-          if (x_e) {
-            const float e = __fmul_rn(sel0(M1o[c], MB_C, __fadd_rn(e00, e01)), prolong_rcp(fC + fN));
-            P1o[c] = __fadd_rn(P1o[c], e);
-          }
-          if (x_o) {
-            const float es = __fadd_rn(__fadd_rn(__fadd_rn(e00, e11), e10), e01);
-            const float e = __fmul_rn(sel0(M0o[c], MB_C, es), prolong_rcp(fC + fNE + fE + fN));
-            P0o[c] = __fadd_rn(P0o[c], e);
-          }
-        }
-      }
-    }
+  if (MODE == MODE_POST && a.zgbc) { // setZeroGradientBC after correct (pressure_solver.cpp:236-239)
+    zero_gradient(0);
     __syncthreads();
-    if (a.zgbc) {
-      zero_gradient(0);
-      __syncthreads();
-    }
   }
 
 #pragma unroll 1
