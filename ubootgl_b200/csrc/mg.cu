@@ -285,16 +285,22 @@ void DeviceMG::update_fields(const Grid &flag0) {
 // (Re)build the level-0 stencil mask from the flag grid the caller solves with.
 // Synchronises the stream (reads back the "non-binary flag seen" bit), so the
 // owners call it when the flag changes, not inside the step.
-void DeviceMG::prepare_mask0(const Grid &flag) {
+void DeviceMG::prepare_mask0(const Grid &flag, bool known_binary) {
   if (mask0_src == flag.d) return;
   UBGL_REQUIRE(flag.w == lv[0].w && flag.h == lv[0].h && flag.pitch == lv[0].pitch,
                "flag grid does not match the MG level-0 layout");
   UBGL_CUDA(cudaMemsetAsync(d_nonbinary, 0, sizeof(int), stream));
   launch_make_mask(flag, mask0, d_nonbinary, stream, lc, 0);
-  int nb = 0;
-  UBGL_CUDA(cudaMemcpyAsync(&nb, d_nonbinary, sizeof(int), cudaMemcpyDeviceToHost, stream));
-  UBGL_CUDA(cudaStreamSynchronize(stream));
-  mask0_binary = (nb == 0);
+  if (known_binary) {
+    // device-side edit that only writes 0.0 / 1.0 into a field that was binary: no need to
+    // read the verdict back (a host sync per terrain edit would serialise the frame loop)
+    mask0_binary = true;
+  } else {
+    int nb = 0;
+    UBGL_CUDA(cudaMemcpyAsync(&nb, d_nonbinary, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    UBGL_CUDA(cudaStreamSynchronize(stream));
+    mask0_binary = (nb == 0);
+  }
   mask0_src = flag.d;
 }
 

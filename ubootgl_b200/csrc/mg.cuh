@@ -46,7 +46,7 @@ public:
   // The fused path needs binary flags; level 0 uses the caller's flag grid
   // (pressure_solver.hpp:59-62), whose mask is rebuilt when it changes.
   void invalidate_mask0() { mask0_src = nullptr; }
-  void prepare_mask0(const Grid &flag);
+  void prepare_mask0(const Grid &flag, bool known_binary = false);
   const uint8_t *mask0_ptr() const { return mask0; }
   bool mask0_is_binary() const { return mask0_src != nullptr && mask0_binary; }
 

@@ -697,7 +697,7 @@ int ubgl_sim_draw_circles(ubgl_sim_t *sim, const float *xyd, int n, float val) {
   S.stage_done();
   UBGL_LAUNCH(&S.lc, K_TERRAIN, 0, S.stream, k_draw_circles<<<n, 256, 0, S.stream>>>(S.field(F_FLAG), d_xyd, n, val));
   UBGL_CUDA(cudaFreeAsync(d_xyd, S.stream));
-  S.flag_changed(true); // MG::updateFields + stencil masks (ubootgl_app.cpp:111-112)
+  S.flag_changed(true, true); // MG::updateFields + stencil masks (ubootgl_app.cpp:111-112); cells get 0.0 / 1.0
   UBGL_CATCH
 }
 

@@ -408,10 +408,11 @@ void DeviceSim::upload(int id, const float *host) {
 // The level-0 flag changed: refresh what is derived from it.  `pyramid` also
 // rebuilds the coarse flags (MG::updateFields); a bare write to sim.flag does
 // not, exactly as in the reference (simulation.hpp:85 vs ubootgl_app.cpp:111-112).
-void DeviceSim::flag_changed(bool pyramid) {
+void DeviceSim::flag_changed(bool pyramid, bool binary_edit) {
   if (pyramid) mg->update_fields(flag);
+  const bool keep = binary_edit && mg->mask0_is_binary(); // the edit wrote only 0.0 / 1.0
   mg->invalidate_mask0();
-  mg->prepare_mask0(flag);
+  mg->prepare_mask0(flag, keep);
 }
 
 void DeviceSim::download(int id, float *host) {

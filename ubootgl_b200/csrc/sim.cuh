@@ -82,7 +82,7 @@ public:
   void upload(int id, const float *host);
   void download(int id, float *host);
   void update_flag(const float *host_flag);
-  void flag_changed(bool pyramid);
+  void flag_changed(bool pyramid, bool binary_edit = false);
 
   void stage(int st, float dt);
   void step(float dt);
