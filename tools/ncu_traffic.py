@@ -33,8 +33,8 @@ for r in rows[2:]:
             acc["_cycle_done"] = True  # first V-cycle only
     else:
         for pat, kind in kinds:
-            if pat in name:
-                key = f"{kind}:0"
+            if pat in name and not (kind == "mg_coarse_fused" and acc.get("_cycle_done")):
+                key = f"{kind}:{n_pre if kind == 'mg_coarse_fused' else 0}"
     if key:
         acc.setdefault(key, []).append(b)
 out = {"workload": workload, "source": f"{src} (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)",

@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "_lib", "libubgl.so")
+LIB_PATH = os.environ.get("UBGL_LIB_PATH") or os.path.join(HERE, "_lib", "libubgl.so")  # override: A/B builds only
 
 FLAG, VX, VY, VXB, VYB, P, F, VX_ACCUM, VY_ACCUM, R, VX_CURRENT, VY_CURRENT = range(12)
 ST_ACCUM, ST_DIFFUSE, ST_ADVECT, ST_SETVBCS, ST_PROJECT, ST_SAVE = range(6)

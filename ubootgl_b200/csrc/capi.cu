@@ -285,12 +285,18 @@ int ubgl_sim_step_host(ubgl_sim_t *sim, float dt, const ubgl_host_mirrors *m) {
       if (o.dst && o.cur) {
         Grid g = S.field(o.id);
         const size_t row = sizeof(float) * (size_t)g.w;
-        const int nb = (size_t)g.h * row >= (size_t)(16 << 20) ? std::min(32, g.h) : 1;
+        const bool big = (size_t)g.h * row >= (size_t)(16 << 20);
+        const int nb = big ? std::min(32, g.h) : 1;
+        const float *pk = big ? S.packed(g) : nullptr; // unpadded rows: contiguous DMA
         for (int b = 0; b < nb; b++) {
           const int y0 = (int)((long long)g.h * b / nb), y1 = (int)((long long)g.h * (b + 1) / nb);
-          UBGL_CUDA(cudaMemcpy2DAsync(o.dst + (size_t)y0 * g.w, row, g.d + (size_t)y0 * g.pitch,
-                                      sizeof(float) * g.pitch, row, y1 - y0, cudaMemcpyDeviceToHost,
-                                      S.stream));
+          if (pk)
+            UBGL_CUDA(cudaMemcpyAsync(o.dst + (size_t)y0 * g.w, pk + (size_t)y0 * g.w, row * (size_t)(y1 - y0),
+                                      cudaMemcpyDeviceToHost, S.stream));
+          else
+            UBGL_CUDA(cudaMemcpy2DAsync(o.dst + (size_t)y0 * g.w, row, g.d + (size_t)y0 * g.pitch,
+                                        sizeof(float) * g.pitch, row, y1 - y0, cudaMemcpyDeviceToHost,
+                                        S.stream));
           HostBand hb;
           UBGL_CUDA(cudaEventCreateWithFlags(&hb.ready, cudaEventDisableTiming));
           bands.push_back(hb);
@@ -310,7 +316,11 @@ int ubgl_sim_step_host(ubgl_sim_t *sim, float dt, const ubgl_host_mirrors *m) {
     }
     if (m->p) {
       Grid g = S.field(F_P);
-      download_grid(g, m->p, g.w, g.h, S.stream);
+      if (g.bytes() >= (size_t)(16 << 20) && g.w != g.pitch)
+        UBGL_CUDA(cudaMemcpyAsync(m->p, S.packed(g), sizeof(float) * (size_t)g.w * g.h, cudaMemcpyDeviceToHost,
+                                  S.stream));
+      else
+        download_grid(g, m->p, g.w, g.h, S.stream);
     }
     cudaError_t herr = cudaSuccess;
     if (uploaded || !bands.empty())

@@ -445,7 +445,10 @@ __global__ void __launch_bounds__(NT, 2) k_mg_tile(TileArgs a) {
 // k_mg_tile and to the plain path (tests/test_gpu_fused.py).
 // ---------------------------------------------------------------------------
 constexpr int RUN_R = 4;                 // rows per thread
-constexpr int RUN_NCH = 16;              // row chunks per window
+#ifndef UBGL_RUN_NCH
+#define UBGL_RUN_NCH 16
+#endif
+constexpr int RUN_NCH = UBGL_RUN_NCH;    // row chunks per window
 constexpr int RUN_LH = RUN_R * RUN_NCH;  // 64 window rows
 constexpr int RUN_NT = 16 * RUN_NCH;     // 16 column groups x 16 chunks = 256 threads
 constexpr int RUN_HX = 8;                // x halo: whole 8-cell column groups
@@ -463,7 +466,7 @@ template <int MODE> struct RunGeom {
 __device__ __forceinline__ float4 lds4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
 
 template <int MODE>
-__global__ void __launch_bounds__(RUN_NT, 2) k_mg_run(TileArgs a) {
+__global__ void __launch_bounds__(RUN_NT, RUN_NT <= 256 ? 2 : 1) k_mg_run(TileArgs a) {
   using G = RunGeom<MODE>;
   constexpr int S = G::S, R = RUN_R, LH = RUN_LH, NT = RUN_NT, HX = RUN_HX, HY = G::HY;
   constexpr int TX = G::TX, TY = G::TY, NW = NT / 32;
@@ -653,15 +656,21 @@ __global__ void __launch_bounds__(RUN_NT, 2) k_mg_run(TileArgs a) {
     if (r0 + R <= r_lo || r0 >= r_hi) return;
     const float *po = P(CPAR ^ 1, r0 - 1) + ci;
     float *pd = P(CPAR, r0) + ci;
-    float4 Sv = lds4(po), A = lds4(po + RS);
+    // all R+2 rows of the other colour and the R lane-edge values first (independent loads
+    // and shuffles in flight together), then the arithmetic
+    float4 O[R + 2];
+#pragma unroll
+    for (int j = 0; j < R + 2; j++) O[j] = lds4(po + j * RS);
+    float ed[R];
+#pragma unroll
+    for (int i = 0; i < R; i++) ed[i] = edge(O[i + 1], (CPAR + i) & 1);
 #pragma unroll
     for (int i = 0; i < R; i++) {
-      const float4 Nv = lds4(po + (i + 2) * RS);
       const int q = (CPAR + i) & 1;
-      const float ed = edge(A, q);
+      const float4 Sv = O[i], A = O[i + 1], Nv = O[i + 2];
       if (r0 + i >= r_lo && r0 + i < r_hi) {
-        const float4 Wv = q == 0 ? make_float4(ed, A.x, A.y, A.z) : A;
-        const float4 Ev = q == 0 ? A : make_float4(A.y, A.z, A.w, ed);
+        const float4 Wv = q == 0 ? make_float4(ed[i], A.x, A.y, A.z) : A;
+        const float4 Ev = q == 0 ? A : make_float4(A.y, A.z, A.w, ed[i]);
         const float4 Fv = q == 0 ? FE[i] : FO[i];
         const float4 Wt = q == 0 ? WE[i] : WO[i];
         auto upd = [&](float pw, float pe, float ps, float pn, float f, float wt) {
@@ -684,8 +693,6 @@ __global__ void __launch_bounds__(RUN_NT, 2) k_mg_run(TileArgs a) {
           if (!(z & 8)) d[3] = v.w;
         }
       }
-      Sv = A;
-      A = Nv;
     }
   };
 
@@ -741,12 +748,17 @@ __global__ void __launch_bounds__(RUN_NT, 2) k_mg_run(TileArgs a) {
 #pragma unroll
       for (int cpar = 0; cpar < 2; cpar++) {
         const float *po = P(cpar ^ 1, r0 - 1) + ci;
-        float4 Sv = lds4(po), A = lds4(po + RS);
+        float4 O[R + 2];
+#pragma unroll
+        for (int j = 0; j < R + 2; j++) O[j] = lds4(po + j * RS);
+        float edv[R];
+#pragma unroll
+        for (int i = 0; i < R; i++) edv[i] = edge(O[i + 1], (cpar + i) & 1);
 #pragma unroll
         for (int i = 0; i < R; i++) {
-          const float4 Nv = lds4(po + (i + 2) * RS);
+          const float4 Sv = O[i], A = O[i + 1], Nv = O[i + 2];
           const int q = (cpar + i) & 1;
-          const float ed = edge(A, q);
+          const float ed = edv[i];
           const int r = r0 + i, gy = Y0 + r;
           if (r >= rr_lo && r < rr_hi) {
             const float4 Wv = q == 0 ? make_float4(ed, A.x, A.y, A.z) : A;
@@ -774,8 +786,6 @@ __global__ void __launch_bounds__(RUN_NT, 2) k_mg_run(TileArgs a) {
             v.w = res(Cv.w, Wv.w, Ev.w, Sv.w, Nv.w, Fv.w, 3);
             *reinterpret_cast<float4 *>(Rr(cpar, r) + ci) = v;
           }
-          Sv = A;
-          A = Nv;
         }
       }
     }

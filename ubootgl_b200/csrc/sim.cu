@@ -363,6 +363,7 @@ DeviceSim::~DeviceSim() {
   if (d_sinks) cudaFree(d_sinks);
   if (d_fnorm) cudaFree(d_fnorm);
   if (h_stage) cudaFreeHost(h_stage);
+  if (d_pack) cudaFree(d_pack);
   if (ev_stage) cudaEventDestroy(ev_stage);
   if (d_vxy) cudaFree(d_vxy);
   if (d_mag) cudaFree(d_mag);
@@ -563,6 +564,25 @@ float *DeviceSim::stage_host(size_t nfloats) {
   return h_stage;
 }
 void DeviceSim::stage_done() { UBGL_CUDA(cudaEventRecord(ev_stage, stream)); }
+
+__global__ void k_pack_rows(const float *__restrict__ src, int pitch, int w, float *__restrict__ dst) {
+  const size_t y = blockIdx.y;
+  for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < w; x += gridDim.x * blockDim.x)
+    dst[y * w + x] = src[y * pitch + x];
+}
+float *DeviceSim::packed(const Grid &g) {
+  const size_t n = (size_t)g.w * g.h;
+  if (n > cap_pack) {
+    if (d_pack) UBGL_CUDA(cudaFree(d_pack)); // synchronises: no copy out of the old buffer is left
+    d_pack = nullptr;
+    cap_pack = 0;
+    UBGL_CUDA(cudaMalloc(&d_pack, sizeof(float) * (size_t)W * H));
+    cap_pack = (size_t)W * H;
+  }
+  dim3 grid(std::min(ceil_div(g.w, 256), 8), g.h);
+  UBGL_LAUNCH(&lc, K_OTHER, 0, stream, k_pack_rows<<<grid, 256, 0, stream>>>(g.d, g.pitch, g.w, d_pack));
+  return d_pack;
+}
 
 void DeviceSim::project_sinks() {
   // sinks (simulation.cpp:173-187): grid position, border skip, decay and erase

@@ -122,6 +122,12 @@ public:
   float *h_stage = nullptr;
   size_t cap_stage = 0;
   cudaEvent_t ev_stage = nullptr;
+  // D->H of a large field for the host mirrors: rows packed to the reference's unpadded
+  // layout on the device, then ONE contiguous DMA (a pitched 2-D copy of 8191-float rows
+  // runs at 40 GB/s on this box, a contiguous one at 45 GB/s; tools/pcie_probe.py)
+  float *packed(const Grid &g); // stream-ordered; the buffer is reused by the next call
+  float *d_pack = nullptr;
+  size_t cap_pack = 0;
 
 private:
   // Three buffers per velocity component in the roles front / back
