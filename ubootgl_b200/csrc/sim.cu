@@ -134,6 +134,37 @@ struct TapRows {
   int *err = nullptr;
 };
 
+// The rare slab case -- a tap row that is not stored locally -- is kept out of line so that
+// the common path of the slab kernels stays as lean (registers, instruction count) as the
+// single-GPU one.  Same arithmetic, rows fetched from the neighbour's arena.
+__device__ __noinline__ float bicubic_far(const float *g, int pitch, int icx, int icy, float stx,
+                                          float sty, int h, int lo, int hi_, int plo, int phi,
+                                          const float *g_lo, const float *g_hi, int *err) {
+  if (icy - 1 < plo || icy + 2 >= min(phi, h)) {
+    *err = 1;
+    icy = max(plo + 1, min(icy, min(phi, h) - 3));
+  }
+  const int hi = min(hi_, h);
+  float y0, y1, y2, y3, x0, x1, x2, x3;
+  cr_weights(sty, y0, y1, y2, y3);
+  cr_weights(stx, x0, x1, x2, x3);
+  auto rowp = [&](int y) {
+    const float *b = y < lo ? g_lo : (y >= hi ? g_hi : g);
+    return b + ((size_t)y * pitch + (icx - 1));
+  };
+  const float *r0 = rowp(icy - 1), *r1 = rowp(icy), *r2 = rowp(icy + 1), *r3 = rowp(icy + 2);
+  auto col = [&](int j) {
+    float c = __fmul_rn(y0, __ldg(r0 + j));
+    c = __fmaf_rn(y1, __ldg(r1 + j), c);
+    c = __fmaf_rn(y2, __ldg(r2 + j), c);
+    return __fmaf_rn(y3, __ldg(r3 + j), c);
+  };
+  float v = __fmul_rn(x0, col(0));
+  v = __fmaf_rn(x1, col(1), v);
+  v = __fmaf_rn(x2, col(2), v);
+  return __fmaf_rn(x3, col(3), v);
+}
+
 template <bool SLAB>
 __device__ __forceinline__ float bicubic(const float *__restrict__ g, int pitch, int w, int h,
                                          float cx, float cy, const TapRows &tr,
@@ -141,27 +172,15 @@ __device__ __forceinline__ float bicubic(const float *__restrict__ g, int pitch,
   cx = fmaxf(fminf(cx, (float)w - 3.0f), 3.0f);
   cy = fmaxf(fminf(cy, (float)h - 3.0f), 3.0f);
   const int icx = (int)cx;
-  int icy = (int)cy;
+  const int icy = (int)cy;
   const float stx = __fsub_rn(cx, (float)icx), sty = __fsub_rn(cy, truncf(cy));
+  if (SLAB && (icy - 1 < tr.lo || icy + 2 >= min(tr.hi, h)))
+    return bicubic_far(g, pitch, icx, icy, stx, sty, h, tr.lo, tr.hi, tr.plo, tr.phi, g_lo, g_hi, tr.err);
   float y0, y1, y2, y3, x0, x1, x2, x3;
   cr_weights(sty, y0, y1, y2, y3);
   cr_weights(stx, x0, x1, x2, x3);
-  const float *r0, *r1, *r2, *r3;
-  if (SLAB && (icy - 1 < tr.lo || icy + 2 >= min(tr.hi, h))) {
-    if (icy - 1 < tr.plo || icy + 2 >= min(tr.phi, h)) {
-      *tr.err = 1;
-      icy = max(tr.plo + 1, min(icy, min(tr.phi, h) - 3));
-    }
-    const int hi = min(tr.hi, h);
-    auto rowp = [&](int y) {
-      const float *b = y < tr.lo ? g_lo : (y >= hi ? g_hi : g);
-      return b + ((size_t)y * pitch + (icx - 1));
-    };
-    r0 = rowp(icy - 1); r1 = rowp(icy); r2 = rowp(icy + 1); r3 = rowp(icy + 2);
-  } else {
-    r0 = g + ((icy - 1) * pitch + (icx - 1));
-    r1 = r0 + pitch; r2 = r1 + pitch; r3 = r2 + pitch;
-  }
+  const float *r0 = g + ((icy - 1) * pitch + (icx - 1));
+  const float *r1 = r0 + pitch, *r2 = r1 + pitch, *r3 = r2 + pitch;
   auto col = [&](int j) {
     float c = __fmul_rn(y0, __ldg(r0 + j));
     c = __fmaf_rn(y1, __ldg(r1 + j), c);

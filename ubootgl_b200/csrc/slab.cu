@@ -3,6 +3,7 @@
 #include "stencils.cuh"
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace ubgl {
@@ -10,7 +11,13 @@ namespace ubgl {
 // ---------------------------------------------------------------------------
 // plan (pure host)
 // ---------------------------------------------------------------------------
-static const int SLAB_MIN_ROWS = 64; // own rows per rank on the coarsest distributed level
+// own rows per rank on the coarsest distributed level; coarser levels are replicated
+// (an exchange costs ~20 us of NVLink latency, a replicated 512^2 level about as much)
+static int slab_min_rows() {
+  const char *e = getenv("UBGL_SLAB_MIN_ROWS");
+  const int v = e ? atoi(e) : 64;
+  return v >= 32 ? v : 32;
+}
 
 SlabPlan make_slab_plan(int W, int H, int nranks, int rank) {
   UBGL_REQUIRE(nranks >= 1 && nranks <= SLAB_MAXRANKS, "slab: 1..8 ranks");
@@ -28,7 +35,8 @@ SlabPlan make_slab_plan(int W, int H, int nranks, int rank) {
   UBGL_REQUIRE(P.levels >= 3, "slab: grid too small for a multigrid pyramid");
   const int L = P.levels - 2; // coarsest used level (pressure_solver.cpp:203)
   int n = 0;
-  while (n < L && ((H >> n) / nranks) >= SLAB_MIN_ROWS) n++;
+  const int min_rows = slab_min_rows();
+  while (n < L && ((H >> n) / nranks) >= min_rows) n++;
   UBGL_REQUIRE(n >= 1, "slab: fewer than 64 rows per GPU at level 0 -- use fewer GPUs");
   P.ndist = n;
   const int align = 1 << n;
@@ -82,15 +90,32 @@ __global__ void __launch_bounds__(256) k_halo_push(HaloPush a) {
   }
   __threadfence_system();
   __syncthreads();
+  __shared__ int is_last;
   if (threadIdx.x == 0) {
     const unsigned done = atomicAdd(a.counter, 1u);
-    if (done == gridDim.x - 1) {
+    is_last = done == gridDim.x - 1;
+    if (is_last) {
       *a.counter = 0; // ready for the next launch on this stream
       __threadfence_system();
       for (int i = 0; i < a.nsig; i++)
         if (a.sig[i]) *reinterpret_cast<volatile unsigned *>(a.sig[i]) = a.seq;
       __threadfence_system();
     }
+  }
+  __syncthreads();
+  // the last block stays until the neighbours have released the same sequence number into
+  // this rank's slots (bounded spin, see k_halo_wait); every rank releases before it waits
+  if (is_last && (int)threadIdx.x < a.nwait) {
+    volatile unsigned *s = a.wait[threadIdx.x];
+    const long long t0 = clock64();
+    while ((int)(*s - a.seq) < 0) {
+      if (clock64() - t0 > 40000000000LL) {
+        *a.err = 2;
+        break;
+      }
+      __nanosleep(100);
+    }
+    __threadfence_system();
   }
 }
 
@@ -323,8 +348,10 @@ void SlabSim::push_and_wait(HaloPush &a, const std::vector<int> &peers) {
   for (int s = 0; s < a.nseg; s++) total += a.seg[s].n16;
   halo_bytes += total * 16;
   exchanges++;
+  a.nwait = nslots;
+  for (int i = 0; i < nslots; i++) a.wait[i] = slots[i];
+  a.err = err;
   launch_halo_push(a, total, stream, &lc);
-  launch_halo_wait(slots, nslots, seq, err, stream, &lc);
 }
 
 // Neighbour exchange: my first `depth` own rows go into the lower neighbour's
@@ -633,17 +660,21 @@ void SlabSim::step(float dt_) {
 
   // project: divergence, sinks, V-cycles, setPBC, gradient
   {
-    Grid none{};
-    launch_divergence4(vxb[ixf], vyb[iyf], f, none, none, ih, R.own_lo, R.own_hi, stream, &lc);
-    // accumulator interiors of every stored row (simulation.cpp:384,392)
-    const int y0 = std::max(1, R.st_lo);
-    const int yx = std::min(H - 1, R.st_hi), yy = std::min(H - 2, R.st_hi);
-    if (yx > y0)
-      UBGL_CUDA(cudaMemset2DAsync(&vx_accum.at(1, y0), sizeof(float) * pitch, 0,
-                                  sizeof(float) * (W - 3), yx - y0, stream));
-    if (yy > y0)
-      UBGL_CUDA(cudaMemset2DAsync(&vy_accum.at(1, y0), sizeof(float) * pitch, 0,
-                                  sizeof(float) * (W - 2), yy - y0, stream));
+    // the divergence pass also zeroes the accumulator interiors of the own rows
+    // (simulation.cpp:384,392); the few ghost rows are cleared by memsets
+    launch_divergence4(vxb[ixf], vyb[iyf], f, vx_accum, vy_accum, ih, R.own_lo, R.own_hi, stream, &lc);
+    auto clear_rows = [&](int y0, int y1) {
+      y0 = std::max(1, y0);
+      const int yx = std::min(H - 1, y1), yy = std::min(H - 2, y1);
+      if (yx > y0)
+        UBGL_CUDA(cudaMemset2DAsync(&vx_accum.at(1, y0), sizeof(float) * pitch, 0,
+                                    sizeof(float) * (W - 3), yx - y0, stream));
+      if (yy > y0)
+        UBGL_CUDA(cudaMemset2DAsync(&vy_accum.at(1, y0), sizeof(float) * pitch, 0,
+                                    sizeof(float) * (W - 2), yy - y0, stream));
+    };
+    clear_rows(R.st_lo, R.own_lo);
+    clear_rows(R.own_hi, R.st_hi);
   }
   project_sinks();
   exchange({xf(f, 0)}, 8);

@@ -57,6 +57,11 @@ struct HaloPush {
   unsigned *sig[SLAB_MAXRANKS];    // peer signal slots to release (nullptr: none)
   int nsig;
   unsigned seq;
+  // the same launch then waits for the neighbours' releases of `seq` (one kernel per
+  // exchange instead of a push + a wait launch)
+  unsigned *wait[SLAB_MAXRANKS];   // local signal slots to wait on
+  int nwait;
+  int *err;
 };
 
 class SlabSim {

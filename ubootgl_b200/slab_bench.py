@@ -132,8 +132,10 @@ def run(args, name):
         "halo": {"wait_ms_per_step_max_rank": wait_max, "wait_ms_per_step_min_rank": wait_min,
                  "push_ms_per_step_max_rank": push_max, "compute_ms_per_step_max_rank": compute_max,
                  "compute_ms_per_step_min_rank": compute_min,
-                 "note": "profiled run (events around every launch); wait = k_halo_wait spinning on the "
-                         "neighbours' signals = load imbalance + NVLink latency"},
+                 "note": "profiled run (events around every launch); one k_halo_push launch per exchange "
+                         "stores the boundary rows into the neighbours, releases, then waits for their "
+                         "releases: push time = NVLink stores + load imbalance + latency (wait is 0: "
+                         "the separate k_halo_wait launch is gone)"},
         "kernels_ms_per_step_rank0": [{"kernel": k, "level": l, "launches": n, "ms": round(ms, 4)}
                                       for ms, n, k, l in kern[:14]],
         "cpu_baseline": None,
