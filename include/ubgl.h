@@ -234,9 +234,10 @@ long long ubgl_slab_launch_count(ubgl_slab_t *s);
 void *ubgl_slab_stream(ubgl_slab_t *s);
 /* halo exchanges issued and bytes pushed to peers so far */
 int ubgl_slab_stats(ubgl_slab_t *s, long long *exchanges, long long *halo_bytes);
-/* per-kernel profile of this rank, as ubgl_sim_profile / ubgl_sim_kernel_stats; the halo
- * kernels appear as kinds "halo_push" (peer stores + signal) and "halo_wait" (time spent
- * waiting for the neighbours, i.e. load imbalance + NVLink latency) */
+/* per-kernel profile of this rank, as ubgl_sim_profile / ubgl_sim_kernel_stats; an exchange
+ * is ONE launch of kind "halo_push": peer stores, release of the sequence number, then the
+ * wait for the neighbours' releases (so its time = NVLink stores + load imbalance + latency;
+ * the kind "halo_wait" is kept for the stand-alone wait kernel, unused by step) */
 int ubgl_slab_profile(ubgl_slab_t *s, int on);
 int ubgl_slab_kernel_stats(ubgl_slab_t *s, int kind, int level, long long *count, double *ms);
 

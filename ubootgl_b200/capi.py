@@ -407,8 +407,10 @@ class Items:
         self.n = len(items)
         _ck(lib.ubgl_items_upload(self._h, items.ctypes.data_as(C.c_void_p), len(items)))
 
-    def get(self):
-        a = np.zeros(self.n, ITEM_DTYPE)
+    def get(self, out=None):
+        """Item records back to the host; `out` (n x ITEM_DTYPE, e.g. pinned) is filled in place."""
+        a = np.zeros(self.n, ITEM_DTYPE) if out is None else out
+        assert a.dtype == ITEM_DTYPE and a.size >= self.n and a.flags.c_contiguous
         n = C.c_int()
         _ck(lib.ubgl_items_download(self._h, a.ctypes.data_as(C.c_void_p), self.n, C.byref(n)))
         return a

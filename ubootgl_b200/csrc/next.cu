@@ -250,17 +250,37 @@ __global__ void __launch_bounds__(ITEMS_NT) k_items_advect(Item *items, const in
         tile[t] = base + t < qhi ? __ldg(&spos[base + t]) : make_float2(0.0f, 0.0f);
       __syncthreads();
       const int j1 = min(qe, base + ITEMS_TILE) - base;
-#pragma unroll 8
-      for (int j = max(qs, base) - base; j < j1; j++) {
+      int j = max(qs, base) - base;
+      auto hit = [&](float dx, float dy, float d2) { // :170-180, taken for a handful of the pairs
+        const float len = fmaxf(lmin, sqrtf(d2));
+        rfx += 0.0001f * (dx / len / len);
+        rfy += 0.0001f * (dy / len / len);
+        contacts++;
+      };
+      // 8 pair tests at a time, branch-free; the (rare) contacts of a batch are then applied in
+      // array order, so the sums round exactly as in the one-by-one loop
+      for (; j + 8 <= j1; j += 8) {
+        float dx[8], dy[8], d2[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          const float2 o = tile[j + k];
+          dx[k] = px0 - o.x;
+          dy[k] = py0 - o.y;
+          d2[k] = dx[k] * dx[k] + dy[k] * dy[k];
+        }
+        const float m = fminf(fminf(fminf(d2[0], d2[1]), fminf(d2[2], d2[3])),
+                              fminf(fminf(d2[4], d2[5]), fminf(d2[6], d2[7])));
+        if (m < r2) {
+#pragma unroll
+          for (int k = 0; k < 8; k++)
+            if (d2[k] < r2) hit(dx[k], dy[k], d2[k]);
+        }
+      }
+      for (; j < j1; j++) {
         const float2 o = tile[j];
         const float dx = px0 - o.x, dy = py0 - o.y;
         const float d2 = dx * dx + dy * dy;
-        if (d2 < r2) {
-          const float len = fmaxf(lmin, sqrtf(d2));
-          rfx += 0.0001f * (dx / len / len);
-          rfy += 0.0001f * (dy / len / len);
-          contacts++;
-        }
+        if (d2 < r2) hit(dx, dy, d2);
       }
     }
   }
