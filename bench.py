@@ -552,6 +552,7 @@ KERNEL_BYTES = {
     "mg_pre_fused": 3 * 16.0 + 16.0 + 5.0,          # 3 sweeps + residual + restrict
     "mg_post_fused": 1.0 + 22.0 + 3 * 16.0,         # zero ec + prolong+correct + 3 sweeps
     "diffuse": 12.0, "accum": 16.0, "advect": 10.0, "divergence": 12.0, "gradient": 24.0,
+    "mg_coarse_fused": 140.0 * 4.0 / 3.0,           # k_mg_tail: levels t..L, per cell of level t (geometric sum)
     "prestep_fused": 32.0 + 48.0, "advect_div_fused": 20.0 + 12.0, "finish_fused": 24.0 + 16.0,
 }
 
