@@ -1,0 +1,28 @@
+"""GPU: the row-pair advect kernels (default) must reproduce the one-face-per-thread kernels
+BIT FOR BIT -- same per-face arithmetic, only the tap loads are shared between the two rows of
+a pair.  The variant is fixed per process (UBGL_ADVECT_VARIANT), hence two subprocesses."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_pair_kernels_equal_single_face_kernels(ubgl, tmp_path):
+    outs = []
+    for variant in ("1", "2"):
+        out = str(tmp_path / f"advect_v{variant}.npz")
+        env = dict(os.environ, UBGL_ADVECT_VARIANT=variant)
+        subprocess.run([sys.executable, os.path.join(ROOT, "tests", "advect_dump.py"), out], check=True, env=env,
+                       timeout=300)
+        outs.append(np.load(out))
+    a, b = outs
+    assert sorted(a.files) == sorted(b.files) and len(a.files) > 0
+    for k in a.files:
+        x, y = a[k], b[k]
+        same = (x.view(np.uint32) == y.view(np.uint32)) | ((x == 0) & (y == 0))
+        assert same.all(), (k, float(np.abs(x - y).max()))

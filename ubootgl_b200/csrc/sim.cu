@@ -2,6 +2,7 @@
 // simulation.hpp / interpolators.hpp of te42kyfo/ubootgl (file:line per kernel).
 #include "sim.cuh"
 #include "stencils.cuh"
+#include <cstdlib>
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -276,6 +277,160 @@ __global__ void __launch_bounds__(256, 8) k_advect_vy(Grid vx, Grid vy, Grid vyb
   vyb.at(xi, y) = __fmul_rn(__fmul_rn(yvel, f0), f1);
 }
 
+// ---------------------------------------------------------------------------
+// Row-pair advect (EXPERIMENT, off by default: UBGL_ADVECT_VARIANT=2).  Question: are
+// k_advect_vx / vy above bound by the L1 wavefront rate (56 loads per face, each touching
+// two 128-byte lines) or by instruction issue?  Here a thread advects the faces (x, y) and
+// (x, y+1): their back-traced 4x4 tap windows are, almost everywhere, the same columns and
+// rows shifted by one, so the pair needs 5 tap rows instead of 2 x 4 (and 6 instead of 8
+// loads for the RK2 start velocity): 38 loads per face.  Where the pair's windows do not
+// line up (strong shear, clamping at the border, a far tap of a slab run) the two samples
+// are taken separately with bicubic<SLAB>().  Per-face arithmetic is unchanged, the results
+// are bit-identical to the one-face kernels (tests/test_gpu_advect_variants.py).
+// Answer (B200, 8192^2): 0.789 vs 0.776 ms per launch -- a third fewer loads buys nothing,
+// the kernel is bound by instruction issue (154 FP + ~150 address / conversion / control
+// instructions per face), so the simpler one-face kernels stay the default.
+// ---------------------------------------------------------------------------
+template <bool SLAB>
+__device__ __forceinline__ void bicubic2(const float *__restrict__ g, int pitch, int w, int h,
+                                         float cxA, float cyA, float cxB, float cyB, const TapRows &tr,
+                                         const float *g_lo, const float *g_hi, float &outA, float &outB) {
+  const float ax = fmaxf(fminf(cxA, (float)w - 3.0f), 3.0f), ay = fmaxf(fminf(cyA, (float)h - 3.0f), 3.0f);
+  const float bx = fmaxf(fminf(cxB, (float)w - 3.0f), 3.0f), by = fmaxf(fminf(cyB, (float)h - 3.0f), 3.0f);
+  const int iax = (int)ax, iay = (int)ay, ibx = (int)bx, iby = (int)by;
+  bool together = iax == ibx && iby == iay + 1;
+  if (SLAB) together = together && !(iay - 1 < tr.lo || iby + 2 >= min(tr.hi, h));
+  if (!together) {
+    outA = bicubic<SLAB>(g, pitch, w, h, cxA, cyA, tr, g_lo, g_hi);
+    outB = bicubic<SLAB>(g, pitch, w, h, cxB, cyB, tr, g_lo, g_hi);
+    return;
+  }
+  float a0, a1, a2, a3, b0, b1, b2, b3, xa0, xa1, xa2, xa3, xb0, xb1, xb2, xb3;
+  cr_weights(__fsub_rn(ay, truncf(ay)), a0, a1, a2, a3);
+  cr_weights(__fsub_rn(ax, (float)iax), xa0, xa1, xa2, xa3);
+  cr_weights(__fsub_rn(by, truncf(by)), b0, b1, b2, b3);
+  cr_weights(__fsub_rn(bx, (float)ibx), xb0, xb1, xb2, xb3);
+  const float *r0 = g + ((iay - 1) * pitch + (iax - 1));
+  const float *r1 = r0 + pitch, *r2 = r1 + pitch, *r3 = r2 + pitch, *r4 = r3 + pitch;
+  float ca[4], cb[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const float t0 = __ldg(r0 + j), t1 = __ldg(r1 + j), t2 = __ldg(r2 + j), t3 = __ldg(r3 + j), t4 = __ldg(r4 + j);
+    float c = __fmul_rn(a0, t0);
+    c = __fmaf_rn(a1, t1, c);
+    c = __fmaf_rn(a2, t2, c);
+    ca[j] = __fmaf_rn(a3, t3, c);
+    c = __fmul_rn(b0, t1);
+    c = __fmaf_rn(b1, t2, c);
+    c = __fmaf_rn(b2, t3, c);
+    cb[j] = __fmaf_rn(b3, t4, c);
+  }
+  float v = __fmul_rn(xa0, ca[0]);
+  v = __fmaf_rn(xa1, ca[1], v);
+  v = __fmaf_rn(xa2, ca[2], v);
+  outA = __fmaf_rn(xa3, ca[3], v);
+  v = __fmul_rn(xb0, cb[0]);
+  v = __fmaf_rn(xb1, cb[1], v);
+  v = __fmaf_rn(xb2, cb[2], v);
+  outB = __fmaf_rn(xb3, cb[3], v);
+}
+
+// COMP 0: x-velocity faces (simulation.cpp:246-297), COMP 1: y-velocity faces (:300-347).
+// blockDim = (32, 8): a block covers 32 faces x 16 rows, thread (lane, ty) the rows
+// y and y+1 with y = y_lo + 16 blockIdx.y + 2 ty.  Octet logic per row as in the
+// one-face kernels.
+template <bool SLAB, int COMP>
+__global__ void __launch_bounds__(256, 4) k_advect_pair(Grid vx, Grid vy, Grid out, Grid flag, float half, float full,
+                                                        int y_lo, int y_hi, TapRows tr) {
+  const int lane = threadIdx.x;
+  const int xi = 1 + blockIdx.x * 32 + lane;
+  const int yA = y_lo + (blockIdx.y * blockDim.y + threadIdx.y) * 2, yB = yA + 1;
+  const Grid &self = COMP == 0 ? vx : vy;
+  const int x0 = xi - (lane & 7);
+  const bool octA = yA < y_hi && (x0 < self.w - 8), octB = yB < y_hi && (x0 < self.w - 8);
+  bool condA = false, condB = false;
+  float fA0 = 0.f, fA1 = 0.f, fB0 = 0.f, fB1 = 0.f;
+  const int fp = flag.pitch;
+  if (octA) {
+    const float *fl = flag.d + (size_t)yA * fp + xi;
+    fA0 = fl[0];
+    if (COMP == 0) {
+      fA1 = fl[1];
+      condA = (__fadd_rn(fl[-1], fA0) == 2.0f);
+    } else {
+      fA1 = fl[fp];
+      condA = (__fadd_rn(fA0, fl[-fp]) == 2.0f);
+      if (octB) { // row B's flags: (x, y+1) = fA1, (x, y+2), and its test pairs (x, y+1) with (x, y)
+        fB0 = fA1;
+        fB1 = fl[2 * fp];
+        condB = (__fadd_rn(fB0, fA0) == 2.0f);
+      }
+    }
+  }
+  if (COMP == 0 && octB) {
+    const float *fl = flag.d + (size_t)yB * fp + xi;
+    fB0 = fl[0];
+    fB1 = fl[1];
+    condB = (__fadd_rn(fl[-1], fB0) == 2.0f);
+  }
+  const unsigned ballA = __ballot_sync(0xffffffffu, condA), ballB = __ballot_sync(0xffffffffu, condB);
+  const bool actA = octA && ((ballA >> (lane & ~7)) & 0xffu) != 0;
+  const bool actB = octB && ((ballB >> (lane & ~7)) & 0xffu) != 0;
+  if (!actA && !actB) return;
+  // an inactive face of the pair is computed on the coordinates of the active one (never stored)
+  const int ya = actA ? yA : yB, yb = actB ? yB : yA;
+
+  float posxA, posyA, posxB, posyB, vx1A, vy1A, vx1B, vy1B;
+  if (COMP == 0) {
+    posxA = posxB = __fadd_rn((float)xi, 0.5f);
+    posyA = (float)ya;
+    posyB = (float)yb;
+    vx1A = vx.at(xi, ya);
+    vx1B = vx.at(xi, yb);
+    // vy rows ya-1, ya (and yb = ya+1 when the pair is whole) at x and x+1
+    const float p0 = vy.at(xi, ya - 1), q0 = vy.at(xi + 1, ya - 1), p1 = vy.at(xi, ya), q1 = vy.at(xi + 1, ya);
+    vy1A = __fmul_rn(__fadd_rn(__fadd_rn(p1, p0), __fadd_rn(q1, q0)), 0.25f);
+    if (yb == ya + 1) {
+      const float p2 = vy.at(xi, yb), q2 = vy.at(xi + 1, yb);
+      vy1B = __fmul_rn(__fadd_rn(__fadd_rn(p2, p1), __fadd_rn(q2, q1)), 0.25f);
+    } else {
+      vy1B = vy1A;
+    }
+  } else {
+    posxA = posxB = (float)xi;
+    posyA = __fadd_rn((float)ya, 0.5f);
+    posyB = __fadd_rn((float)yb, 0.5f);
+    vy1A = vy.at(xi, ya);
+    vy1B = vy.at(xi, yb);
+    const float p0 = vx.at(xi, ya - 1), q0 = vx_flat(vx, xi + 1, ya - 1), p1 = vx.at(xi, ya), q1 = vx_flat(vx, xi + 1, ya);
+    vx1A = __fmul_rn(__fadd_rn(__fadd_rn(p1, p0), __fadd_rn(q1, q0)), 0.25f);
+    if (yb == ya + 1) {
+      const float p2 = vx.at(xi, yb), q2 = vx_flat(vx, xi + 1, yb);
+      vx1B = __fmul_rn(__fadd_rn(__fadd_rn(p2, p1), __fadd_rn(q2, q1)), 0.25f);
+    } else {
+      vx1B = vx1A;
+    }
+  }
+  const float midxA = __fmaf_rn(-vx1A, half, posxA), midyA = __fmaf_rn(-vy1A, half, posyA);
+  const float midxB = __fmaf_rn(-vx1B, half, posxB), midyB = __fmaf_rn(-vy1B, half, posyB);
+  float vx2A, vx2B, vy2A, vy2B;
+  bicubic2<SLAB>(vx.d, vx.pitch, vx.w, vx.h, __fsub_rn(midxA, 0.5f), midyA, __fsub_rn(midxB, 0.5f), midyB, tr,
+                 tr.x_lo, tr.x_hi, vx2A, vx2B);
+  bicubic2<SLAB>(vy.d, vy.pitch, vy.w, vy.h, midxA, __fsub_rn(midyA, 0.5f), midxB, __fsub_rn(midyB, 0.5f), tr,
+                 tr.y_lo, tr.y_hi, vy2A, vy2B);
+  const float endxA = __fmaf_rn(-vx2A, full, posxA), endyA = __fmaf_rn(-vy2A, full, posyA);
+  const float endxB = __fmaf_rn(-vx2B, full, posxB), endyB = __fmaf_rn(-vy2B, full, posyB);
+  float rA, rB;
+  if (COMP == 0)
+    bicubic2<SLAB>(vx.d, vx.pitch, vx.w, vx.h, __fsub_rn(endxA, 0.5f), endyA, __fsub_rn(endxB, 0.5f), endyB, tr,
+                   tr.x_lo, tr.x_hi, rA, rB);
+  else
+    bicubic2<SLAB>(vy.d, vy.pitch, vy.w, vy.h, endxA, __fsub_rn(endyA, 0.5f), endxB, __fsub_rn(endyB, 0.5f), tr,
+                   tr.y_lo, tr.y_hi, rA, rB);
+  if (actA) out.at(xi, yA) = __fmul_rn(__fmul_rn(rA, fA0), fA1);
+  if (actB) out.at(xi, yB) = __fmul_rn(__fmul_rn(rB, fB0), fB1);
+}
+
 // project part 1 (simulation.cpp:166-171): f = -(1/h) div v on the interior
 __global__ void k_divergence(Grid vx, Grid vy, Grid f, float ih) {
   int x = 1 + blockIdx.x * blockDim.x + threadIdx.x;
@@ -485,6 +640,25 @@ void launch_advect(const Grid &vx, const Grid &vy, const Grid &vxbk, const Grid 
   if (y_hi <= y_lo) return;
   dim3 b(32, 8);
   dim3 g(ceil_div(W - 2, 32), ceil_div(y_hi - y_lo, 8));
+  static const int variant = [] { // 1 (default): one face per thread; 2: row-pair kernels
+    const char *e = getenv("UBGL_ADVECT_VARIANT");
+    return (e && e[0] == '2') ? 2 : 1;
+  }();
+  if (variant == 2) {
+    dim3 g2(g.x, ceil_div(y_hi - y_lo, 16));
+    TapRows tr{};
+    if (peers) {
+      tr.lo = peers->st_lo; tr.hi = peers->st_hi; tr.plo = peers->peer_lo; tr.phi = peers->peer_hi;
+      tr.x_lo = peers->vx_lo; tr.x_hi = peers->vx_hi; tr.y_lo = peers->vy_lo; tr.y_hi = peers->vy_hi;
+      tr.err = peers->err;
+      UBGL_LAUNCH(lc, K_ADVECT, LVL, stream, (k_advect_pair<true, 0><<<g2, b, 0, stream>>>(vx, vy, vxbk, flag, half, full, y_lo, y_hi, tr)));
+      UBGL_LAUNCH(lc, K_ADVECT, LVL, stream, (k_advect_pair<true, 1><<<g2, b, 0, stream>>>(vx, vy, vybk, flag, half, full, y_lo, y_hi, tr)));
+    } else {
+      UBGL_LAUNCH(lc, K_ADVECT, LVL, stream, (k_advect_pair<false, 0><<<g2, b, 0, stream>>>(vx, vy, vxbk, flag, half, full, y_lo, y_hi, tr)));
+      UBGL_LAUNCH(lc, K_ADVECT, LVL, stream, (k_advect_pair<false, 1><<<g2, b, 0, stream>>>(vx, vy, vybk, flag, half, full, y_lo, y_hi, tr)));
+    }
+    return;
+  }
   if (!peers) {
     TapRows tr{};
     UBGL_LAUNCH(lc, K_ADVECT, LVL, stream, k_advect_vx<false><<<g, b, 0, stream>>>(vx, vy, vxbk, flag, half, full, y_lo, y_hi, tr));
