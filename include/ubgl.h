@@ -289,6 +289,11 @@ int ubgl_items_download(ubgl_items_t *it, ubgl_item *items, int cap, int *n);
  * reference scatters serially under accum_mutex, :160), which removes the per-step
  * upload of the accumulator grids.  Asynchronous on the simulation's stream. */
 int ubgl_items_advect_simple(ubgl_items_t *it, ubgl_sim_t *sim, float game_dt);
+/* Simulation::advectFloatingItems (advect_floating_items.cpp:16-146): the same records
+ * advanced as rigid rectangular bodies (the reference's CoItem + CoKinematics entities --
+ * submarines, torpedoes): five terrain probes and drag sampled along the four sides per
+ * sub-step, reaction forces into the device accumulators.  Bodies do not interact. */
+int ubgl_items_advect(ubgl_items_t *it, ubgl_sim_t *sim, float game_dt);
 
 /* (3) Terrain edits on the resident simulation-resolution mask (terrain scale 1).
  * Terrain::drawCircle (terrain.cpp:213-234) for n circles (cx, cy, diam triples, grid

@@ -329,11 +329,18 @@ class Ref(_Checker):
         L.ref_terrain_draw_circle.argtypes = [v, f, f, i, f]
         L.ref_items_advect_simple.argtypes = [v, v, i, f]
         L.ref_items_view_order.argtypes = [i, IP]
+        if hasattr(L, "ref_items_advect"):
+            L.ref_items_advect.argtypes = [v, v, i, f]
 
     def items_advect_simple(self, sim, items, game_dt):
         """Unmodified Simulation::advectFloatingItemsSimple on sim's fields (in place on items)."""
         assert items.dtype == ITEM_DTYPE and items.flags["C_CONTIGUOUS"]
         self.lib.ref_items_advect_simple(sim.h, items.ctypes.data_as(C.c_void_p), len(items), game_dt)
+
+    def items_advect(self, sim, items, game_dt):
+        """Unmodified Simulation::advectFloatingItems (rigid bodies) on sim's fields (in place on items)."""
+        assert items.dtype == ITEM_DTYPE and items.flags["C_CONTIGUOUS"]
+        self.lib.ref_items_advect(sim.h, items.ctypes.data_as(C.c_void_p), len(items), game_dt)
 
     def items_view_order(self, n):
         o = np.zeros(n, np.int32)
@@ -389,6 +396,7 @@ class Port(_Checker):
         L.orc_tracers_advect.argtypes = [FP, UP, UP, FP, i, i, f, f, f, u, FP, i, i, FP, i, i]
         L.orc_tracers_shift.argtypes = [FP, i, i, f]
         L.orc_items_advect_simple.argtypes = [v, i, f, FP, FP, FP, FP, FP, FP, i, i, f]
+        L.orc_items_advect.argtypes = [v, i, f, FP, FP, FP, FP, FP, i, i, f]
         L.orc_draw_circle.argtypes = [FP, FP, i, i, f, f, i, f]
         L.orc_set_grids_all.argtypes = [FP, FP, FP, FP, FP, i, i]
         L.orc_shift_map.argtypes = [FP] * 9 + [i, i]
@@ -423,6 +431,13 @@ class Port(_Checker):
         self.lib.orc_items_advect_simple(items.ctypes.data_as(C.c_void_p), len(items), game_dt,
                                          fp(f32(flag)), fp(f32(vx)), fp(f32(vy)), fp(f32(p)),
                                          fp(vx_accum), fp(vy_accum), W, H, pwidth)
+
+    def items_advect(self, items, game_dt, flag, vx, vy, vx_accum, vy_accum, pwidth=0.8):
+        """advectFloatingItems (rigid bodies); items and the accumulators are updated in place."""
+        assert items.dtype == ITEM_DTYPE and items.flags["C_CONTIGUOUS"]
+        H, W = flag.shape
+        self.lib.orc_items_advect(items.ctypes.data_as(C.c_void_p), len(items), game_dt, fp(f32(flag)),
+                                  fp(f32(vx)), fp(f32(vy)), fp(vx_accum), fp(vy_accum), W, H, pwidth)
 
     def draw_circle(self, flag_full, flag_sim, cx, cy, diam, val):
         h, w = flag_sim.shape

@@ -1,9 +1,10 @@
 // TEST INFRASTRUCTURE ONLY -- never linked into or called from the product path.
 //
-// Forwards to the UNMODIFIED reference Simulation::advectFloatingItemsSimple
-// (advect_floating_items.cpp:148-274, compiled where it lies by oracle/Makefile)
-// through an entt registry, to pin the restatement orc_items_advect_simple
-// (oracle/ubgl_oracle_next.c).  Nothing here restates the algorithm.
+// Forwards to the UNMODIFIED reference Simulation::advectFloatingItemsSimple and
+// Simulation::advectFloatingItems (advect_floating_items.cpp:148-274 / :16-146, compiled
+// where it lies by oracle/Makefile) through an entt registry, to pin the restatements
+// orc_items_advect_simple / orc_items_advect (oracle/ubgl_oracle_next.c).  Nothing here
+// restates the algorithm.
 #include <cstring>
 #include <vector>
 
@@ -42,6 +43,39 @@ void ref_items_advect_simple(void *sim_, void *items_, int n, float game_dt) {
   for (int i = 0; i < n; i++) {
     const auto &it = reg.get<CoItem>(ent[i]);
     const auto &k = reg.get<CoKinematicsSimple>(ent[i]);
+    ItemRec &r = items[i];
+    r.size[0] = it.size.x; r.size[1] = it.size.y;
+    r.pos[0] = it.pos.x; r.pos[1] = it.pos.y;
+    r.rotation = it.rotation;
+    r.mass = k.mass;
+    r.vel[0] = k.vel.x; r.vel[1] = k.vel.y;
+    r.force[0] = k.force.x; r.force[1] = k.force.y;
+    r.angVel = k.angVel; r.angForce = k.angForce;
+    r.bumpCount = k.bumpCount;
+  }
+}
+
+// The same for Simulation::advectFloatingItems (advect_floating_items.cpp:16-146), whose
+// view is <CoItem, CoKinematics> (same fields as CoKinematicsSimple, components.hpp:12-43).
+void ref_items_advect(void *sim_, void *items_, int n, float game_dt) {
+  auto *sim = (Simulation *)sim_;
+  auto *items = (ItemRec *)items_;
+  entt::registry reg;
+  std::vector<entt::entity> ent(n);
+  for (int i = n - 1; i >= 0; i--) {
+    const ItemRec &r = items[i];
+    auto e = reg.create();
+    reg.emplace<CoItem>(e, glm::vec2(r.size[0], r.size[1]), glm::vec2(r.pos[0], r.pos[1]), r.rotation);
+    auto &k = reg.emplace<CoKinematics>(e, r.mass, glm::vec2(r.vel[0], r.vel[1]), r.angVel);
+    k.force = glm::vec2(r.force[0], r.force[1]);
+    k.angForce = r.angForce;
+    k.bumpCount = r.bumpCount;
+    ent[i] = e;
+  }
+  sim->advectFloatingItems(reg, game_dt);
+  for (int i = 0; i < n; i++) {
+    const auto &it = reg.get<CoItem>(ent[i]);
+    const auto &k = reg.get<CoKinematics>(ent[i]);
     ItemRec &r = items[i];
     r.size[0] = it.size.x; r.size[1] = it.size.y;
     r.pos[0] = it.pos.x; r.pos[1] = it.pos.y;

@@ -86,6 +86,8 @@ void orc_tracers_shift(float *points, int ntracers, int npoints, float shift);
 void orc_items_advect_simple(orc_item *items, int n, float game_dt, const float *flag, const float *vx,
                              const float *vy, const float *p, float *vx_accum, float *vy_accum, int W,
                              int H, float pwidth);
+void orc_items_advect(orc_item *items, int n, float game_dt, const float *flag, const float *vx,
+                      const float *vy, float *vx_accum, float *vy_accum, int W, int H, float pwidth);
 void orc_draw_circle(float *flag_full, float *flag_sim, int w, int h, float cx, float cy, int diam,
                      float val);
 void orc_set_grids_all(float *flag, float *vx, float *vy, float *p, const float *newflag, int W, int H);

@@ -10,7 +10,8 @@
  *     alpha = frac(u), wrap = the texture-object default GL_REPEAT, LOD 0 in a
  *     compute shader => magnification filter, whose default is GL_LINEAR) in
  *     exact fp32, where real GPUs use ~8-bit filter weights.
- *  2. Simulation::advectFloatingItemsSimple (advect_floating_items.cpp:148-274)
+ *  2. Simulation::advectFloatingItemsSimple (advect_floating_items.cpp:148-274) and
+ *     Simulation::advectFloatingItems (:16-146)
  *     with bilinearSample / bilinearScatter (interpolators.hpp:11-40) and
  *     psampleFlagLinear / psampleFlagNormal (simulation.cpp:398-420).
  *     PARITY PINNED against the unmodified reference TU in oracle/_ref
@@ -304,6 +305,126 @@ void orc_items_advect_simple(orc_item *items, int n, float game_dt, const float 
   }
   free(bin_of);
   free(bx);
+}
+
+/* Simulation::advectFloatingItems, advect_floating_items.cpp:16-146: rigid rectangular
+ * bodies (CoItem + CoKinematics: the submarines and torpedoes) -- five terrain probes per
+ * sub-step, drag from the fluid sampled along the four sides, reaction scattered into the
+ * accumulators.  glm::rotate / normalize / reflect as GLM defines them (2-D rotation,
+ * a / length(a), I - N dot(N,I) 2).  vx, vy are the FRONT buffers. */
+static void rot2(float x, float y, float ang, float *ox, float *oy) {
+  const float c = cosf(ang), s = sinf(ang);
+  *ox = x * c - y * s;
+  *oy = x * s + y * c;
+}
+void orc_items_advect(orc_item *items, int n, float game_dt, const float *flag, const float *vx,
+                      const float *vy, float *vx_accum, float *vy_accum, int W, int H, float pwidth) {
+  const float h = pwidth / ((float)W - 1.0f); /* simulation.hpp:60 */
+  static const float SPX[5] = {1.0f, -1.0f, 1.0f, -1.0f, 0.0f}, SPY[5] = {1.0f, 1.0f, -1.0f, -1.0f, 0.0f}; /* :48-50 */
+  static const float SFX[4] = {-1.0f, 1.0f, 0.0f, 0.0f}, SFY[4] = {0.0f, 0.0f, -1.0f, 1.0f};               /* :80-81 */
+  for (int q = 0; q < n; q++) {
+    orc_item *it = &items[q];
+    const int steps = (int)fmin(15.0f, fmax(1.0f, (double)(fmaxf(fabsf(it->vel[0]), fabsf(it->vel[1])) *
+                                                           game_dt / h) * 2.5)); /* :23-25 */
+    const float sub = game_dt / (float)steps;
+    for (int st = 0; st < steps; st++) {
+      const float bx = it->pos[0], by = it->pos[1]; /* posBefore */
+      it->pos[0] += sub * it->vel[0];               /* :33 */
+      it->pos[1] += sub * it->vel[1];
+      it->rotation = (float)fmod((double)(it->rotation + sub * it->angVel) + 2 * M_PI, 2 * M_PI); /* :36-37 */
+      const float gs = pwidth / (float)W;
+      const float gpx = it->pos[0] / gs, gpy = it->pos[1] / gs;
+      if (gpx >= (float)(W - 2) || gpx <= 1.0f || gpy >= (float)(H - 2) || gpy <= 1.0f) continue; /* :42-45 */
+      it->force[0] += 0.0f * it->mass; /* :47 */
+      it->force[1] += -0.5f * it->mass;
+      for (int k = 0; k < 5; k++) { /* terrain probes, :52-72 */
+        float spx, spy;
+        rot2(SPX[k] * 0.5f * it->size[0], SPY[k] * 0.5f * it->size[1], it->rotation, &spx, &spy);
+        if (psample_flag_linear(flag, W, H, pwidth, it->pos[0] + spx, it->pos[1] + spy) < 0.5f) {
+          const float mx = 0.5f * (bx + it->pos[0]) + spx, my = 0.5f * (by + it->pos[1]) + spy;
+          const float p01 = psample_flag_linear(flag, W, H, pwidth, mx - h, my + h);
+          const float p11 = psample_flag_linear(flag, W, H, pwidth, mx + h, my + h);
+          const float p00 = psample_flag_linear(flag, W, H, pwidth, mx - h, my - h);
+          const float p10 = psample_flag_linear(flag, W, H, pwidth, mx + h, my - h);
+          float nx = p11 + p10 - p01 - p00, ny = p01 + p11 - p00 - p10; /* simulation.cpp:414-420 */
+          float nl = sqrtf(nx * nx + ny * ny);
+          nx /= nl; /* normalize(): 0/0 = NaN when the normal vanishes */
+          ny /= nl;
+          if (psample_flag_linear(flag, W, H, pwidth, bx + spx, by + spy) > 0.5f) {
+            it->pos[0] = bx;
+            it->pos[1] = by;
+          }
+          nl = sqrtf(nx * nx + ny * ny);
+          if (nl > 0.0f) { /* false for NaN */
+            nx /= nl;
+            ny /= nl;
+            if (it->vel[0] * nx + it->vel[1] * ny < 0.0f) { /* reflect(v, n) * 0.7 */
+              const float d = nx * it->vel[0] + ny * it->vel[1];
+              it->vel[0] = (it->vel[0] - nx * d * 2.0f) * 0.7f;
+              it->vel[1] = (it->vel[1] - ny * d * 2.0f) * 0.7f;
+            }
+            const float fl = psample_flag_linear(flag, W, H, pwidth, it->pos[0] + spx, it->pos[1] + spy);
+            it->vel[0] += nx * 0.07f * fl;
+            it->vel[1] += ny * 0.07f * fl;
+            const float df = it->force[0] * nx + it->force[1] * ny;
+            if (df < 0.0f) {
+              it->force[0] += 1.1f * df * nx;
+              it->force[1] += 1.1f * df * ny;
+            }
+          }
+          it->bumpCount++;
+        }
+      }
+      const float efx = 0.0f * it->mass + it->force[0], efy = -0.5f * it->mass + it->force[1]; /* :74 */
+      float cfx = 0.0f, cfy = 0.0f;
+      const float ang_force = it->angForce;
+      const float side[4] = {it->size[1], it->size[1], it->size[0], it->size[0]}; /* :83 */
+      for (int i = 0; i < 4; i++) {
+        const int nsp = (int)fmaxf(2.0f, side[i] / h); /* :86 */
+        for (int k = 0; k < nsp; k++) {
+          const float tpar = 1.0f - (float)k * 2.0f / (float)(nsp - 1);
+          const float sx = SFX[i] + fabsf(SFY[i]) * tpar, sy = SFY[i] + fabsf(SFX[i]) * tpar; /* :89-91 */
+          const float lx = sx * it->size[0] * 0.5f, ly = sy * it->size[1] * 0.5f;
+          float tx, ty;
+          rot2(lx, ly, it->rotation, &tx, &ty);
+          tx += it->pos[0];
+          ty += it->pos[1];
+          const float gx = tx / h, gy = ty / h;
+          float rx, ry;
+          rot2(lx, ly, it->rotation + 0.5f * 3.141f, &rx, &ry);
+          const float dvx = bilinear_sample(vx, W - 1, H, gx - 0.5f, gy) - (it->vel[0] + 3.141f * rx * it->angVel);
+          const float dvy = bilinear_sample(vy, W, H - 1, gx, gy - 0.5f) - (it->vel[1] + 3.141f * ry * it->angVel);
+          const float sl = sqrtf(sx * sx + sy * sy);
+          float nx, ny, ox, oy;
+          rot2(sx / sl, sy / sl, it->rotation, &nx, &ny);  /* rotate(normalize(sp), rotation) */
+          rot2(SFX[i], SFY[i], it->rotation, &ox, &oy);
+          const float pr = fminf(0.0f, dvx * ox + dvy * oy);
+          const float fx = nx * pr, fy = ny * pr;
+          cfx += fx * 400000.0f * (0.003f + side[i]) * side[i] / (float)nsp; /* :110-111 */
+          cfy += fy * 400000.0f * (0.003f + side[i]) * side[i] / (float)nsp;
+          if (gx < 1.0f || gx > (float)(W - 1) - 2.0f || gy < 1.0f || gy > (float)H - 2.0f) continue; /* :113-115 */
+          const float ddx = fx * (0.003f + side[i]) * side[i] / (float)nsp * sub * 18000000.0f;
+          const float ddy = fy * (0.003f + side[i]) * side[i] / (float)nsp * sub * 18000000.0f;
+          bilinear_scatter(vx_accum, W - 1, H, gx - 0.5f, gy, -ddx);
+          bilinear_scatter(vy_accum, W, H - 1, gx, gy - 0.5f, -ddy);
+        }
+      }
+      {
+        const float gx = it->pos[0] / h, gy = it->pos[1] / h; /* :125-126 */
+        const float kk = 1000.0f * (it->size[0] + it->size[1]);
+        cfx += kk * (bilinear_sample(vx, W - 1, H, gx - 0.5f, gy) - it->vel[0]);
+        cfy += kk * (bilinear_sample(vy, W, H - 1, gx, gy - 0.5f) - it->vel[1]);
+      }
+      it->vel[0] += sub * (efx + cfx) / it->mass; /* :129 */
+      it->vel[1] += sub * (efy + cfy) / it->mass;
+      const float ang_mass = it->size[0] * it->size[1] * it->mass * (1.0f / 12.0f);
+      it->angVel += sub * ang_force / ang_mass;
+      it->angVel = (float)((double)it->angVel * 0.98); /* :135 */
+    }
+    it->angForce = 0.0f;
+    it->force[0] = 0.0f;
+    it->force[1] = 0.0f;
+  }
 }
 
 /* ------------------------------------------------------------------------

@@ -85,6 +85,36 @@ def test_items_match_oracle(ubgl, port, W, H, n, dt):
         assert rel_l2(G.get(f), O.get(f)) <= 3e-5
 
 
+@pytest.mark.parametrize("W,H,n,dt", [(130, 97, 300, 0.004), (258, 131, 1000, 0.01), (545, 218, 400, 1.0 / 60.0)])
+def test_bodies_match_oracle(ubgl, port, W, H, n, dt):
+    """ubgl_items_advect (Simulation::advectFloatingItems, rigid bodies) against the restatement
+    that tests/test_oracle_next.py pins on the unmodified reference."""
+    from tests.test_oracle_next import close_fraction
+    flag, O = next_cases.developed_flow(port, W, H, seed=W + H)
+    G = gpu_twin(ubgl, O, flag)
+    items = next_cases.make_bodies(n, W, H, seed=5, flag=flag)
+    I = ubgl.Items(items)
+    o = items.copy()
+    ax, ay = O.get(ob.VX_ACCUM), O.get(ob.VY_ACCUM)
+    vx, vy = O.get(ob.VX), O.get(ob.VY)
+    for k in range(3):
+        I.advect(G, dt)
+        port.items_advect(o, dt, flag, vx, vy, ax, ay)
+        g = I.get()
+        assert np.isfinite(g["pos"]).all()
+        assert close_fraction(g, o) >= 0.99, (k, close_fraction(g, o))
+        assert (g["bumpCount"] == o["bumpCount"]).mean() >= 0.99
+        assert (g["force"] == 0).all() and (g["angForce"] == 0).all()
+    assert o["bumpCount"].sum() > 0
+    assert np.abs(ax).sum() > 0
+    assert rel_l2(G.get(ob.VX_ACCUM), ax) <= 1e-3 and rel_l2(G.get(ob.VY_ACCUM), ay) <= 1e-3
+    # the scattered reaction feeds the next fluid step like host-uploaded accumulators
+    O.set(ob.VX_ACCUM, ax); O.set(ob.VY_ACCUM, ay)
+    G.step(0.001); O.step(0.001)
+    for f in (ob.VX, ob.VY, ob.P):
+        assert rel_l2(G.get(f), O.get(f)) <= 1e-3
+
+
 def test_items_empty_and_regrow(ubgl, port):
     flag, O = next_cases.developed_flow(port, 70, 40, seed=1)
     G = gpu_twin(ubgl, O, flag)

@@ -33,6 +33,40 @@ def test_items_port_matches_reference(port, ref, W, H, n, dt):
     assert rel_l2(ax, rx) <= 1e-4 and rel_l2(ay, ry) <= 1e-4
 
 
+def close_fraction(a, b, rtol=2e-4):
+    """Share of items whose record agrees (collisions are threshold tests: an item whose probe
+    lands within rounding of the 0.5 iso-line may take the other branch)."""
+    ok = np.ones(len(a), bool)
+    for name in ("pos", "vel", "rotation", "angVel", "force", "angForce"):
+        x, y = a[name].reshape(len(a), -1).astype(np.float64), b[name].reshape(len(a), -1).astype(np.float64)
+        scale = np.abs(y).max() + 1e-30
+        ok &= (np.abs(x - y) <= rtol * (np.abs(y) + 1e-3 * scale)).all(axis=1)
+    return ok.mean()
+
+
+@pytest.mark.parametrize("W,H,n,dt", [(130, 97, 300, 0.004), (258, 131, 1000, 0.01), (545, 218, 400, 1.0 / 60.0)])
+def test_bodies_port_matches_reference(port, ref, W, H, n, dt):
+    """orc_items_advect against the UNMODIFIED Simulation::advectFloatingItems
+    (advect_floating_items.cpp:16-146)."""
+    flag, O = next_cases.developed_flow(port, W, H, seed=W + H)
+    R = ref.Sim(flag)
+    for f in (ob.VX, ob.VY, ob.P):
+        R.set(f, O.get(f))
+    items = next_cases.make_bodies(n, W, H, seed=5, flag=flag)
+    a, b = items.copy(), items.copy()
+    ax, ay = np.zeros((H, W - 1), np.float32), np.zeros((H - 1, W), np.float32)
+    for k in range(3):
+        ref.items_advect(R, a, dt)
+        port.items_advect(b, dt, flag, O.get(ob.VX), O.get(ob.VY), ax, ay)
+        assert np.isfinite(a["pos"]).all() and np.isfinite(b["pos"]).all()
+        assert close_fraction(b, a) >= 0.99, (k, close_fraction(b, a))
+        assert (a["bumpCount"] == b["bumpCount"]).mean() >= 0.99
+    assert a["bumpCount"].sum() > 0, "no body touched terrain: the probe branch is untested"
+    rx, ry = R.get(ob.VX_ACCUM), R.get(ob.VY_ACCUM)
+    assert np.abs(rx).sum() > 0
+    assert rel_l2(ax, rx) <= 5e-4 and rel_l2(ay, ry) <= 5e-4
+
+
 def test_entt_view_order_is_array_order(ref):
     assert (ref.items_view_order(17) == np.arange(17)).all()
 

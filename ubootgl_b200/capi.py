@@ -123,6 +123,7 @@ def _load():
         "ubgl_items_upload": (i, [v, v, i]),
         "ubgl_items_download": (i, [v, v, i, IP]),
         "ubgl_items_advect_simple": (i, [v, v, f]),
+        "ubgl_items_advect": (i, [v, v, f]),
         "ubgl_sim_draw_circles": (i, [v, FP, i, f]),
         "ubgl_sim_set_grids_all": (i, [v, FP]),
         "ubgl_sim_shift_map": (i, [v, FP]),
@@ -414,6 +415,10 @@ class Items:
         n = C.c_int()
         _ck(lib.ubgl_items_download(self._h, a.ctypes.data_as(C.c_void_p), self.n, C.byref(n)))
         return a
+
+    def advect(self, sim, game_dt):
+        """Simulation::advectFloatingItems (rigid bodies, advect_floating_items.cpp:16-146)."""
+        _ck(lib.ubgl_items_advect(self._h, sim._h, game_dt))
 
     def advect_simple(self, sim, game_dt):
         """Simulation::advectFloatingItemsSimple (advect_floating_items.cpp:148-274)."""

@@ -370,6 +370,127 @@ __global__ void __launch_bounds__(ITEMS_NT) k_items_advect(Item *items, const in
   items[order[k]] = it;
 }
 
+// Simulation::advectFloatingItems (advect_floating_items.cpp:16-146): the rigid rectangular
+// bodies (CoItem + CoKinematics -- submarines, torpedoes).  Bodies do not interact, so it is
+// one thread per body; per sub-step five terrain probes (each up to six bilinear flag samples),
+// then drag sampled at max(2, side/h) points along each of the four sides with the reaction
+// scattered into the device accumulators by atomicAdd, like the simple items above.
+__device__ __forceinline__ void rot2(float x, float y, float ang, float &ox, float &oy) {
+  const float c = cosf(ang), s = sinf(ang); // glm::rotate(vec2, angle)
+  ox = x * c - y * s;
+  oy = x * s + y * c;
+}
+__global__ void __launch_bounds__(64) k_items_advect_rigid(Item *items, int n, float game_dt, Grid flag, Grid vx,
+                                                          Grid vy, Grid ax, Grid ay, float pwidth, float h) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  Item it = items[q];
+  const int W = flag.w, H = flag.h;
+  const float SPX[5] = {1.0f, -1.0f, 1.0f, -1.0f, 0.0f}, SPY[5] = {1.0f, 1.0f, -1.0f, -1.0f, 0.0f}; // :48-50
+  const float SFX[4] = {-1.0f, 1.0f, 0.0f, 0.0f}, SFY[4] = {0.0f, 0.0f, -1.0f, 1.0f};               // :80-81
+  const int steps = (int)fmin(15.0, fmax(1.0, (double)(fmaxf(fabsf(it.vel[0]), fabsf(it.vel[1])) * game_dt / h) * 2.5));
+  const float sub = game_dt / (float)steps;
+  const float gs = pwidth / (float)W;
+  for (int st = 0; st < steps; st++) {
+    const float bx = it.pos[0], by = it.pos[1]; // posBefore
+    it.pos[0] += sub * it.vel[0];
+    it.pos[1] += sub * it.vel[1];
+    it.rotation = (float)fmod((double)(it.rotation + sub * it.angVel) + 2 * M_PI, 2 * M_PI);
+    const float gpx = it.pos[0] / gs, gpy = it.pos[1] / gs;
+    if (gpx >= (float)(W - 2) || gpx <= 1.0f || gpy >= (float)(H - 2) || gpy <= 1.0f) continue; // :42-45
+    it.force[0] += 0.0f * it.mass; // :47
+    it.force[1] += -0.5f * it.mass;
+#pragma unroll 1
+    for (int k = 0; k < 5; k++) { // terrain probes, :52-72
+      float spx, spy;
+      rot2(SPX[k] * 0.5f * it.size[0], SPY[k] * 0.5f * it.size[1], it.rotation, spx, spy);
+      if (psample_flag_linear(flag, pwidth, it.pos[0] + spx, it.pos[1] + spy) < 0.5f) {
+        const float mx = 0.5f * (bx + it.pos[0]) + spx, my = 0.5f * (by + it.pos[1]) + spy;
+        const float p01 = psample_flag_linear(flag, pwidth, mx - h, my + h);
+        const float p11 = psample_flag_linear(flag, pwidth, mx + h, my + h);
+        const float p00 = psample_flag_linear(flag, pwidth, mx - h, my - h);
+        const float p10 = psample_flag_linear(flag, pwidth, mx + h, my - h);
+        float nx = p11 + p10 - p01 - p00, ny = p01 + p11 - p00 - p10; // psampleFlagNormal
+        float nl = sqrtf(nx * nx + ny * ny);
+        nx /= nl; // normalize(): NaN when the normal vanishes, then the block below is skipped
+        ny /= nl;
+        if (psample_flag_linear(flag, pwidth, bx + spx, by + spy) > 0.5f) {
+          it.pos[0] = bx;
+          it.pos[1] = by;
+        }
+        nl = sqrtf(nx * nx + ny * ny);
+        if (nl > 0.0f) {
+          nx /= nl;
+          ny /= nl;
+          if (it.vel[0] * nx + it.vel[1] * ny < 0.0f) { // reflect(v, n) * 0.7
+            const float d = nx * it.vel[0] + ny * it.vel[1];
+            it.vel[0] = (it.vel[0] - nx * d * 2.0f) * 0.7f;
+            it.vel[1] = (it.vel[1] - ny * d * 2.0f) * 0.7f;
+          }
+          const float fl = psample_flag_linear(flag, pwidth, it.pos[0] + spx, it.pos[1] + spy);
+          it.vel[0] += nx * 0.07f * fl;
+          it.vel[1] += ny * 0.07f * fl;
+          const float df = it.force[0] * nx + it.force[1] * ny;
+          if (df < 0.0f) {
+            it.force[0] += 1.1f * df * nx;
+            it.force[1] += 1.1f * df * ny;
+          }
+        }
+        it.bumpCount++;
+      }
+    }
+    const float efx = 0.0f * it.mass + it.force[0], efy = -0.5f * it.mass + it.force[1]; // :74
+    float cfx = 0.0f, cfy = 0.0f;
+    const float ang_force = it.angForce;
+#pragma unroll 1
+    for (int i = 0; i < 4; i++) {
+      const float side = i < 2 ? it.size[1] : it.size[0]; // :83
+      const int nsp = (int)fmaxf(2.0f, side / h);         // :86
+      float ox, oy;
+      rot2(SFX[i], SFY[i], it.rotation, ox, oy);
+      for (int k = 0; k < nsp; k++) {
+        const float tpar = 1.0f - (float)k * 2.0f / (float)(nsp - 1);
+        const float sx = SFX[i] + fabsf(SFY[i]) * tpar, sy = SFY[i] + fabsf(SFX[i]) * tpar; // :89-91
+        const float lx = sx * it.size[0] * 0.5f, ly = sy * it.size[1] * 0.5f;
+        float tx, ty, rx, ry, nx, ny;
+        rot2(lx, ly, it.rotation, tx, ty);
+        tx += it.pos[0];
+        ty += it.pos[1];
+        const float gx = tx / h, gy = ty / h;
+        rot2(lx, ly, it.rotation + 0.5f * 3.141f, rx, ry);
+        const float dvx = bilinear_sample(vx, gx - 0.5f, gy) - (it.vel[0] + 3.141f * rx * it.angVel);
+        const float dvy = bilinear_sample(vy, gx, gy - 0.5f) - (it.vel[1] + 3.141f * ry * it.angVel);
+        const float sl = sqrtf(sx * sx + sy * sy);
+        rot2(sx / sl, sy / sl, it.rotation, nx, ny); // rotate(normalize(sp), rotation)
+        const float pr = fminf(0.0f, dvx * ox + dvy * oy);
+        const float fx = nx * pr, fy = ny * pr;
+        cfx += fx * 400000.0f * (0.003f + side) * side / (float)nsp; // :110-111
+        cfy += fy * 400000.0f * (0.003f + side) * side / (float)nsp;
+        if (gx < 1.0f || gx > (float)vx.w - 2.0f || gy < 1.0f || gy > (float)vx.h - 2.0f) continue; // :113-115
+        const float ddx = fx * (0.003f + side) * side / (float)nsp * sub * 18000000.0f;
+        const float ddy = fy * (0.003f + side) * side / (float)nsp * sub * 18000000.0f;
+        bilinear_scatter(ax, gx - 0.5f, gy, -ddx);
+        bilinear_scatter(ay, gx, gy - 0.5f, -ddy);
+      }
+    }
+    {
+      const float gx = it.pos[0] / h, gy = it.pos[1] / h; // :125-126
+      const float kk = 1000.0f * (it.size[0] + it.size[1]);
+      cfx += kk * (bilinear_sample(vx, gx - 0.5f, gy) - it.vel[0]);
+      cfy += kk * (bilinear_sample(vy, gx, gy - 0.5f) - it.vel[1]);
+    }
+    it.vel[0] += sub * (efx + cfx) / it.mass; // :129
+    it.vel[1] += sub * (efy + cfy) / it.mass;
+    const float ang_mass = it.size[0] * it.size[1] * it.mass * (1.0f / 12.0f);
+    it.angVel += sub * ang_force / ang_mass;
+    it.angVel = (float)((double)it.angVel * 0.98); // :135
+  }
+  it.angForce = 0.0f;
+  it.force[0] = 0.0f;
+  it.force[1] = 0.0f;
+  items[q] = it;
+}
+
 // ---------------------------------------------------------------------------
 // terrain edits on the resident simulation-resolution mask
 // ---------------------------------------------------------------------------
@@ -691,6 +812,21 @@ int ubgl_items_advect_simple(ubgl_items_t *it, ubgl_sim_t *sim, float game_dt) {
                                                                game_dt, S.field(F_FLAG), S.field(F_VX),
                                                                S.field(F_VY), S.field(F_P), S.field(F_VX_ACCUM),
                                                                S.field(F_VY_ACCUM), S.pwidth, S.h));
+  UBGL_CATCH
+}
+
+int ubgl_items_advect(ubgl_items_t *it, ubgl_sim_t *sim, float game_dt) {
+  UBGL_TRY
+  NEED(it, "items");
+  SIM(sim);
+  UBGL_REQUIRE(S.device == it->device, "items and simulation live on different devices");
+  const int n = it->n;
+  if (n == 0) return UBGL_OK;
+  UBGL_LAUNCH(&S.lc, K_ITEMS, 2, S.stream,
+              k_items_advect_rigid<<<ceil_div(n, 64), 64, 0, S.stream>>>(it->items, n, game_dt, S.field(F_FLAG),
+                                                                       S.field(F_VX), S.field(F_VY),
+                                                                       S.field(F_VX_ACCUM), S.field(F_VY_ACCUM),
+                                                                       S.pwidth, S.h));
   UBGL_CATCH
 }
 
