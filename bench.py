@@ -306,6 +306,12 @@ def run_single_gpu(args, name):
         cpu = {"value": r["value"], "unit": "MLUP/s", "cores": r["cores"], "kind": r["kind"],
                "sample": f"{sample}: {r['warmup']} warm-up + {r['steps']} timed Simulation::step "
                          f"({r['ms_per_step']:.0f} ms/step), OMP threads {r['cores']} of {r['nproc']}, rbgs {r['rbgs_path']}"}
+        # the game's own thread policy, sim_loop.cpp:19: max(1, nproc/2 - 1)
+        tg = max(1, r["nproc"] // 2 - 1)
+        if tg != r["cores"]:
+            r2 = cpu_reference_run(sample, 1 if sample != "game" else 20, 1, threads=tg)
+            cpu["game_thread_policy"] = {"value": r2["value"], "cores": tg, "ms_per_step": r2["ms_per_step"],
+                                         "rbgs_path": r2["rbgs_path"]}
 
     bpc = bytes_per_cell()
     step_gbs = N * bpc / (ms_step * 1e-3) / 1e9
