@@ -40,6 +40,12 @@ B_VCYCLE = 186.7                 # algorithmic B/level-0-cell per V-cycle, whole
 PWIDTH, MU = 0.8, 0.001
 
 
+def pcie_d2h_bytes(outs):
+    """Bytes ubgl_sim_step_host moves device -> host: fields of 16 MB and more send vx / vy once and
+    fill the *_current mirrors by host copies; smaller ones are simply downloaded too."""
+    return sum(a.nbytes for k_, a in outs.items() if not (k_.endswith("_current") and a.nbytes >= (16 << 20)))
+
+
 def bytes_per_cell(k=VCYCLES):
     return B_NONMG + B_VCYCLE * k
 
@@ -287,7 +293,7 @@ def run_single_gpu(args, name):
     outs = dict(vx=pin((H, W - 1)), vy=pin((H - 1, W)), p=pin((H, W)),
                 vx_current=pin((H, W - 1)), vy_current=pin((H - 1, W)))
     h2d = ax.nbytes + ay.nbytes
-    d2h = sum(a.nbytes for k_, a in outs.items() if not k_.endswith("_current"))  # *_current: host copies
+    d2h = pcie_d2h_bytes(outs)
     KE = max(2, min(K, 8))
     sim.step_host(dt, vx_accum=ax, vy_accum=ay, **outs)
     t_calls = []
@@ -335,9 +341,10 @@ def run_single_gpu(args, name):
         "cpu_baseline": cpu,
         "e2e": {"value": e2e, "unit": "MLUP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": t_e2e * 1e3, "calls": KE, "ms_min": min(t_calls) * 1e3, "ms_max": max(t_calls) * 1e3,
-                "api": "ubgl_sim_step_host (pinned host mirrors: accumulators in; vx, vy, p out over PCIe, "
-                       "vx_current, vy_current filled from the vx, vy mirrors by host threads like "
-                       "saveCurrentVelocityFields' memcpy)"},
+                "api": "ubgl_sim_step_host (pinned host mirrors: accumulators in; vx, vy, p out over PCIe; "
+                       + ("vx_current, vy_current filled from the vx, vy mirrors by host threads like "
+                          "saveCurrentVelocityFields' memcpy)" if N * 4 >= (16 << 20) else
+                          "vx_current, vy_current downloaded too: fields under 16 MB)")},
         "gpu_launches": int(launches),
         "clocks": clk.summary(),
         "kernels_ms_per_step": [{"kernel": k, "level": l, "launches": n, "ms": round(ms, 4)} for ms, n, k, l in kern[:12]],
@@ -459,7 +466,7 @@ def run_explosion(args, name):
         I.get(rec)
         t_calls.append(time.perf_counter() - t0)
     t_e2e = sum(t_calls) / KE
-    d2h = sum(a.nbytes for k_, a in outs.items() if not k_.endswith("_current")) + rec.nbytes
+    d2h = pcie_d2h_bytes(outs) + rec.nbytes
     h2d = CRATERS * 12 + len(sim.sinks()) * 12
 
     cpu = None

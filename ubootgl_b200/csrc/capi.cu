@@ -282,21 +282,18 @@ int ubgl_sim_step_host(ubgl_sim_t *sim, float dt, const ubgl_host_mirrors *m) {
     struct { int id, cur_id; float *dst, *cur; } vel[] = {{F_VX, F_VX_CURRENT, m->vx, m->vx_current},
                                                           {F_VY, F_VY_CURRENT, m->vy, m->vy_current}};
     for (auto &o : vel) {
-      if (o.dst && o.cur) {
+      const bool big = o.dst && (size_t)S.field(o.id).h * S.field(o.id).w * sizeof(float) >= (size_t)(16 << 20);
+      if (o.dst && o.cur && big) {
+        // large field: one PCIe crossing, the *_current mirror is a multi-threaded host copy of
+        // the bands as they land (for a few MB a second small DMA beats a single-core memcpy)
         Grid g = S.field(o.id);
         const size_t row = sizeof(float) * (size_t)g.w;
-        const bool big = (size_t)g.h * row >= (size_t)(16 << 20);
-        const int nb = big ? std::min(32, g.h) : 1;
-        const float *pk = big ? S.packed(g) : nullptr; // unpadded rows: contiguous DMA
+        const int nb = std::min(32, g.h);
+        const float *pk = S.packed(g); // unpadded rows: contiguous DMA
         for (int b = 0; b < nb; b++) {
           const int y0 = (int)((long long)g.h * b / nb), y1 = (int)((long long)g.h * (b + 1) / nb);
-          if (pk)
-            UBGL_CUDA(cudaMemcpyAsync(o.dst + (size_t)y0 * g.w, pk + (size_t)y0 * g.w, row * (size_t)(y1 - y0),
-                                      cudaMemcpyDeviceToHost, S.stream));
-          else
-            UBGL_CUDA(cudaMemcpy2DAsync(o.dst + (size_t)y0 * g.w, row, g.d + (size_t)y0 * g.pitch,
-                                        sizeof(float) * g.pitch, row, y1 - y0, cudaMemcpyDeviceToHost,
-                                        S.stream));
+          UBGL_CUDA(cudaMemcpyAsync(o.dst + (size_t)y0 * g.w, pk + (size_t)y0 * g.w, row * (size_t)(y1 - y0),
+                                    cudaMemcpyDeviceToHost, S.stream));
           HostBand hb;
           UBGL_CUDA(cudaEventCreateWithFlags(&hb.ready, cudaEventDisableTiming));
           bands.push_back(hb);
@@ -306,12 +303,15 @@ int ubgl_sim_step_host(ubgl_sim_t *sim, float dt, const ubgl_host_mirrors *m) {
           k.dst = o.cur + (size_t)y0 * g.w;
           k.bytes = row * (size_t)(y1 - y0);
         }
-      } else if (o.dst) {
-        Grid g = S.field(o.id);
-        download_grid(g, o.dst, g.w, g.h, S.stream);
-      } else if (o.cur) {
-        Grid g = S.field(o.cur_id);
-        download_grid(g, o.cur, g.w, g.h, S.stream);
+      } else {
+        if (o.dst) {
+          Grid g = S.field(o.id);
+          download_grid(g, o.dst, g.w, g.h, S.stream);
+        }
+        if (o.cur) {
+          Grid g = S.field(o.cur_id);
+          download_grid(g, o.cur, g.w, g.h, S.stream);
+        }
       }
     }
     if (m->p) {
