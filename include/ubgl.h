@@ -73,9 +73,10 @@ enum ubgl_option {
                             passes with register-resident runs (k_mg_run), 1: the shared-memory
                             tile schedule (k_mg_tile; the choice between 1 and 2 is process wide);
                             0: one plain kernel per reference stage.  Same results in all three. */
-  UBGL_OPT_GRAPH = 2,    /* reserved (accepted, no effect): the step is queued asynchronously on the
-                            handle's stream and is GPU-bound at every measured size, so it is
-                            not captured into a CUDA graph */
+  UBGL_OPT_GRAPH = 2,    /* 1 (default): grids up to 4 M cells replay CUDA graphs of the fused step's two launch
+                            sequences (prestep..divergence, V-cycles..save), captured from the handle's stream
+                            once a buffer-role state (and dt) has repeated; larger grids are GPU-bound and are
+                            always launched directly.  0: never use graphs.  Same results either way. */
   UBGL_OPT_TIMING = 3    /* 1: record per-stage CUDA events (ubgl_sim_stage_ms) */
 };
 

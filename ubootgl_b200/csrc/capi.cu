@@ -92,6 +92,7 @@ int ubgl_sim_set_option(ubgl_sim_t *sim, int option, int value) {
   case UBGL_OPT_TIMING: S.timing = value != 0; break;
   default: throw ArgError{"unknown option"};
   }
+  S.drop_graphs(); // captured launch sequences depend on every option
   UBGL_CATCH
 }
 
@@ -101,6 +102,7 @@ int ubgl_sim_set_bc(ubgl_sim_t *sim, int west, int east, int north, int south) {
   auto ok = [](int b) { return b >= 0 && b <= 3; };
   UBGL_REQUIRE(ok(west) && ok(east) && ok(north) && ok(south), "bad BC id");
   S.bcW = west; S.bcE = east; S.bcN = north; S.bcS = south;
+  S.drop_graphs();
   UBGL_CATCH
 }
 

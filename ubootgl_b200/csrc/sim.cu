@@ -534,6 +534,7 @@ DeviceSim::~DeviceSim() {
   }
   free_grid(vx_accum); free_grid(vy_accum);
   free_grid(p); free_grid(f); free_grid(flag); free_grid(r);
+  drop_graphs();
   if (d_sinks) cudaFree(d_sinks);
   if (d_fnorm) cudaFree(d_fnorm);
   if (h_stage) cudaFreeHost(h_stage);
@@ -585,6 +586,7 @@ void DeviceSim::upload(int id, const float *host) {
 // not, exactly as in the reference (simulation.hpp:85 vs ubootgl_app.cpp:111-112).
 void DeviceSim::flag_changed(bool pyramid, bool binary_edit) {
   if (pyramid) mg->update_fields(flag);
+  drop_graphs(); // the fused / plain decision and the mask build are outside the graphs
   const bool keep = binary_edit && mg->mask0_is_binary(); // the edit wrote only 0.0 / 1.0
   mg->invalidate_mask0();
   mg->prepare_mask0(flag, keep);
@@ -832,6 +834,68 @@ void DeviceSim::stage(int st, float dt_) {
   }
 }
 
+void DeviceSim::drop_graphs() {
+  for (auto *c : {&graphs_a, &graphs_b}) {
+    for (auto &kv : *c)
+      if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    c->clear();
+  }
+}
+
+// Runs one part of the fused step: replays its graph when one exists for the current buffer
+// roles (and dt), captures one the third time the key is seen, otherwise just enqueues.
+template <class F>
+void DeviceSim::run_part(std::map<int, StepGraph> &cache, bool dt_dependent, bool graphable, F &&enqueue) {
+  if (!graphable) {
+    enqueue();
+    return;
+  }
+  const int key = ixf | (ixb << 2) | (ixc << 4) | (iyf << 6) | (iyb << 8) | (iyc << 10);
+  StepGraph &g = cache[key];
+  if (g.exec && (!dt_dependent || g.dt == dt)) {
+    UBGL_CUDA(cudaGraphLaunch(g.exec, stream));
+    lc.n += g.launches;
+    ixf = g.post[0]; ixb = g.post[1]; ixc = g.post[2]; iyf = g.post[3]; iyb = g.post[4]; iyc = g.post[5];
+    return;
+  }
+  if (dt_dependent && g.dt != dt) { // a new time step: wait until it repeats before capturing
+    g.dt = dt;
+    g.seen = 0;
+  }
+  if (++g.seen < 3) {
+    enqueue();
+    return;
+  }
+  if (g.exec) {
+    cudaGraphExecDestroy(g.exec);
+    g.exec = nullptr;
+  }
+  const long long n0 = lc.n;
+  cudaGraph_t graph = nullptr;
+  UBGL_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+  bool ok = true;
+  try {
+    enqueue();
+  } catch (...) {
+    ok = false;
+  }
+  cudaError_t e = cudaStreamEndCapture(stream, &graph);
+  if (ok && e == cudaSuccess && graph && cudaGraphInstantiate(&g.exec, graph, 0) == cudaSuccess) {
+    g.launches = lc.n - n0;
+    g.dt = dt;
+    g.post[0] = ixf; g.post[1] = ixb; g.post[2] = ixc; g.post[3] = iyf; g.post[4] = iyb; g.post[5] = iyc;
+    cudaGraphDestroy(graph);
+    UBGL_CUDA(cudaGraphLaunch(g.exec, stream)); // the captured work has not run yet
+    return;
+  }
+  // capture failed: nothing was enqueued; give up on graphs for this handle and run directly
+  if (graph) cudaGraphDestroy(graph);
+  cudaGetLastError();
+  g.exec = nullptr;
+  use_graph = false;
+  throw ArgError{"internal: CUDA graph capture of the step failed (UBGL_OPT_GRAPH is now off for this handle)"};
+}
+
 // Simulation::step (simulation.cpp:356-374)
 void DeviceSim::step(float dt_) {
   dt = dt_;
@@ -843,20 +907,30 @@ void DeviceSim::step(float dt_) {
   auto mark = [&]() { if (timing) UBGL_CUDA(cudaEventRecord(ev[k++], stream)); };
   mark();
   if (fz) {
+    // small grids replay CUDA graphs of the two launch sequences (see sim.cuh)
+    const bool graphable = use_graph && !timing && !lc.prof && tol <= 0.0f && (size_t)W * H <= ((size_t)1 << 22);
     mark(); // applyAccumulatedVelocity is part of the fused diffuse pass
-    fused_prestep();
-    fused_borders(false, false);
-    mark();
-    advect();
-    mark();
-    fused_borders(false, false);
-    mark();
-    fused_divergence();
+    run_part(graphs_a, true, graphable, [&]() {
+      fused_prestep();
+      fused_borders(false, false);
+      mark();
+      advect();
+      mark();
+      fused_borders(false, false);
+      mark();
+      fused_divergence();
+    });
     project_sinks();
-    solve_cycles();
-    fused_gradient_save(); // reads only interior p: independent of setPBC
-    mark();
-    fused_borders(true, true); // setPBC + setVBCs, also into vx_current / vy_current
+    run_part(graphs_b, false, graphable, [&]() {
+      solve_cycles();
+      fused_gradient_save(); // reads only interior p: independent of setPBC
+      mark();
+      fused_borders(true, true); // setPBC + setVBCs, also into vx_current / vy_current
+    });
+    if (graphable) { // what solve_cycles() records on the host
+      cycles_done = vcycles;
+      res_hist.clear();
+    }
     mark();
     mark();
   } else {

@@ -3,6 +3,7 @@
 #pragma once
 #include "common.cuh"
 #include "mg.cuh"
+#include <map>
 #include <memory>
 #include <vector>
 
@@ -126,6 +127,19 @@ public:
   // layout on the device, then ONE contiguous DMA (a pitched 2-D copy of 8191-float rows
   // runs at 40 GB/s on this box, a contiguous one at 45 GB/s; tools/pcie_probe.py)
   float *packed(const Grid &g); // stream-ordered; the buffer is reused by the next call
+  // CUDA graphs of the fused step for small grids (UBGL_OPT_GRAPH, default on): below ~4 M
+  // cells a step is ~26 dependent launches of ~10 us each and the gaps between them count.
+  // Part A = prestep .. divergence (depends on dt and on the buffer-role rotation), part B =
+  // V-cycles .. save (rotation only); the sink stamps between them stay ordinary launches.
+  // A graph is captured from the stream the third time its key is seen and replayed after.
+  struct StepGraph {
+    cudaGraphExec_t exec = nullptr;
+    long long launches = 0;
+    float dt = 0.0f;
+    int seen = 0;
+    int post[6] = {0, 0, 0, 0, 0, 0}; // buffer roles after the part
+  };
+  void drop_graphs();
   float *d_pack = nullptr;
   size_t cap_pack = 0;
 
@@ -145,6 +159,8 @@ private:
   void fused_borders(bool with_p, bool with_current);
   void fused_divergence();
   void fused_gradient_save();
+  std::map<int, StepGraph> graphs_a, graphs_b; // key: buffer roles before the part
+  template <class F> void run_part(std::map<int, StepGraph> &cache, bool dt_dependent, bool graphable, F &&enqueue);
   float *d_sinks = nullptr; // ix, iy, z triples stamped into f
   int cap_sinks = 0;
   bool r_alloc = false;
