@@ -255,6 +255,8 @@ def run_single_gpu(args, name):
     W, H, flag, vx, vy, dt = make_inputs(name)
     N = W * H
     sim = u.Simulation(flag, PWIDTH, MU, device=dev)
+    if os.environ.get("UBGL_BENCH_GRAPH") == "0":  # A/B of UBGL_OPT_GRAPH (small grids only)
+        sim.set_option(capi.OPT_GRAPH, 0)
     sim.set(capi.VX, vx)
     sim.set(capi.VY, vy)
     stream = torch.cuda.ExternalStream(sim.stream(), device=dev)
