@@ -498,8 +498,16 @@ def run_explosion(args, name):
     h2d = CRATERS * 12 + len(sim.sinks()) * 12
 
     cpu = None
-    if not args.no_cpu_baseline:
-        cpu = explosion_cpu_baseline(name)
+    if not args.no_cpu_baseline:  # in a child process, like cpu_reference_isolated
+        try:
+            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-worker-explosion", name],
+                                 capture_output=True, text=True, timeout=900)
+            cpu = next((json.loads(l) for l in reversed(out.stdout.strip().splitlines()) if l.startswith("{")), None)
+        except Exception:
+            cpu = None
+        if cpu is None:
+            cpu = {"value": None, "unit": "MLUP/s", "cores": None, "kind": "reference",
+                   "sample": f"{name}: the reference process died (out-of-bounds read in its pipelined rbgs path)"}
     bpc = bytes_per_cell()
     step_only = sum(ms for ms, n, k, l in fluid)
     line = {
@@ -633,6 +641,9 @@ def main():
         t = int(sys.argv[5])
         print(json.dumps(cpu_reference_run(sys.argv[2], int(sys.argv[3]), int(sys.argv[4]), threads=t or None)),
               flush=True)
+        return
+    if len(sys.argv) >= 3 and sys.argv[1] == "--cpu-worker-explosion":
+        print(json.dumps(explosion_cpu_baseline(sys.argv[2])), flush=True)
         return
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
