@@ -1,0 +1,32 @@
+"""CPU: bench.py's reference arm (`--impl reference`) and the isolated CPU-baseline runner print the
+contract's JSON line without a GPU (the driver runs this arm on the GPU box's host cores)."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_prints_the_contract_line():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload",
+                          "channel256", "--steps", "2", "--warmup", "1"], capture_output=True, text=True,
+                         timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "fluid_step_throughput" and line["unit"] == "MLUP/s"
+    assert line["value"] > 0 and line["higher_is_better"] is True and line["gpu_launches"] == 0
+    assert line["config"]["workload"] == "channel256" and line["config"]["grid"] == [256, 256]
+    cb, e2e = line["cpu_baseline"], line["e2e"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == line["value"]
+    assert e2e["value"] == line["value"] and e2e["h2d_bytes_per_step"] == 0 and e2e["d2h_bytes_per_step"] == 0
+
+
+def test_isolated_cpu_runner_survives_and_reports():
+    sys.path.insert(0, ROOT)
+    import bench
+    r = bench.cpu_reference_isolated("channel256", 1, 1, threads=1)
+    assert r is not None and r["cores"] == 1 and r["W"] == 256 and r["ms_per_step"] > 0
+    # a child that dies (unknown workload -> SystemExit) is reported as None, not as an exception
+    assert bench.cpu_reference_isolated("no-such-workload", 1, 1) is None
+    assert bench.pcie_d2h_bytes({"vx": __import__("numpy").zeros(4, "f4"), "vx_current": __import__("numpy").zeros(4, "f4")}) == 32
