@@ -30,3 +30,12 @@ def test_isolated_cpu_runner_survives_and_reports():
     # a child that dies (unknown workload -> SystemExit) is reported as None, not as an exception
     assert bench.cpu_reference_isolated("no-such-workload", 1, 1) is None
     assert bench.pcie_d2h_bytes({"vx": __import__("numpy").zeros(4, "f4"), "vx_current": __import__("numpy").zeros(4, "f4")}) == 32
+
+
+def test_reference_arm_non_zero_ranks_exit_quietly():
+    """Under torchrun (N > 1) only rank 0 runs the reference; the others exit 0 without output."""
+    env = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
+                          "--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=120, cwd=ROOT,
+                         env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ""
