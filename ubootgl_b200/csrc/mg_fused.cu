@@ -1,10 +1,23 @@
-// mg_fused.cu -- temporally blocked multigrid tile kernels (sm_100a).
+// mg_fused.cu -- temporally blocked multigrid kernels (sm_100a).
 //
-// One CTA stages a (128 x LH) window of p, f and the 1-byte stencil mask in
-// shared memory, runs S complete red-black Gauss-Seidel sweeps on it (the valid
-// region shrinks by one cell per half-sweep, so the window carries a halo of
-// 2S (+2) cells) and fuses the neighbouring multigrid operators into the same
-// pass:
+// Three schedules of the same passes, bit-identical to each other and to the plain
+// one-kernel-per-operator path of mg.cu (tests/test_gpu_fused.py):
+//   k_mg_run  (default)  PRE / POST with the thread's cells held in REGISTERS: a thread owns
+//                        4 window rows x 8 cells, keeps f*h*h and the smoothing weights in
+//                        registers over all six half-sweeps, reads the other colour through
+//                        a rolling set of six 128-bit loads and gets its lane-edge neighbour
+//                        by shuffle; POST applies prolongation + correction in registers
+//                        while staging; the next window is prefetched into L2.
+//   k_mg_tail (default)  levels below ~8K cells down to the coarsest: the whole bottom of
+//                        the V-cycle in one shared-memory resident single-CTA launch.
+//   k_mg_tile            the first schedule (window of p, f, mask in shared memory, 4 cells
+//                        per thread and sweep); still used for the 5-sweep coarsest pass
+//                        when the tail is off, selectable with UBGL_OPT_FUSED = 1 as the
+//                        cross-check.
+//
+// A pass stages a (128 x LH) window of a level (the valid region shrinks by one cell per
+// half-sweep, so the window carries a halo of 2S (+2) cells) and fuses the neighbouring
+// multigrid operators:
 //   MODE_PRE    : S x (rbgs [+ zero-gradient BC]) -> residual -> full-weighting
 //                 restriction.  HBM traffic per cell: read p, f, mask (9 B),
 //                 write p (4 B) + rc (1 B); the residual field is never stored.
@@ -13,11 +26,9 @@
 // p is ping-ponged between two buffers (tiles read their neighbours' cells as
 // halo, so an in-place update would race).
 //
-// The kernels are instruction-issue bound, not DRAM bound (ncu, profiles/), so
-// the inner loops are written for instruction count:
+// Common conventions:
 //  * red and black cells live in separate shared-memory planes (plane =
-//    (x+y)&1, column x>>1); a thread updates 4 consecutive same-colour cells
-//    with 128-bit LDS/STS;
+//    (x+y)&1, column x>>1), so a half-sweep touches consecutive words;
 //  * solid cells are stored as 0 in the window (their value is never used by
 //    the reference either: every read is multiplied by the cell's flag,
 //    pressure_solver.cpp:13-17,101-108), so the 5-point sum needs no flag
@@ -26,9 +37,6 @@
 //  * border cells (never smoothed) keep flag*value in the window for their
 //    neighbours and are re-materialised from p_in / the zero-gradient copy at
 //    write-back.
-// Every per-cell rounding sequence equals the plain one-kernel-per-operator
-// path in mg.cu for binary flags: the fused result is bit-identical to the
-// plain one up to the sign of zeros (tests/test_gpu_fused.py).
 //
 // Reference semantics: pressure_solver.cpp:10-24 (smoothingKernel), :35-72
 // (canonical red-black order), :91-116 (residual), :118-132 (restrict),
