@@ -101,6 +101,10 @@ int ubgl_sim_set_bc(ubgl_sim_t *sim, int west, int east, int north, int south);
 /* whole-field H->D / D->H of one public member; host layout as the reference */
 int ubgl_sim_upload(ubgl_sim_t *sim, int field, const float *host);
 int ubgl_sim_download(ubgl_sim_t *sim, int field, float *host);
+/* field += host grid.  For vx_accum / vy_accum, which both sides of this boundary add into:
+ * the items kernels on the device (atomicAdd) and a host caller running the reference's own
+ * advect_floating_items.cpp:118-120 on its mirrors (`sim.vx_accum(...) += ...`). */
+int ubgl_sim_upload_add(ubgl_sim_t *sim, int field, const float *host);
 /* memcpy(sim.flag.data(), ...) + sim.mg.updateFields(sim.flag)
  * (ubootgl_app.cpp:111-112, pressure_solver.hpp:34-57) */
 int ubgl_sim_update_flag(ubgl_sim_t *sim, const float *flag);

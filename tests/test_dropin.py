@@ -1,0 +1,95 @@
+"""Boundary completeness of the C++ drop-in (ubootgl_b200/host): the reference's own caller
+files compile UNMODIFIED against the drop-in headers, and Simulation::advectFloatingItems /
+advectFloatingItemsSimple (simulation.hpp:116-117, called by ubootgl_app.cpp:129-130) driven
+through an entt registry reproduce the unmodified reference (oracle/_ref).
+
+tests/dropin/Makefile assembles a stand-in of the reference tree from symlinks (needs
+/root/reference, i.e. the build container); the GPU box runs the prebuilt
+tests/dropin/_build/itemsdemo that travelled with the snapshot."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests import cases, next_cases
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DROPIN = os.path.join(ROOT, "tests", "dropin")
+BUILD = os.path.join(DROPIN, "_build")
+HAVE_REF_TREE = os.path.exists("/root/reference/simulation.hpp")
+
+
+@pytest.mark.skipif(not HAVE_REF_TREE, reason="needs the reference tree (build container only)")
+def test_reference_callers_compile_against_the_dropin_headers():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "ubootgl_b200")])
+    subprocess.check_call(["make", "-s", "-C", DROPIN])
+    # (1) the reference's CPU item path and the swarm AI, unmodified, against OUR simulation.hpp /
+    #     db2dgrid.hpp / pressure_solver.hpp (they are symlinks into /root/reference and host/)
+    tree = os.path.join(BUILD, "tree")
+    assert os.path.realpath(os.path.join(tree, "advect_floating_items.cpp")) == "/root/reference/advect_floating_items.cpp"
+    assert os.path.realpath(os.path.join(tree, "simulation.hpp")) == os.path.join(ROOT, "ubootgl_b200", "host", "simulation.hpp")
+    nm = lambda o: subprocess.run(["nm", "-C", os.path.join(BUILD, o)], capture_output=True, text=True, check=True).stdout
+    syms = nm("ref_advect_floating_items.o")
+    for name in ("T Simulation::advectFloatingItems(", "T Simulation::advectFloatingItemsSimple("):
+        assert name in syms, name
+    # it reaches the drop-in's members: flag samplers and the accumulator mutex are external references
+    assert "U Simulation::psampleFlagLinear(" in syms
+    assert "classicSwarmAI" in nm("ref_swarm.o")
+    # (2) the drop-in's own (GPU) definitions link into a program that includes components.hpp + entt
+    assert os.access(os.path.join(BUILD, "itemsdemo"), os.X_OK)
+
+
+def _write_case(prefix, W, H, items, kind, frames, game_dt, step_dt, flag, vx, vy, p):
+    with open(prefix + ".meta", "w") as fp:
+        fp.write(f"{W} {H} {len(items)} {kind} {frames} {game_dt!r} {step_dt!r}\n")
+    for name, a in (("flag", flag), ("vx", vx), ("vy", vy), ("p", p)):
+        np.ascontiguousarray(a, np.float32).tofile(prefix + "." + name)
+    items.tofile(prefix + ".items")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,W,H,n,game_dt", [(1, 130, 97, 500, 0.004), (1, 258, 131, 3000, 0.01),
+                                                 (0, 130, 97, 300, 0.004), (0, 258, 131, 800, 0.01)])
+def test_registry_item_advection_matches_the_unmodified_reference(ubgl, port, ref, tmp_path, kind, W, H, n, game_dt):
+    from oracle import bind as ob
+    from tests.test_oracle_next import close_fraction
+    exe = os.path.join(BUILD, "itemsdemo")
+    if not os.access(exe, os.X_OK):
+        if HAVE_REF_TREE:
+            subprocess.check_call(["make", "-s", "-C", DROPIN])
+        else:
+            pytest.fail("tests/dropin/_build/itemsdemo was not shipped with the snapshot (run build() first)")
+    ref.canonical_threads(H)
+    flag, O = next_cases.developed_flow(port, W, H, seed=W + H + kind)
+    vx, vy, p = O.get(ob.VX), O.get(ob.VY), O.get(ob.P)
+    items = (next_cases.make_bodies(n, W, H, seed=5, flag=flag) if kind == 0
+             else next_cases.make_items(n, W, H, seed=3, flag=flag, cluster=0.2))
+    frames, step_dt = 2, 0.001
+    pin, pout = str(tmp_path / "in"), str(tmp_path / "out")
+    _write_case(pin, W, H, items, kind, frames, game_dt, step_dt, flag, vx, vy, p)
+    subprocess.run([exe, pin, pout], check=True, timeout=300)
+
+    R = ref.Sim(flag, 0.8, 0.001)
+    R.set(ob.VX, vx); R.set(ob.VY, vy); R.set(ob.P, p)
+    o = items.copy()
+    for _ in range(frames):
+        (ref.items_advect if kind == 0 else ref.items_advect_simple)(R, o, game_dt)
+    g = np.fromfile(pout + ".items", ob.ITEM_DTYPE)
+    ax = np.fromfile(pout + ".ax", np.float32).reshape(H, W - 1)
+    ay = np.fromfile(pout + ".ay", np.float32).reshape(H - 1, W)
+    rax, ray = R.get(ob.VX_ACCUM), R.get(ob.VY_ACCUM)
+    assert np.abs(rax).sum() > 0
+    if kind == 1:
+        for name in ("pos", "vel", "rotation", "angVel", "size", "mass"):
+            assert cases.rel_l2(g[name], o[name]) <= 2e-5, (name, cases.rel_l2(g[name], o[name]))
+        assert cases.rel_l2(ax, rax) <= 2e-5 and cases.rel_l2(ay, ray) <= 2e-5
+        tol = 5e-5
+    else:
+        assert close_fraction(g, o) >= 0.99
+        assert cases.rel_l2(ax, rax) <= 1e-3 and cases.rel_l2(ay, ray) <= 1e-3
+        tol = 1e-3
+    R.step(step_dt)
+    for name, fld, shape in (("vx", ob.VX, (H, W - 1)), ("vy", ob.VY, (H - 1, W)), ("p", ob.P, (H, W))):
+        got = np.fromfile(pout + "." + name, np.float32).reshape(shape)
+        assert cases.rel_l2(got, R.get(fld)) <= tol, (name, cases.rel_l2(got, R.get(fld)))

@@ -239,3 +239,31 @@ def test_graph_replay_equals_direct_launches(ubgl):
     for a, b in zip(*outs):
         assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
     assert launches[0] == launches[1]  # replayed launches are counted like direct ones
+
+
+def test_graph_not_replayed_after_dt_change(ubgl):
+    """Round-1 bug (ADVICE): part A's graph was captured with dt = A baked into its kernel arguments;
+    after step(dt = B) the same role key (period 3) recurred with dt = B and the stale exec was
+    replayed.  Here no flag edit drops the graphs between the two dt phases and every role key
+    recurs >= 4 times after each change: graph mode must equal direct launches bit for bit."""
+    from ubootgl_b200 import capi
+    W, H = 258, 131
+    c = cases.sim_case(W, H, seed=23)
+    dts = [0.001] * 12 + [0.0006] * 12 + [0.001] * 12
+    outs, launches = [], []
+    for graph in (1, 0):
+        s = ubgl.Simulation(c["flag"])
+        s.set_option(capi.OPT_GRAPH, graph)
+        s.set(capi.VX, c["vx"]); s.set(capi.VY, c["vy"])
+        s.set(capi.VX_ACCUM, c["vx_accum"]); s.set(capi.VY_ACCUM, c["vy_accum"])
+        snap = []
+        for k, dt in enumerate(dts):
+            s.step(dt)
+            if k in (11, 14, 17, 23, 26, 35):
+                snap.append([s.get(f) for f in (capi.VX, capi.VY, capi.P, capi.F)])
+        outs.append(snap)
+        launches.append(s.launch_count())
+    for sa, sb in zip(*outs):
+        for a, b in zip(sa, sb):
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    assert launches[0] == launches[1]

@@ -78,7 +78,11 @@ def test_bootstrap_two_ranks_gloo(tmp_path):
     """world_size 2 over gloo on CPU: IPC-blob all-gather, row gather, reductions."""
     script = tmp_path / "worker.py"
     script.write_text(_GLOO_WORKER.format(root=ROOT))
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29517", WORLD_SIZE="2")
+    import socket
+    with socket.socket() as so:  # a free port: a fixed one collides with a lingering earlier run
+        so.bind(("127.0.0.1", 0))
+        port = so.getsockname()[1]
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), WORLD_SIZE="2")
     procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r), LOCAL_RANK=str(r)),
                               stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
     outs = [p.communicate(timeout=240)[0] for p in procs]

@@ -52,6 +52,7 @@ def _load():
         "ubgl_sim_set_option": (i, [v, i, i]),
         "ubgl_sim_set_bc": (i, [v, i, i, i, i]),
         "ubgl_sim_upload": (i, [v, i, FP]),
+        "ubgl_sim_upload_add": (i, [v, i, FP]),
         "ubgl_sim_download": (i, [v, i, FP]),
         "ubgl_sim_update_flag": (i, [v, FP]),
         "ubgl_sim_mg_levels": (i, [v]),
@@ -202,6 +203,13 @@ class Simulation:
         if a.shape != field_shape(field, self.width, self.height):
             raise UbglError(f"field {field}: shape {a.shape} does not match the grid")
         _ck(lib.ubgl_sim_upload(self._h, field, _fp(a)))
+
+    def add(self, field, a):
+        """field += a (host contributions to a device-resident accumulator)."""
+        a = _f32(a)
+        if a.shape != field_shape(field, self.width, self.height):
+            raise UbglError(f"field {field}: shape {a.shape} does not match the grid")
+        _ck(lib.ubgl_sim_upload_add(self._h, field, _fp(a)))
 
     def update_flag(self, flag):
         """memcpy into sim.flag + mg.updateFields (ubootgl_app.cpp:111-112)."""

@@ -114,6 +114,14 @@ int ubgl_sim_upload(ubgl_sim_t *sim, int field, const float *host) {
   UBGL_CATCH
 }
 
+int ubgl_sim_upload_add(ubgl_sim_t *sim, int field, const float *host) {
+  UBGL_TRY
+  SIM(sim);
+  UBGL_REQUIRE(field >= 0 && field < UBGL_NUM_FIELDS, "bad field id");
+  S.upload_add(field, host);
+  UBGL_CATCH
+}
+
 int ubgl_sim_download(ubgl_sim_t *sim, int field, float *host) {
   UBGL_TRY
   SIM(sim);

@@ -6,6 +6,7 @@
 #include <cstdint>
 #include <string>
 #include <vector>
+#include <atomic>
 
 namespace ubgl {
 
@@ -57,6 +58,19 @@ struct ArgError {
   do {                                                                         \
     if (!(cond)) throw ::ubgl::ArgError{std::string(text)};                    \
   } while (0)
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute of a kernel: a handle
+// created on another GPU of the same process needs its own opt-in.  One bit per device ordinal;
+// every C-ABI entry point has made the handle's device current before a launcher runs.
+template <class K>
+inline void ensure_dyn_smem(K kernel, size_t bytes, std::atomic<unsigned long long> &done) {
+  int dev = 0;
+  UBGL_CUDA(cudaGetDevice(&dev));
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (done.load(std::memory_order_acquire) & bit) return;
+  UBGL_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  done.fetch_or(bit, std::memory_order_release);
+}
 
 // Kernel kinds for the per-kernel profile (ubgl_sim_kernel_stats).
 enum Kind {

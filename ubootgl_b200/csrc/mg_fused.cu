@@ -1068,12 +1068,8 @@ static void launch_tile(const TileArgs &a, cudaStream_t stream, LaunchCounter *l
   constexpr int TX = TileGeom<S, MODE>::TX;
   constexpr int TY = LH - 2 * HALO;
   constexpr size_t smem = sizeof(TileSmem<LH>);
-  static bool attr_set = false;
-  if (!attr_set) {
-    UBGL_CUDA(cudaFuncSetAttribute(k_mg_tile<S, MODE, LH, NT>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  static std::atomic<unsigned long long> attr_done{0};
+  ensure_dyn_smem(k_mg_tile<S, MODE, LH, NT>, smem, attr_done);
   dim3 grid(ceil_div(a.w, TX), ceil_div(a.own_hi - a.own_lo, TY));
   UBGL_LAUNCH(lc, kind, level, stream, k_mg_tile<S, MODE, LH, NT><<<grid, NT, smem, stream>>>(a));
 }
@@ -1103,12 +1099,8 @@ int tile_variant() { return g_tile_variant; }
 template <int MODE>
 static void launch_run(const TileArgs &a, cudaStream_t stream, LaunchCounter *lc, int kind, int level) {
   using G = RunGeom<MODE>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    UBGL_CUDA(cudaFuncSetAttribute(k_mg_run<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)G::smem));
-    attr_set = true;
-  }
+  static std::atomic<unsigned long long> attr_done{0};
+  ensure_dyn_smem(k_mg_run<MODE>, G::smem, attr_done);
   dim3 grid(ceil_div(a.w, G::TX), ceil_div(a.own_hi - a.own_lo, G::TY));
   TileArgs b = a;
   b.pf_dist = g_prefetch_dist;
@@ -1201,11 +1193,8 @@ void launch_mg_tail(const std::vector<TailLevel> &lv, int t, const float *hh, co
   a.rhs = rhs;
   a.out = out;
   const size_t smem = (size_t)cells * 9 + 16;
-  static bool attr_set = false;
-  if (!attr_set) {
-    UBGL_CUDA(cudaFuncSetAttribute(k_mg_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TAIL_SMEM_MAX));
-    attr_set = true;
-  }
+  static std::atomic<unsigned long long> attr_done{0};
+  ensure_dyn_smem(k_mg_tail, TAIL_SMEM_MAX, attr_done);
   UBGL_LAUNCH(lc, K_MG_COARSE, t, stream, k_mg_tail<<<1, TAIL_NT, smem, stream>>>(a));
 }
 

@@ -581,6 +581,38 @@ void DeviceSim::upload(int id, const float *host) {
   if (id == F_FLAG) flag_changed(false);
 }
 
+// dst(x, y) += src[y * w + x]: host contributions to a device-resident accumulator
+__global__ void k_add_packed(Grid dst, const float *__restrict__ src, int border) {
+  const size_t y = blockIdx.y + border;
+  for (int x = border + blockIdx.x * blockDim.x + threadIdx.x; x < dst.w - border; x += gridDim.x * blockDim.x)
+    dst.d[y * dst.pitch + x] = __fadd_rn(dst.d[y * dst.pitch + x], src[y * dst.w + x]);
+}
+
+// += of a host grid onto a device field.  The accumulators are written from both sides of the
+// C ABI: the items kernels scatter into the device copies with atomicAdd (next.cu), a host
+// caller (advect_floating_items.cpp:118-120 running on the CPU) adds into its mirror; a plain
+// upload of the mirror would erase what the device has collected since the last step.
+void DeviceSim::upload_add(int id, const float *host) {
+  UBGL_REQUIRE(host != nullptr, "upload_add: null host pointer");
+  UBGL_REQUIRE(id != F_FLAG, "upload_add: not meaningful for the flag field");
+  Grid g = field(id);
+  const size_t n = (size_t)g.w * g.h;
+  if (n > cap_pack) {
+    if (d_pack) UBGL_CUDA(cudaFree(d_pack));
+    d_pack = nullptr;
+    cap_pack = 0;
+    UBGL_CUDA(cudaMalloc(&d_pack, sizeof(float) * (size_t)W * H));
+    cap_pack = (size_t)W * H;
+  }
+  UBGL_CUDA(cudaMemcpyAsync(d_pack, host, sizeof(float) * n, cudaMemcpyHostToDevice, stream));
+  // the accumulators exist on the interior only (simulation.cpp:380-394 applies and clears
+  // 1..w-2 x 1..h-2); their border cells are not part of the sum
+  const int border = (id == F_VX_ACCUM || id == F_VY_ACCUM) ? 1 : 0;
+  dim3 grid(std::min(ceil_div(g.w, 256), 8), g.h - 2 * border);
+  UBGL_LAUNCH(&lc, K_ACCUM, 0, stream, k_add_packed<<<grid, 256, 0, stream>>>(g, d_pack, border));
+  UBGL_CUDA(cudaStreamSynchronize(stream)); // host buffer is only borrowed for the call
+}
+
 // The level-0 flag changed: refresh what is derived from it.  `pyramid` also
 // rebuilds the coarse flags (MG::updateFields); a bare write to sim.flag does
 // not, exactly as in the reference (simulation.hpp:85 vs ubootgl_app.cpp:111-112).
@@ -859,6 +891,10 @@ void DeviceSim::run_part(std::map<int, StepGraph> &cache, bool dt_dependent, boo
     return;
   }
   if (dt_dependent && g.dt != dt) { // a new time step: wait until it repeats before capturing
+    if (g.exec) { // captured with the old dt's constants baked in: must never be replayed again
+      cudaGraphExecDestroy(g.exec);
+      g.exec = nullptr;
+    }
     g.dt = dt;
     g.seen = 0;
   }

@@ -81,6 +81,7 @@ public:
   Grid field(int id); // current device grid of a public member (front/back resolved)
   void field_size(int id, int *w, int *h) const;
   void upload(int id, const float *host);
+  void upload_add(int id, const float *host); // field += host grid
   void download(int id, float *host);
   void update_flag(const float *host_flag);
   void flag_changed(bool pyramid, bool binary_edit = false);

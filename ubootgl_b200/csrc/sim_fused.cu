@@ -380,14 +380,9 @@ __global__ void k_gradient_save(Grid vx, Grid vy, Grid p, const uint8_t *mask, G
 // launchers
 // ---------------------------------------------------------------------------
 void launch_prestep(int comp, const PrestepArgs &g, cudaStream_t stream, LaunchCounter *lc) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    UBGL_CUDA(cudaFuncSetAttribute(k_prestep<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)sizeof(PrestepSmem)));
-    UBGL_CUDA(cudaFuncSetAttribute(k_prestep<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)sizeof(PrestepSmem)));
-    attr_set = true;
-  }
+  static std::atomic<unsigned long long> attr_done0{0}, attr_done1{0};
+  ensure_dyn_smem(k_prestep<0>, sizeof(PrestepSmem), attr_done0);
+  ensure_dyn_smem(k_prestep<1>, sizeof(PrestepSmem), attr_done1);
   const int rows = std::min(g.gh, g.own_hi) - g.own_lo;
   if (rows <= 0) return;
   dim3 grid(ceil_div(g.gw, PTX), ceil_div(rows, PTY));

@@ -12,29 +12,72 @@
 #include <algorithm>
 #include <cassert>
 #include <cstddef>
+#include <functional>
 #include <utility>
 #include <vector>
 
 namespace ubgl_host {
-// row-major fp32 storage with a "host wrote to me" flag
+// row-major fp32 storage with a "host wrote to me" flag (dirty: the next step() uploads it) and
+// a "device is newer" flag (stale: set by Simulation in SyncMode::RESIDENT, where step() does not
+// download; the first host access then pulls the field from the device, so a mirror the game
+// reads or edits is never older than the device state it is about to overwrite).
 class MirrorStore {
 public:
+  using Pull = std::function<void(float *)>;
   MirrorStore() = default;
   MirrorStore(int w, int h) : cells_((size_t)w * h, 0.0f) {}
+  // value semantics like std::vector<float> (the reference copy-assigns grids, simulation.hpp:38-43):
+  // a copy is a plain host grid (no device behind it); assignment keeps the destination's device link
+  MirrorStore(const MirrorStore &o) : cells_((o.fresh(), o.cells_)), dirty_(true) {}
+  MirrorStore(MirrorStore &&o) : cells_((o.fresh(), std::move(o.cells_))), dirty_(true) {}
+  MirrorStore &operator=(const MirrorStore &o) {
+    if (this != &o) {
+      o.fresh();
+      cells_ = o.cells_;
+      dirty_ = true;
+      stale_ = false;
+    }
+    return *this;
+  }
+  MirrorStore &operator=(MirrorStore &&o) {
+    if (this != &o) {
+      o.fresh();
+      cells_ = std::move(o.cells_);
+      dirty_ = true;
+      stale_ = false;
+    }
+    return *this;
+  }
   float *rw() {
+    fresh();
     dirty_ = true;
     return cells_.data();
   }
-  const float *ro() const { return cells_.data(); }
-  float *raw() { return cells_.data(); } // library-side access: does not mark
+  const float *ro() const {
+    fresh();
+    return cells_.data();
+  }
+  float *raw() { return cells_.data(); } // library-side access: neither marks nor pulls
   size_t size() const { return cells_.size(); }
   bool dirty() const { return dirty_; }
   void clean() { dirty_ = false; }
   void touch() { dirty_ = true; }
+  // ---- used by Simulation only ----
+  void set_pull(Pull p) { pull_ = std::move(p); }
+  void mark_stale() { stale_ = pull_ != nullptr; }
+  void mark_fresh() { stale_ = false; }
+  bool stale() const { return stale_; }
 
 private:
+  void fresh() const {
+    if (!stale_) return;
+    stale_ = false;
+    pull_(const_cast<float *>(cells_.data()));
+  }
   std::vector<float> cells_;
   bool dirty_ = true; // a fresh grid has never been uploaded
+  mutable bool stale_ = false;
+  Pull pull_;
 };
 } // namespace ubgl_host
 
@@ -107,6 +150,8 @@ public:
 
   ubgl_host::MirrorStore &front_mirror() { return s_[front_]; }
   ubgl_host::MirrorStore &back_mirror() { return s_[front_ ^ 1]; }
+  ubgl_host::MirrorStore &store(int k) { return s_[k]; }
+  int front_index() const { return front_; }
 
 private:
   int front_ = 0;

@@ -54,7 +54,34 @@ void Simulation::create() {
   dev_.reset(raw, [](ubgl_sim_t *s) { ubgl_sim_destroy(s); });
   flag.mirror().clean();
   mg = MG::attached(dev_, width, height);
+  // lazy pulls of SyncMode::RESIDENT: a stale mirror fetches its field on first access
+  auto pull = [this](int field) {
+    return [this, field](float *dst) { ck(ubgl_sim_download(dev_.get(), field, dst), "pull"); };
+  };
+  for (int k = 0; k < 2; k++) {
+    vx.store(k).set_pull([this, k](float *dst) {
+      ck(ubgl_sim_download(dev_.get(), vx.front_index() == k ? UBGL_VX : UBGL_VXB, dst), "pull");
+    });
+    vy.store(k).set_pull([this, k](float *dst) {
+      ck(ubgl_sim_download(dev_.get(), vy.front_index() == k ? UBGL_VY : UBGL_VYB, dst), "pull");
+    });
+  }
+  p.mirror().set_pull(pull(UBGL_P));
+  f.mirror().set_pull(pull(UBGL_F));
+  vx_current.mirror().set_pull(pull(UBGL_VX_CURRENT));
+  vy_current.mirror().set_pull(pull(UBGL_VY_CURRENT));
   syncToDevice();
+}
+
+void Simulation::markStale() {
+  for (int k = 0; k < 2; k++) {
+    vx.store(k).mark_stale();
+    vy.store(k).mark_stale();
+  }
+  p.mirror().mark_stale();
+  f.mirror().mark_stale();
+  vx_current.mirror().mark_stale();
+  vy_current.mirror().mark_stale();
 }
 
 void Simulation::pushBCs() {
@@ -72,8 +99,10 @@ void Simulation::syncToDevice() {
     ck(ubgl_sim_upload(dev_.get(), field, m.ro()), "upload");
     m.clean();
   };
-  if (flag.mirror().dirty()) { // memcpy into sim.flag (+ the pyramid is rebuilt, see MG::updateFields)
-    ck(ubgl_sim_update_flag(dev_.get(), flag.mirror().ro()), "update_flag");
+  if (flag.mirror().dirty()) {
+    // a bare write to sim.flag (memcpy ubootgl_app.cpp:111, setGrids simulation.hpp:85) changes
+    // level 0 only; the coarse flags follow at mg.updateFields(flag), as in the reference
+    ck(ubgl_sim_upload(dev_.get(), UBGL_FLAG, flag.mirror().ro()), "upload flag");
     flag.mirror().clean();
   }
   up(UBGL_VX, vx.front_mirror());
@@ -87,7 +116,8 @@ void Simulation::syncToDevice() {
     std::lock_guard<std::mutex> lock(accum_mutex);
     auto take = [&](int field, Single2DGrid &g) {
       if (!g.mirror().dirty()) return;
-      ck(ubgl_sim_upload(dev_.get(), field, g.mirror().ro()), "upload accum");
+      // += : the device accumulators may already hold what the items kernels scattered
+      ck(ubgl_sim_upload_add(dev_.get(), field, g.mirror().ro()), "upload accum");
       float *a = g.mirror().raw();
       for (int y = 1; y < g.height - 1; y++)
         std::memset(a + (size_t)y * g.width + 1, 0, sizeof(float) * (g.width - 2));
@@ -104,6 +134,7 @@ void Simulation::syncToDevice() {
 void Simulation::download(int field, ubgl_host::MirrorStore &m) {
   ck(ubgl_sim_download(dev_.get(), field, m.raw()), "download");
   m.clean();
+  m.mark_fresh();
 }
 
 void Simulation::syncToHost() {
@@ -129,6 +160,7 @@ void Simulation::step(float timestep) {
   if (mode_ == SyncMode::MIRROR) {
     syncToHost();
   } else {
+    markStale();
     int n = 0; // the sink list is host-side state in either mode
     ck(ubgl_sim_get_sinks(dev_.get(), nullptr, 0, &n), "get_sinks");
     sinks.resize(n);
@@ -142,6 +174,7 @@ void Simulation::runStage(int stage) {
   syncToDevice();
   ck(ubgl_sim_stage(dev_.get(), stage, dt), "stage");
   if (mode_ == SyncMode::MIRROR) syncToHost();
+  else markStale();
 }
 void Simulation::applyAccumulatedVelocity() { runStage(UBGL_ST_ACCUM); }
 void Simulation::diffuse() { runStage(UBGL_ST_DIFFUSE); }
@@ -231,7 +264,6 @@ float Simulation::psampleFlagNearest(glm::vec2 pc) {
 
 // simulation.cpp:210-224 (unused by step): mean-free pressure on the interior
 void Simulation::centerP() {
-  if (mode_ == SyncMode::RESIDENT) download(UBGL_P, p.mirror());
   double sum = 0.0;
   const Single2DGrid &pc = p;
   for (int y = 1; y < height - 1; y++)

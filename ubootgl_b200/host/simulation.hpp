@@ -10,11 +10,22 @@
 //                 sinks are handed over);
 //   step() exit : vx, vy (front and back), p, f, vx_current, vy_current and the
 //                 surviving sinks are downloaded.
-// setSyncMode(RESIDENT) switches the automatic downloads off for benchmarks;
-// syncToHost() fetches on demand.  Floating-item advection
-// (advect_floating_items.cpp) and the entt registry are outside the hot path
-//  -- the reference's own file compiles against this header.
+// setSyncMode(RESIDENT) switches the automatic downloads off: the mirrors are then
+// marked stale and pulled from the device lazily, by the first host access to each.
+//
+// Floating items (simulation.hpp:116-117, called by ubootgl_app.cpp:129-130): inside the
+// reference tree -- where components.hpp and the vendored entt are on the include path --
+// advectFloatingItems / advectFloatingItemsSimple are declared exactly as in the reference.
+// Two definitions fit them: this directory's advect_floating_items.cpp (copies the
+// registry view into ubgl_item records and runs ubgl_items_advect[_simple] on the GPU), or
+// the reference's own advect_floating_items.cpp unchanged (CPU, on the host mirrors; it
+// compiles against this header -- tests/test_dropin_compile.py does exactly that).
 #pragma once
+#if __has_include("components.hpp") && __has_include("entt/entity/registry.hpp")
+#define UBGL_HAVE_REGISTRY 1
+#include "components.hpp" // CoItem, CoKinematics, CoKinematicsSimple (components.hpp:6-43)
+#include "entt/entity/registry.hpp"
+#endif
 #include "db2dgrid.hpp"
 #include "pressure_solver.hpp"
 #include <memory>
@@ -46,6 +57,7 @@ public:
 
   void setGrids(glm::ivec2 c, float val); // simulation.hpp:82-98
 
+  glm::vec2 bilinearVel(glm::vec2 c); // simulation.hpp:100, defined by the items TU
   float psampleFlagNearest(glm::vec2 pc);
   float psampleFlagLinear(glm::vec2 pc);
   glm::vec2 psampleFlagNormal(glm::vec2 pc);
@@ -58,6 +70,13 @@ public:
   void applyAccumulatedVelocity();
   void saveCurrentVelocityFields();
   void step(float timestep);
+  void interpolateFields();      // simulation.hpp:77, declared and never defined there either
+  float diffusion_l2_residual(); // simulation.hpp:105, likewise
+
+#ifdef UBGL_HAVE_REGISTRY
+  void advectFloatingItems(entt::registry &registry, float gameDT);       // simulation.hpp:116
+  void advectFloatingItemsSimple(entt::registry &registry, float gameDT); // simulation.hpp:117
+#endif
 
   // ---- additions of the drop-in ----
   void setSyncMode(SyncMode m) { mode_ = m; }
@@ -96,7 +115,9 @@ private:
   void runStage(int stage);
   void pushBCs();
   void download(int field, ubgl_host::MirrorStore &m);
+  void markStale();
   std::shared_ptr<ubgl_sim> dev_;
+  std::shared_ptr<struct ubgl_items> items_[2]; // device item sets of advectFloatingItems / ...Simple
   SyncMode mode_ = SyncMode::MIRROR;
   BC sentBC_[4] = {BC::INFLOW, BC::OUTFLOW_ZERO_PRESSURE, BC::NOSLIP, BC::NOSLIP};
 };
