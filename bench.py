@@ -206,19 +206,59 @@ def cpu_reference_isolated(name, steps, warmup, threads=None):
     return None
 
 
+def l2_note(N):
+    return (f"state {12 * N * 4 / 1e6:.0f} MB per step vs 126 MB L2"
+            + (" (inputs larger than L2)" if N * 4 > 126e6 else " (L2 RESIDENT: latency bound, HBM % not meaningful)"))
+
+
+def workload_config(ran, asked=None, parallelism="1 GPU"):
+    """`config` of a bench line: the SAME keys (and, for the same workload, the same values) in
+    our arm and in the reference arm.  `ran` is the workload that was timed; `sampled_for` names
+    the workload it stands in for when the asked one does not fit the arm (the reference CPU run
+    of channel32768 needs ~80 GB of host memory and minutes per step)."""
+    W, H = workload_dims(ran)
+    dt = 0.001 if ran == "game" else float(np.float32(PWIDTH) / np.float32(W - 1))
+    return {"workload": ran, "grid": [W, H], "vcycles_per_step": VCYCLES, "dt": dt,
+            "sampled_for": asked if (asked and asked != ran) else None,
+            "parallelism": parallelism, "l2": l2_note(W * H)}
+
+
+def cpu_baseline_entry(sample, steps=2, warmup=1, policy=True):
+    """cpu_baseline object: the reference's own solver on this box's host cores, bounded sample."""
+    r = cpu_reference_isolated(sample, steps, warmup) or cpu_reference_isolated(sample, steps, warmup)  # one retry
+    if r is None:
+        return {"value": None, "unit": "MLUP/s", "cores": None, "kind": "reference",
+                "sample": f"{sample}: the reference process died twice (its rbgs path 3 reads out of bounds)"}
+    cpu = {"value": r["value"], "unit": "MLUP/s", "cores": r["cores"], "kind": r["kind"],
+           "sample": f"{sample}: {r['warmup']} warm-up + {r['steps']} timed Simulation::step "
+                     f"({r['ms_per_step']:.0f} ms/step), OMP threads {r['cores']} of {r['nproc']}, rbgs {r['rbgs_path']}"}
+    # the game's own thread policy, sim_loop.cpp:19: max(1, nproc/2 - 1) (SURVEY.md 8d)
+    tg = max(1, r["nproc"] // 2 - 1)
+    if policy and tg != r["cores"]:
+        r2 = cpu_reference_isolated(sample, 1 if sample != "game" else 20, 1, threads=tg)
+        if r2:
+            cpu["game_thread_policy"] = {"value": r2["value"], "cores": tg, "ms_per_step": r2["ms_per_step"],
+                                         "rbgs_path": r2["rbgs_path"]}
+    return cpu
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    name = args.workload or ("channel8192" if args.gpus == 1 else "channel32768")
-    sample = name
-    W, H = workload_dims(name)
+    asked = args.workload or ("channel8192" if args.gpus == 1 else "channel32768")
+    sample = asked
+    W, H = workload_dims(asked)
     if W * H > 8192 * 8192:
         # a 32768^2 reference step needs ~80 GB and minutes per step: time the
-        # 8192^2 member of the same generator instead and say so
+        # 8192^2 member of the same generator instead and SAY so (config.workload = what ran)
         sample = "channel8192"
-    steps = max(1, min(args.steps, 3 if sample != "game" else args.steps))
-    warmup = max(1, min(args.warmup, 1 if sample != "game" else args.warmup))
+    W, H = workload_dims(sample)
+    # exactly the K timed steps after W warm-up steps the driver asked for, as long as that stays
+    # a bounded sample (~0.55 s per 8192^2 step on 16 cores); what actually ran is what is printed
+    est = 0.6 * (W * H) / (8192.0 * 8192.0)
+    steps = max(1, min(args.steps, int(120.0 / max(est, 1e-3))))
+    warmup = max(1, min(args.warmup, 5))
     r = cpu_reference_isolated(sample, steps, warmup) or cpu_reference_isolated(sample, steps, warmup)
     if r is None:
         print(json.dumps({"impl": "reference", "unavailable": "the reference process died twice (out-of-bounds "
@@ -226,11 +266,12 @@ def run_reference(args):
         return
     line = {
         "impl": "reference", "metric": "fluid_step_throughput", "value": r["value"], "unit": "MLUP/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
-        "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None,
+        "n_gpus": args.gpus, "steps": r["steps"], "warmup": r["warmup"], "ms_per_step": r["ms_per_step"],
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": name, "grid": [W, H], "vcycles_per_step": VCYCLES,
-                   "note": "reference CPU solver (OpenMP+AVX2) on the GPU box's host cores"},
+        "config": workload_config(sample, asked, parallelism="1 GPU" if args.gpus == 1 else f"row slabs x{args.gpus}"),
+        "note": f"reference CPU solver (OpenMP+AVX2, oracle/_ref = the unmodified reference) on the GPU box's host "
+                f"cores: {r['cores']} OMP threads; the same CPU run stands beside every GPU count",
         "cpu_baseline": {"value": r["value"], "unit": "MLUP/s", "cores": r["cores"], "kind": r["kind"],
                          "sample": f"{sample}: {r['warmup']} warm-up + {r['steps']} timed Simulation::step, "
                                    f"OMP threads {r['cores']} of {r['nproc']} procs, rbgs {r['rbgs_path']}"},
@@ -330,34 +371,29 @@ def run_single_gpu(args, name):
     cpu = None
     if not args.no_cpu_baseline:
         sample = name if N <= 8192 * 8192 else "channel8192"
-        nst = 2 if sample != "game" else 20
-        r = cpu_reference_isolated(sample, nst, 1) or cpu_reference_isolated(sample, nst, 1)  # one retry
-        if r is None:
-            cpu = {"value": None, "unit": "MLUP/s", "cores": None, "kind": "reference",
-                   "sample": f"{sample}: the reference process died twice (its rbgs path 3 reads out of bounds)"}
-        else:
-            cpu = {"value": r["value"], "unit": "MLUP/s", "cores": r["cores"], "kind": r["kind"],
-                   "sample": f"{sample}: {r['warmup']} warm-up + {r['steps']} timed Simulation::step "
-                             f"({r['ms_per_step']:.0f} ms/step), OMP threads {r['cores']} of {r['nproc']}, rbgs {r['rbgs_path']}"}
-            # the game's own thread policy, sim_loop.cpp:19: max(1, nproc/2 - 1)
-            tg = max(1, r["nproc"] // 2 - 1)
-            if tg != r["cores"]:
-                r2 = cpu_reference_isolated(sample, 1 if sample != "game" else 20, 1, threads=tg)
-                if r2:
-                    cpu["game_thread_policy"] = {"value": r2["value"], "cores": tg, "ms_per_step": r2["ms_per_step"],
-                                                 "rbgs_path": r2["rbgs_path"]}
+        cpu = cpu_baseline_entry(sample, steps=3 if sample != "game" else 20, warmup=1)
+
+    # ---- the 1-GPU base of the strong-scaling study (BASELINE.json: ">= 6x at 8 GPUs on 32768^2"):
+    # the SAME workload the N > 1 runs decompose, whole on this one GPU with the single-GPU kernels,
+    # measured in this process so that the driver's N = 1 record contains it ----
+    base = None
+    if name == "channel8192" and not args.no_strong_base:
+        del sim, outs, ax, ay
+        base = strong_scaling_base("channel32768", dev, steps=min(K, 5), warmup=3)
 
     bpc = bytes_per_cell()
     step_gbs = N * bpc / (ms_step * 1e-3) / 1e9
     line = {
         "metric": "fluid_step_throughput", "value": value, "unit": "MLUP/s", "n_gpus": 1, "steps": K,
-        "warmup": Wm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "warmup": Wm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": name, "grid": [W, H], "vcycles_per_step": VCYCLES, "dt": dt,
-                   "l2": f"state {12 * N * 4 / 1e6:.0f} MB per step vs 126 MB L2"
-                         + (" (inputs larger than L2)" if N * 4 > 126e6 else " (L2 RESIDENT: latency bound, HBM % not meaningful)"),
-                   "residual_after": res_after, "fused": True},
+        "config": workload_config(name),
+        "run_info": {"residual_after": res_after, "fused": True,
+                     "scaling_note": "N = 1 anchors the strong-scaling study of channel32768 (see strong_scaling_base); "
+                                     "MLUP/s is size-normalised, so the driver's v_N / (N v_1) compares like with like"},
+        "strong_scaling_base": base,
         "roofline": roof,
+        "roofline_by_kernel": roofline_by_kernel(kern, W, H, peak, prof_total / PK, workload=name),
         "roofline_step": {"bound": "hbm", "achieved": step_gbs, "peak": peak, "unit": "GB/s",
                           "frac": step_gbs / peak, "bytes_per_cell": bpc,
                           "model": "stage-wise algorithmic bytes 152 + 186.7*k B/cell (SURVEY.md 8d), k=2",
@@ -512,13 +548,12 @@ def run_explosion(args, name):
     step_only = sum(ms for ms, n, k, l in fluid)
     line = {
         "metric": "fluid_step_throughput", "value": N / (ms_step * 1e-3) / 1e6, "unit": "MLUP/s", "n_gpus": 1,
-        "steps": K, "warmup": Wm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "steps": K, "warmup": Wm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": name, "grid": [W, H], "vcycles_per_step": VCYCLES, "dt": dt,
-                   "per_step": f"{CRATERS} craters diam {CRATER_DIAM} + coarse-flag/mask rebuild, {CRATERS} sinks, "
-                               f"Simulation::step, {N_PARTICLES} tracers x30 ring, {N_PARTICLES} simple items "
-                               f"(game dt 1/60, up to 15 sub-steps, force scatter by atomicAdd)",
-                   "l2": f"state {12 * N * 4 / 1e6:.0f} MB per step vs 126 MB L2 (inputs larger than L2)"},
+        "config": workload_config(name),
+        "run_info": {"per_step": f"{CRATERS} craters diam {CRATER_DIAM} + coarse-flag/mask rebuild, {CRATERS} sinks, "
+                                 f"Simulation::step, {N_PARTICLES} tracers x30 ring, {N_PARTICLES} simple items "
+                                 f"(game dt 1/60, up to 15 sub-steps, force scatter by atomicAdd)"},
         "particles": {"tracers_per_s": N_PARTICLES / (per.get("tracers", float("nan")) * 1e-3),
                       "items_per_s": N_PARTICLES / (per.get("items", float("nan")) * 1e-3),
                       "tracers_ms": per.get("tracers"), "items_ms": per.get("items"),
@@ -610,12 +645,21 @@ def ncu_traffic(workload, kind, level):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel from the
     committed `ncu --set full` capture of the same workload (profiles/), else None."""
     p = os.path.join(ROOT, "profiles", f"traffic_{workload}.json")
-    if not os.path.exists(p):
+    if not workload or not os.path.exists(p):
         return None
     return json.load(open(p)).get("traffic_bytes_per_launch", {}).get(f"{kind}:{level}")
 
 
+def traffic_source(workload):
+    p = os.path.join(ROOT, "profiles", f"traffic_{workload}.json")
+    if not workload or not os.path.exists(p):
+        return None
+    return f"profiles/traffic_{workload}.json (ncu --set full, DRAM read+write bytes per launch)"
+
+
 def dominant_roofline(kern, W, H, peak, peak_src, prof_ms_step, cells_scale=1.0, workload=None):
+    """`roofline` of the bench line: the (kernel, MG level) with the largest share of the step.
+    achieved = algorithmic bytes per launch (KERNEL_BYTES x cells of its level) / mean launch ms."""
     if not kern:
         return None
     ms, n, k, l = kern[0]
@@ -625,15 +669,83 @@ def dominant_roofline(kern, W, H, peak, peak_src, prof_ms_step, cells_scale=1.0,
         return {"bound": "hbm", "kernel": k, "level": l, "achieved": None, "peak": peak, "unit": "GB/s",
                 "frac": None, "traffic": None}
     per_launch_ms = ms / max(n, 1)
-    units = 1.0 / n if k in ("mg_pre_fused", "mg_post_fused") else 1.0  # bytes above are per launch
-    bytes_launch = cells * bpc * (1.0 if k in ("mg_pre_fused", "mg_post_fused") else 1.0)
+    bytes_launch = cells * bpc
     ach = bytes_launch / (per_launch_ms * 1e-3) / 1e9
-    return {"bound": "hbm", "kernel": k, "level": l, "launches_per_step": n,
-            "avg_launch_ms": per_launch_ms, "share_of_step": ms / prof_ms_step if prof_ms_step else None,
-            "algorithmic_bytes_per_launch": bytes_launch, "achieved": ach, "peak": peak, "unit": "GB/s",
-            "frac": ach / peak, "traffic": ncu_traffic(workload, k, l) if cells_scale == 1.0 else None,
-            "traffic_source": None if workload is None else f"profiles/traffic_{workload}.json (ncu --set full, DRAM read+write bytes per launch)",
-            "peak_source": peak_src}
+    traffic = ncu_traffic(workload, k, l) if cells_scale == 1.0 else None
+    out = {"bound": "hbm", "kernel": k, "level": l, "launches_per_step": n,
+           "avg_launch_ms": per_launch_ms, "share_of_step": ms / prof_ms_step if prof_ms_step else None,
+           "algorithmic_bytes_per_launch": bytes_launch, "achieved": ach, "peak": peak, "unit": "GB/s",
+           "frac": ach / peak, "traffic": traffic, "peak_source": peak_src}
+    if traffic is not None:
+        out["traffic_source"] = traffic_source(workload)
+        out["dram_frac"] = traffic / (per_launch_ms * 1e-3) / 1e9 / peak
+    return out
+
+
+def roofline_by_kernel(kern, W, H, peak, prof_ms_step, workload=None):
+    """Every kernel kind summed over the MG levels it runs on (k_mg_run PRE + POST over the whole
+    pyramid is the largest item of the step, no single (kernel, level) shows that).  `frac` is
+    the algorithmic-byte roofline fraction; `dram_frac` = bytes ncu measured / time / peak, from
+    the committed capture of the same workload (None when there is none)."""
+    agg = {}
+    for ms, n, k, l in kern:
+        a = agg.setdefault(k, {"ms": 0.0, "launches": 0, "alg": 0.0, "traffic": 0.0, "have_traffic": True})
+        a["ms"] += ms
+        a["launches"] += n
+        bpc = KERNEL_BYTES.get(k)
+        if bpc is not None:
+            a["alg"] += (W >> l) * (H >> l) * bpc * n
+        t = ncu_traffic(workload, k, l)
+        if t is None:
+            a["have_traffic"] = False
+        else:
+            a["traffic"] += t * n
+    rows = []
+    for k, a in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
+        if a["ms"] <= 0:
+            continue
+        row = {"kernel": k, "launches_per_step": a["launches"], "ms_per_step": round(a["ms"], 4),
+               "share_of_step": round(a["ms"] / prof_ms_step, 4) if prof_ms_step else None,
+               "algorithmic_gbs": round(a["alg"] / (a["ms"] * 1e-3) / 1e9, 1) if a["alg"] else None,
+               "frac": round(a["alg"] / (a["ms"] * 1e-3) / 1e9 / peak, 4) if a["alg"] else None,
+               "dram_gbs": None, "dram_frac": None}
+        if a["have_traffic"] and a["traffic"] > 0:
+            row["dram_gbs"] = round(a["traffic"] / (a["ms"] * 1e-3) / 1e9, 1)
+            row["dram_frac"] = round(row["dram_gbs"] / peak, 4)
+        rows.append(row)
+    return rows
+
+
+def strong_scaling_base(name, dev, steps, warmup):
+    """One GPU, the whole `name` grid resident (32768^2: 52 GB of state), single-GPU kernels."""
+    import torch
+    import ubootgl_b200 as u
+    from ubootgl_b200 import capi
+    try:
+        W, H, flag, vx, vy, dt = make_inputs(name)
+        sim = u.Simulation(flag, PWIDTH, MU, device=dev)
+        sim.set(capi.VX, vx)
+        del vx, vy, flag  # vy = 0 is the constructor state
+        stream = torch.cuda.ExternalStream(sim.stream(), device=dev)
+        for _ in range(warmup):
+            sim.step(dt)
+        sim.sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            sim.step(dt)
+        e1.record(stream)
+        sim.sync()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        res = sim.residual()
+        sim.close()
+        return {"workload": name, "grid": [W, H], "n_gpus": 1, "ms_per_step": ms, "steps": steps, "warmup": warmup,
+                "value": W * H / (ms * 1e-3) / 1e6, "unit": "MLUP/s", "residual_after": res,
+                "note": "the N > 1 lines of bench.py --gpus N time this same workload; speed-up at N GPUs = "
+                        "this ms_per_step / theirs"}
+    except Exception as e:  # the headline number must survive a failure of the extra
+        return {"workload": name, "error": f"{type(e).__name__}: {e}"[:300]}
 
 
 def main():
@@ -652,6 +764,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strong-base", action="store_true",
+                    help="skip the 1-GPU channel32768 run that anchors the strong-scaling study")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

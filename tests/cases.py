@@ -137,3 +137,19 @@ def mgtest_error(ref, u):
     N = u.shape[0]
     err = (ref - u).astype(np.float64)
     return float(np.sqrt((err ** 2).sum())) / N / N
+
+
+def record_parity(what, size, against, errors):
+    """Append one line of measured parity errors to gpurun_out/parity_errors.jsonl (summarised
+    under profiles/ per round).  Best effort: the tests never depend on it."""
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    d = os.path.join(root, "gpurun_out")
+    try:
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, "parity_errors.jsonl"), "a") as fp:
+            fp.write(json.dumps({"what": what, "size": list(size), "against": against,
+                                 "rel_l2": {k: float(v) for k, v in errors.items()}}) + "\n")
+    except OSError:
+        pass

@@ -17,21 +17,19 @@ sys.path.insert(0, ROOT)
 from tests import cases  # noqa: E402
 
 
-def main():
-    import torch
+FIELDS = (("vx", "VX", 0), ("vy", "VY", 1), ("p", "P", 0), ("vxc", "VX_CURRENT", 0), ("vyc", "VY_CURRENT", 1),
+          ("vxb", "VXB", 0), ("f", "F", 0), ("ax", "VX_ACCUM", 0))
+
+
+def check(W, H, steps, dt, rank, world, dev, verbose=True):
+    """Runs `steps` steps of the seeded W x H case as `world` row slabs (all ranks) and as ONE
+    single-GPU Simulation (rank 0), and compares 8 fields bit for bit (up to the sign of zero)
+    plus the residual norm.  Collective: every rank must call it.  Returns a dict (same on all
+    ranks): bitwise_ok, fields, ranks, mismatches, exchanges, dist_levels, residual."""
     import ubootgl_b200 as u
     from ubootgl_b200 import capi, slab_boot
 
-    W = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
-    H = int(sys.argv[2]) if len(sys.argv) > 2 else 1536
-    steps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
-    rank, world = slab_boot.init_distributed("gloo")
-    dev = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(dev)
-
     c = cases.sim_case(W, H, seed=11, ndiscs=9, radius=H / 17.0)
-    # dt = 0.02 is CFL ~ 25-75: back-traces leave the 16 ghost rows and are served by peer loads
-    dt = float(sys.argv[4]) if len(sys.argv) > 4 else 0.002
     sinks = [[0.4, 0.4 * H / W, 120.0], [0.2, 0.7 * H / W, 60.0]]
     plan = u.slab_plan(W, H, world, rank)
     S = u.SlabSimulation(c["flag"][plan["st_lo"]:plan["st_hi"]], W, H, rank, world,
@@ -44,14 +42,16 @@ def main():
         S.step(dt)
     S.sync()
     got = {}
-    for name, fld, hh in (("vx", capi.VX, H), ("vy", capi.VY, H - 1), ("p", capi.P, H),
-                          ("vxc", capi.VX_CURRENT, H), ("vyc", capi.VY_CURRENT, H - 1),
-                          ("vxb", capi.VXB, H), ("f", capi.F, H), ("ax", capi.VX_ACCUM, H)):
-        lo, rows = S.get_own(fld)
-        got[name] = slab_boot.gather_rows(lo, rows, hh)
+    for name, fid, short in FIELDS:
+        lo, rows = S.get_own(getattr(capi, fid))
+        got[name] = slab_boot.gather_rows(lo, rows, H - short)
     ssq = slab_boot.allreduce_sum(S.residual_sumsq())
     ex, hb = S.stats()
-    ok = True
+    slab_boot.barrier()  # every rank is done with its neighbours' arenas
+    S.close()
+    bad_fields = []
+    resn = float(np.sqrt(ssq))
+    res1 = resn
     if rank == 0:
         G = u.Simulation(c["flag"], device=dev)
         for fld, key in ((capi.VX, "vx"), (capi.VY, "vy"), (capi.VX_ACCUM, "vx_accum"),
@@ -60,27 +60,45 @@ def main():
         G.set_sinks(sinks)
         for _ in range(steps):
             G.step(dt)
-        ref = {"vx": G.get(capi.VX), "vy": G.get(capi.VY), "p": G.get(capi.P),
-               "vxc": G.get(capi.VX_CURRENT), "vyc": G.get(capi.VY_CURRENT), "vxb": G.get(capi.VXB),
-               "f": G.get(capi.F), "ax": G.get(capi.VX_ACCUM)}
-        res1 = G.residual()
-        for k in ref:
-            a, b = got[k], ref[k]
+        for name, fid, short in FIELDS:
+            a, b = got[name], G.get(getattr(capi, fid))
             same = ((a.view(np.uint32) == b.view(np.uint32)) | ((a == 0) & (b == 0)))
             if not same.all():
-                ok = False
+                bad_fields.append(name)
                 bad = np.argwhere(~same)
-                print(f"MISMATCH {k}: {len(bad)} cells, first {bad[:5].tolist()}, "
-                      f"max abs {np.abs(a - b).max():.3e}, rel-L2 {cases.rel_l2(a, b):.3e}", flush=True)
-        resn = float(np.sqrt(ssq))
+                if verbose:
+                    print(f"MISMATCH {name}: {len(bad)} cells, first {bad[:5].tolist()}, "
+                          f"max abs {np.abs(a - b).max():.3e}, rel-L2 {cases.rel_l2(a, b):.3e}", flush=True)
+        res1 = G.residual()
+        G.close()
         if abs(resn - res1) > 1e-5 * max(res1, 1e-30):
-            ok = False
-            print(f"MISMATCH residual norm: slabs {resn} single {res1}", flush=True)
-        print(f"MGPU_EQUIV {'OK' if ok else 'FAIL'} {W}x{H} ranks={world} steps={steps} dt={dt} "
-              f"dist_levels={plan['dist_levels']} exchanges={ex} halo_MB={hb / 1e6:.1f} "
-              f"residual={resn:.6g}", flush=True)
-    okt = slab_boot.allreduce_max(0.0 if ok else 1.0)
-    sys.exit(0 if okt == 0.0 else 1)
+            bad_fields.append("residual_norm")
+            if verbose:
+                print(f"MISMATCH residual norm: slabs {resn} single {res1}", flush=True)
+    nbad = int(slab_boot.allreduce_max(float(len(bad_fields))))
+    return {"bitwise_ok": nbad == 0, "fields": len(FIELDS), "ranks": world, "grid": [W, H], "steps": steps,
+            "dt": dt, "mismatched_fields": bad_fields if rank == 0 else None, "exchanges": ex,
+            "halo_mb": hb / 1e6, "dist_levels": plan["dist_levels"], "residual": resn}
+
+
+def main():
+    import torch
+    from ubootgl_b200 import slab_boot
+
+    W = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
+    H = int(sys.argv[2]) if len(sys.argv) > 2 else 1536
+    steps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+    # dt = 0.02 is CFL ~ 25-75: back-traces leave the 16 ghost rows and are served by peer loads
+    dt = float(sys.argv[4]) if len(sys.argv) > 4 else 0.002
+    rank, world = slab_boot.init_distributed("gloo")
+    dev = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(dev)
+    r = check(W, H, steps, dt, rank, world, dev)
+    if rank == 0:
+        print(f"MGPU_EQUIV {'OK' if r['bitwise_ok'] else 'FAIL'} {W}x{H} ranks={world} steps={steps} dt={dt} "
+              f"dist_levels={r['dist_levels']} exchanges={r['exchanges']} halo_MB={r['halo_mb']:.1f} "
+              f"residual={r['residual']:.6g}", flush=True)
+    sys.exit(0 if r["bitwise_ok"] else 1)
 
 
 if __name__ == "__main__":

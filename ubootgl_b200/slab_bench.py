@@ -23,6 +23,26 @@ def run(args, name):
         raise SystemExit(f"bench.py --gpus {args.gpus} launched with WORLD_SIZE={world}")
     W, H = bench.workload_dims(name)
     N = W * H
+
+    # ---- N-GPU == 1-GPU, bit for bit, BEFORE anything is timed: the slab decomposition of a
+    # seeded 1000 x 1536 case on all ranks against the single-GPU Simulation on rank 0, at
+    # CFL ~ 1-3 (back-traces stay in the ghost rows) and CFL ~ 25-75 (taps served by NVLink
+    # peer loads).  Every scaling number below rests on this equivalence; a mismatch aborts. ----
+    from tests import mgpu_equiv
+    equiv_runs = [mgpu_equiv.check(1000, 1536, 2, dt_, rank, world, dev, verbose=(rank == 0)) for dt_ in (0.002, 0.02)]
+    equiv = {"bitwise_ok": all(r["bitwise_ok"] for r in equiv_runs), "fields": equiv_runs[0]["fields"],
+             "ranks": world, "grid": equiv_runs[0]["grid"], "steps": 2, "dt": [r["dt"] for r in equiv_runs],
+             "dist_levels": equiv_runs[0]["dist_levels"], "exchanges": [r["exchanges"] for r in equiv_runs],
+             "residual": [r["residual"] for r in equiv_runs],
+             "mismatched_fields": [r["mismatched_fields"] for r in equiv_runs],
+             "what": "slab-decomposed step on all ranks vs one-GPU Simulation on rank 0: vx, vy, p, vx_current, "
+                     "vy_current, vx back buffer, f, vx_accum compared as uint32 (sign of zero ignored) + residual norm"}
+    if not equiv["bitwise_ok"]:
+        if rank == 0:
+            print(json.dumps({"metric": "fluid_step_throughput", "n_gpus": world, "error": "slab != single GPU",
+                              "equiv": equiv}), flush=True)
+        raise SystemExit(3)
+
     plan = u.slab_plan(W, H, world, rank)
     dt = float(np.float32(bench.PWIDTH) / np.float32(W - 1))  # dt = h, CFL ~ 1
     # synthetic input, generated slab-wise: only the rows this rank stores
@@ -108,6 +128,11 @@ def run(args, name):
     clocks = clk.summary()
     if rank != 0:
         return
+    cpu = None
+    if not args.no_cpu_baseline:  # rank 0 only; the other ranks are done
+        cpu = bench.cpu_baseline_entry("channel8192", steps=3, warmup=1, policy=False)
+        if cpu.get("sample"):
+            cpu["sample"] += f" -- sampled for {name} (a 32768^2 reference step needs ~80 GB of host memory)"
     peak, peak_src = bench.peaks()
     bpc = bench.bytes_per_cell()
     step_gbs = N * bpc / (ms_step * 1e-3) / 1e9
@@ -115,14 +140,13 @@ def run(args, name):
         "metric": "fluid_step_throughput", "value": value, "unit": "MLUP/s", "n_gpus": world, "steps": K,
         "warmup": Wm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": name, "grid": [W, H], "vcycles_per_step": bench.VCYCLES, "dt": dt,
-                   "parallelism": f"row slabs x{world}, {plan['dist_levels']} distributed MG levels, "
-                                  f"coarser levels replicated, ghost {plan['ghost']} rows",
-                   "l2": "slab state >> 126 MB L2 (inputs larger than L2)",
-                   "halo_mb_per_step_all_ranks": halo_mb, "exchanges_per_step": (x1 - x0) / K,
-                   "residual_after": res_after,
-                   "note": "strong scaling is defined on this workload; the N=1 default of bench.py "
-                           "is channel8192 (same generator, same MLUP/s definition)"},
+        "config": bench.workload_config(name, parallelism=f"row slabs x{world}"),
+        "run_info": {"residual_after": res_after, "decomposition": f"{plan['dist_levels']} distributed MG levels, "
+                     f"coarser levels replicated, ghost {plan['ghost']} rows",
+                     "halo_mb_per_step_all_ranks": halo_mb, "exchanges_per_step": (x1 - x0) / K,
+                     "scaling_note": "strong scaling is defined on this workload; its 1-GPU base is the "
+                                     "strong_scaling_base object of the N = 1 line (bench.py --gpus 1)"},
+        "equiv": equiv,
         "roofline": bench.dominant_roofline([r for r in kern if not r[2].startswith("halo")], W, H, peak, peak_src,
                                             prof_total, cells_scale=1.0 / world),
         "roofline_step": {"bound": "hbm", "kernel": "whole step (all ranks)", "achieved": step_gbs,
@@ -138,7 +162,7 @@ def run(args, name):
                          "the separate k_halo_wait launch is gone)"},
         "kernels_ms_per_step_rank0": [{"kernel": k, "level": l, "launches": n, "ms": round(ms, 4)}
                                       for ms, n, k, l in kern[:14]],
-        "cpu_baseline": None,
+        "cpu_baseline": cpu,
         "e2e": {"value": N / t_e2e / 1e6, "unit": "MLUP/s", "h2d_bytes_per_step": int(h2d_all),
                 "d2h_bytes_per_step": int(d2h_all), "ms_per_step": t_e2e * 1e3,
                 "api": "SlabSimulation: ubgl_slab_upload (accumulators) + ubgl_slab_step + ubgl_slab_download "
