@@ -20,6 +20,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SO = os.path.join(HERE, "_ref", "libubgl_ref.so")
+REF_STRICT_SO = os.path.join(HERE, "_ref", "libubgl_ref_strict.so")
 PORT_SO = os.path.join(HERE, "_build", "liboracle.so")
 
 FP = C.POINTER(C.c_float)
@@ -453,8 +454,20 @@ class Port(_Checker):
                                fp(f32(newflag)), W, H)
 
 
+class RefStrict(_Checker):
+    """The unmodified reference fluid TUs compiled -O2 -ffp-contract=off instead of -Ofast
+    (oracle/Makefile): what the reference computes under IEEE-strict code generation.  Its
+    distance from ``Ref`` is the reference's own rounding sensitivity."""
+    prefix = "ref_"
+    so = REF_STRICT_SO
+
+
 def have_ref():
     return os.path.exists(REF_SO)
+
+
+def have_ref_strict():
+    return os.path.exists(REF_STRICT_SO)
 
 
 def have_port():

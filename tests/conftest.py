@@ -40,3 +40,16 @@ def ubgl():
     if ubootgl_b200.lib.ubgl_device_count() < 1:
         pytest.fail("GPU test selected but libubgl sees no CUDA device")
     return ubootgl_b200
+
+
+@pytest.fixture(scope="session")
+def ref_strict():
+    """The unmodified reference fluid TUs compiled IEEE-strict (-O2 -ffp-contract=off) instead of
+    -Ofast: the yardstick for the reference's own rounding sensitivity."""
+    from oracle import bind
+    if not bind.have_ref_strict():
+        if os.path.exists("/root/reference/simulation.cpp"):
+            bind.build(ref=True)
+        else:
+            pytest.skip("oracle/_ref/libubgl_ref_strict.so not available on this box")
+    return bind.RefStrict()

@@ -431,6 +431,184 @@ __global__ void __launch_bounds__(256, 4) k_advect_pair(Grid vx, Grid vy, Grid o
   if (actB) out.at(xi, yB) = __fmul_rn(__fmul_rn(rB, fB0), fB1);
 }
 
+// ---------------------------------------------------------------------------
+// k_advect_xy -- the advect of the fused step: BOTH components in one launch, packed fp32.
+//
+// k_advect_vx / k_advect_vy above are bound by instruction issue (ncu, 8192^2: issue slots
+// 77 % busy, 360 SASS instructions per face for 48 taps, DRAM 15 %).  This kernel does the
+// same arithmetic, bit for bit, in about half the instructions:
+//  * fma.rn.f32x2 / mul.rn.f32x2 (SASS FFMA2 / FMUL2, new on sm_100): the four vertical
+//    Catmull-Rom column sums of a sample are two packed chains (8 instead of 16 FP
+//    instructions), the tap weights two packed polynomials (6 instead of 10 per coordinate);
+//  * truncation by a round-toward-zero add of 2^23 (FADD.RZ on the FMA pipe) instead of
+//    F2I + I2F + FRND on the quarter-rate conversion pipe: the integer part is the low
+//    mantissa of the sum, its float value one more add;
+//  * one thread advects the vx face AND the vy face of its cell: the RK2 start velocities
+//    share loads (8 instead of 10), the five flags the two octet tests and masks need come
+//    from ONE byte of the level-0 stencil mask (C, W, E, S, N bits), and two independent
+//    dependency chains are in flight per thread;
+//  * the accumulator interiors are zeroed here (simulation.cpp:384,392) with two stores
+//    that cost this issue-bound kernel nothing in DRAM terms, instead of 8 B/cell of the
+//    DRAM-bound divergence pass.
+// Semantics (octets x = 1, 9, 17 ..., whole-octet skip, untouched last columns, flat
+// (x+1) loads of the vy loop, rows 1..H-2 for both components) as k_advect_vx / vy;
+// binary flags only (the fused step's precondition).
+// ---------------------------------------------------------------------------
+struct f2 { // two fp32 in one 64-bit register pair
+  unsigned long long v;
+};
+__device__ __forceinline__ f2 pk(float lo, float hi) {
+  f2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ float lo(f2 a) {
+  float x, y;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(a.v));
+  return x;
+}
+__device__ __forceinline__ float hi(f2 a) {
+  float x, y;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(a.v));
+  return y;
+}
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
+  f2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+  return r;
+}
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) {
+  f2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+  return r;
+}
+
+// cr_weights() of tx (low halves) and ty (high halves) at once: the same operations lane for
+// lane, constants as broadcast scalars (w3 = fma(.., t2, +0) instead of a multiply: equal up to
+// the sign of a zero weight)
+__device__ __forceinline__ f2 bc(float c) { return pk(c, c); }
+__device__ __forceinline__ void cr_weights_xy(float tx, float ty, f2 &w0, f2 &w1, f2 &w2, f2 &w3) {
+  const f2 t = pk(tx, ty);
+  const f2 t2 = mul2(t, t);
+  w0 = mul2(fma2(fma2(bc(-0.5f), t, bc(1.0f)), t, bc(-0.5f)), t);
+  w1 = fma2(fma2(bc(1.5f), t, bc(-2.5f)), t2, bc(1.0f));
+  w2 = mul2(fma2(fma2(bc(-1.5f), t, bc(2.0f)), t, bc(0.5f)), t);
+  w3 = fma2(fma2(bc(0.5f), t, bc(-0.5f)), t2, bc(0.0f));
+}
+
+// floor of a clamped (>= 3) coordinate: c + 2^23 rounded toward zero is 2^23 + floor(c)
+// exactly; returns the integer part, *fl its float value
+__device__ __forceinline__ int floor_rz(float c, float &fl) {
+  const float m = __fadd_rz(c, 8388608.0f);
+  fl = __fsub_rn(m, 8388608.0f);
+  return __float_as_int(m) - 0x4B000000;
+}
+
+// wm3 / hm3: (float)w - 3, (float)h - 3 of the sampled grid (kernel parameters: the clamps read
+// them from the constant bank instead of converting w and h for every sample)
+template <bool SLAB>
+__device__ __forceinline__ float bicubic_pk(const float *__restrict__ g, int pitch, float wm3, float hm3, int h,
+                                            float cx, float cy, const TapRows &tr,
+                                            const float *g_lo, const float *g_hi) {
+  cx = fmaxf(fminf(cx, wm3), 3.0f);
+  cy = fmaxf(fminf(cy, hm3), 3.0f);
+  float flx, fly;
+  const int icx = floor_rz(cx, flx), icy = floor_rz(cy, fly);
+  const float stx = __fsub_rn(cx, flx), sty = __fsub_rn(cy, fly);
+  if (SLAB && (icy - 1 < tr.lo || icy + 2 >= min(tr.hi, h)))
+    return bicubic_far(g, pitch, icx, icy, stx, sty, h, tr.lo, tr.hi, tr.plo, tr.phi, g_lo, g_hi, tr.err);
+  f2 w0, w1, w2, w3; // (x weight, y weight) of tap 0..3
+  cr_weights_xy(stx, sty, w0, w1, w2, w3);
+  const float *r0 = g + ((icy - 1) * pitch + (icx - 1));
+  const float *r1 = r0 + pitch, *r2 = r1 + pitch, *r3 = r2 + pitch;
+  // columns (0, 2) and (1, 3): c_j = ((y0 t0j + y1 t1j) + y2 t2j) + y3 t3j, as bicubic()
+  f2 c02 = mul2(bc(hi(w0)), pk(__ldg(r0), __ldg(r0 + 2)));
+  f2 c13 = mul2(bc(hi(w0)), pk(__ldg(r0 + 1), __ldg(r0 + 3)));
+  c02 = fma2(bc(hi(w1)), pk(__ldg(r1), __ldg(r1 + 2)), c02);
+  c13 = fma2(bc(hi(w1)), pk(__ldg(r1 + 1), __ldg(r1 + 3)), c13);
+  c02 = fma2(bc(hi(w2)), pk(__ldg(r2), __ldg(r2 + 2)), c02);
+  c13 = fma2(bc(hi(w2)), pk(__ldg(r2 + 1), __ldg(r2 + 3)), c13);
+  c02 = fma2(bc(hi(w3)), pk(__ldg(r3), __ldg(r3 + 2)), c02);
+  c13 = fma2(bc(hi(w3)), pk(__ldg(r3 + 1), __ldg(r3 + 3)), c13);
+  float v = __fmul_rn(lo(w0), lo(c02));
+  v = __fmaf_rn(lo(w1), lo(c13), v);
+  v = __fmaf_rn(lo(w2), hi(c02), v);
+  return __fmaf_rn(lo(w3), hi(c13), v);
+}
+
+enum { AMB_C = 1, AMB_W = 2, AMB_E = 32, AMB_S = 64, AMB_N = 128 }; // stencil mask bits (mg_fused.cu)
+
+template <bool SLAB>
+__global__ void __launch_bounds__(256, 4) k_advect_xy(Grid vx, Grid vy, Grid vxb, Grid vyb,
+                                                      const uint8_t *__restrict__ mask, float *ax, float *ay,
+                                                      float half, float full, float4 lim /* vx.w-3, vx.h-3, vy.w-3, vy.h-3 */,
+                                                      int y_lo, int y_hi, TapRows tr) {
+  const int lane = threadIdx.x;
+  const int xi = 1 + blockIdx.x * 32 + lane;
+  const int y = y_lo + blockIdx.y * blockDim.y + threadIdx.y; // y_lo >= 1, y_hi <= H-1
+  const int W = vy.w, H = vx.h;
+  const bool row_ok = y < y_hi;
+  const int x0 = xi - (lane & 7);
+  const bool octx = row_ok && (x0 < vx.w - 8), octy = row_ok && (x0 < vy.w - 8);
+  const int pitch = vx.pitch; // shared by every level-0 grid
+  const int o = y * pitch + xi;
+  unsigned m = 0;
+  if (row_ok && xi <= W - 2) {
+    m = mask[o];
+    // accumulators: interiors 1..W-3 x 1..H-2 (vx) and 1..W-2 x 1..H-3 (vy), simulation.cpp:380-394
+    if (ax) {
+      if (xi <= W - 3) ax[o] = 0.0f;
+      if (y <= H - 3) ay[o] = 0.0f;
+    }
+  }
+  const bool condx = octx && (m & (AMB_C | AMB_W)) == (AMB_C | AMB_W); // flag(x-1,y)+flag(x,y) == 2
+  const bool condy = octy && (m & (AMB_C | AMB_S)) == (AMB_C | AMB_S); // flag(x,y)+flag(x,y-1) == 2
+  const unsigned bx = __ballot_sync(0xffffffffu, condx), by = __ballot_sync(0xffffffffu, condy);
+  const bool actx = octx && ((bx >> (lane & ~7)) & 0xffu) != 0;
+  const bool acty = octy && ((by >> (lane & ~7)) & 0xffu) != 0;
+  if (!actx && !acty) return;
+
+  const float fC = (m & AMB_C) ? 1.0f : 0.0f, fE = (m & AMB_E) ? 1.0f : 0.0f, fN = (m & AMB_N) ? 1.0f : 0.0f;
+  // RK2 start velocities: vx / vy at (x, y), (x, y-1), (x+1, y), (x+1, y-1); the (x+1) loads of
+  // vx are flat (simulation.cpp:317-325: x+1 == vx.width wraps into the next row)
+  const float *px = vx.d + o, *py = vy.d + o;
+  const float ux00 = px[0], uy00 = py[0];
+  const float ux0m = px[-pitch], uy0m = py[-pitch];
+  const float uy10 = py[1], uy1m = py[1 - pitch];
+  float ux10, ux1m;
+  if (xi + 1 >= vx.w) {
+    ux10 = vx.d[(y + 1) * pitch + (xi + 1 - vx.w)];
+    ux1m = vx.d[y * pitch + (xi + 1 - vx.w)];
+  } else {
+    ux10 = px[1];
+    ux1m = px[1 - pitch];
+  }
+  const float fx = (float)xi, fy = (float)y;
+
+  if (actx) { // simulation.cpp:246-297
+    const float posx = __fadd_rn(fx, 0.5f), posy = fy;
+    const float vx1 = ux00;
+    const float vy1 = __fmul_rn(__fadd_rn(__fadd_rn(uy00, uy0m), __fadd_rn(uy10, uy1m)), 0.25f);
+    const float midx = __fmaf_rn(-vx1, half, posx), midy = __fmaf_rn(-vy1, half, posy);
+    const float vx2 = bicubic_pk<SLAB>(vx.d, pitch, lim.x, lim.y, vx.h, __fsub_rn(midx, 0.5f), midy, tr, tr.x_lo, tr.x_hi);
+    const float vy2 = bicubic_pk<SLAB>(vy.d, pitch, lim.z, lim.w, vy.h, midx, __fsub_rn(midy, 0.5f), tr, tr.y_lo, tr.y_hi);
+    const float endx = __fmaf_rn(-vx2, full, posx), endy = __fmaf_rn(-vy2, full, posy);
+    const float xvel = bicubic_pk<SLAB>(vx.d, pitch, lim.x, lim.y, vx.h, __fsub_rn(endx, 0.5f), endy, tr, tr.x_lo, tr.x_hi);
+    vxb.d[o] = __fmul_rn(__fmul_rn(xvel, fC), fE);
+  }
+  if (acty) { // simulation.cpp:300-347
+    const float posy = __fadd_rn(fy, 0.5f), posx = fx;
+    const float vy1 = uy00;
+    const float vx1 = __fmul_rn(__fadd_rn(__fadd_rn(ux00, ux0m), __fadd_rn(ux10, ux1m)), 0.25f);
+    const float midx = __fmaf_rn(-vx1, half, posx), midy = __fmaf_rn(-vy1, half, posy);
+    const float vx2 = bicubic_pk<SLAB>(vx.d, pitch, lim.x, lim.y, vx.h, __fsub_rn(midx, 0.5f), midy, tr, tr.x_lo, tr.x_hi);
+    const float vy2 = bicubic_pk<SLAB>(vy.d, pitch, lim.z, lim.w, vy.h, midx, __fsub_rn(midy, 0.5f), tr, tr.y_lo, tr.y_hi);
+    const float endx = __fmaf_rn(-vx2, full, posx), endy = __fmaf_rn(-vy2, full, posy);
+    const float yvel = bicubic_pk<SLAB>(vy.d, pitch, lim.z, lim.w, vy.h, endx, __fsub_rn(endy, 0.5f), tr, tr.y_lo, tr.y_hi);
+    vyb.d[o] = __fmul_rn(__fmul_rn(yvel, fC), fN);
+  }
+}
+
 // project part 1 (simulation.cpp:166-171): f = -(1/h) div v on the interior
 __global__ void k_divergence(Grid vx, Grid vy, Grid f, float ih) {
   int x = 1 + blockIdx.x * blockDim.x + threadIdx.x;
@@ -665,55 +843,77 @@ void DeviceSim::diffuse() {
   }
 }
 
-void launch_advect(const Grid &vx, const Grid &vy, const Grid &vxbk, const Grid &vybk,
+// 1: one face per thread (k_advect_vx / vy); 2: row-pair experiment; 3 (default): k_advect_xy
+static int advect_variant() {
+  static const int variant = [] {
+    const char *e = getenv("UBGL_ADVECT_VARIANT");
+    return (e && e[0] >= '1' && e[0] <= '3') ? e[0] - '0' : 3;
+  }();
+  return variant;
+}
+
+// Returns true when the launch also zeroed the accumulator interiors of rows [y_lo, y_hi)
+// (k_advect_xy, needs the stencil mask, i.e. binary flags); the caller then skips that part of
+// the divergence pass.
+bool launch_advect(const Grid &vx, const Grid &vy, const Grid &vxbk, const Grid &vybk,
                    const Grid &flag, float half, float full, int y_lo, int y_hi, const AdvectPeers *peers,
-                   cudaStream_t stream, LaunchCounter *lc) {
+                   cudaStream_t stream, LaunchCounter *lc, const uint8_t *mask, float *ax, float *ay) {
   const int W = flag.w, H = flag.h;
   y_lo = std::max(y_lo, 1);
   y_hi = std::min(y_hi, H - 1);
-  if (y_hi <= y_lo) return;
+  if (y_hi <= y_lo) return false;
   dim3 b(32, 8);
   dim3 g(ceil_div(W - 2, 32), ceil_div(y_hi - y_lo, 8));
-  static const int variant = [] { // 1 (default): one face per thread; 2: row-pair kernels
-    const char *e = getenv("UBGL_ADVECT_VARIANT");
-    return (e && e[0] == '2') ? 2 : 1;
-  }();
+  const int variant = advect_variant();
+  TapRows tr{};
+  if (peers) {
+    tr.lo = peers->st_lo; tr.hi = peers->st_hi; tr.plo = peers->peer_lo; tr.phi = peers->peer_hi;
+    tr.x_lo = peers->vx_lo; tr.x_hi = peers->vx_hi; tr.y_lo = peers->vy_lo; tr.y_hi = peers->vy_hi;
+    tr.err = peers->err;
+  }
+  if (variant == 3 && mask) {
+    const float4 lim = make_float4((float)vx.w - 3.0f, (float)vx.h - 3.0f, (float)vy.w - 3.0f, (float)vy.h - 3.0f);
+    if (peers)
+      UBGL_LAUNCH(lc, K_ADVECT, LVL, stream, (k_advect_xy<true><<<g, b, 0, stream>>>(vx, vy, vxbk, vybk, mask, ax, ay, half, full, lim, y_lo, y_hi, tr)));
+    else
+      UBGL_LAUNCH(lc, K_ADVECT, LVL, stream, (k_advect_xy<false><<<g, b, 0, stream>>>(vx, vy, vxbk, vybk, mask, ax, ay, half, full, lim, y_lo, y_hi, tr)));
+    return ax != nullptr;
+  }
   if (variant == 2) {
     dim3 g2(g.x, ceil_div(y_hi - y_lo, 16));
-    TapRows tr{};
     if (peers) {
-      tr.lo = peers->st_lo; tr.hi = peers->st_hi; tr.plo = peers->peer_lo; tr.phi = peers->peer_hi;
-      tr.x_lo = peers->vx_lo; tr.x_hi = peers->vx_hi; tr.y_lo = peers->vy_lo; tr.y_hi = peers->vy_hi;
-      tr.err = peers->err;
       UBGL_LAUNCH(lc, K_ADVECT, LVL, stream, (k_advect_pair<true, 0><<<g2, b, 0, stream>>>(vx, vy, vxbk, flag, half, full, y_lo, y_hi, tr)));
       UBGL_LAUNCH(lc, K_ADVECT, LVL, stream, (k_advect_pair<true, 1><<<g2, b, 0, stream>>>(vx, vy, vybk, flag, half, full, y_lo, y_hi, tr)));
     } else {
       UBGL_LAUNCH(lc, K_ADVECT, LVL, stream, (k_advect_pair<false, 0><<<g2, b, 0, stream>>>(vx, vy, vxbk, flag, half, full, y_lo, y_hi, tr)));
       UBGL_LAUNCH(lc, K_ADVECT, LVL, stream, (k_advect_pair<false, 1><<<g2, b, 0, stream>>>(vx, vy, vybk, flag, half, full, y_lo, y_hi, tr)));
     }
-    return;
+    return false;
   }
   if (!peers) {
-    TapRows tr{};
     UBGL_LAUNCH(lc, K_ADVECT, LVL, stream, k_advect_vx<false><<<g, b, 0, stream>>>(vx, vy, vxbk, flag, half, full, y_lo, y_hi, tr));
     UBGL_LAUNCH(lc, K_ADVECT, LVL, stream, k_advect_vy<false><<<g, b, 0, stream>>>(vx, vy, vybk, flag, half, full, y_lo, y_hi, tr));
-    return;
+    return false;
   }
-  TapRows tr;
-  tr.lo = peers->st_lo; tr.hi = peers->st_hi; tr.plo = peers->peer_lo; tr.phi = peers->peer_hi;
-  tr.x_lo = peers->vx_lo; tr.x_hi = peers->vx_hi; tr.y_lo = peers->vy_lo; tr.y_hi = peers->vy_hi;
-  tr.err = peers->err;
   UBGL_LAUNCH(lc, K_ADVECT, LVL, stream, k_advect_vx<true><<<g, b, 0, stream>>>(vx, vy, vxbk, flag, half, full, y_lo, y_hi, tr));
   UBGL_LAUNCH(lc, K_ADVECT, LVL, stream, k_advect_vy<true><<<g, b, 0, stream>>>(vx, vy, vybk, flag, half, full, y_lo, y_hi, tr));
+  return false;
 }
 
-void DeviceSim::advect() {
+void DeviceSim::advect() { advect_impl(false); }
+
+// fused_step: the stencil mask is valid (binary flags) and the accumulators are consumed, so the
+// merged kernel may run and clear them; returns whether it did
+bool DeviceSim::advect_impl(bool fused_step) {
   float ih = 1.0f / h;
   float half = 0.5f * dt * ih, full = dt * ih; // simulation.cpp:276,286
-  launch_advect(vxb[ixf], vyb[iyf], vxb[ixb], vyb[iyb], flag, half, full, 1, H - 1, nullptr, stream,
-                &lc);
+  const bool zeroed =
+      launch_advect(vxb[ixf], vyb[iyf], vxb[ixb], vyb[iyb], flag, half, full, 1, H - 1, nullptr, stream, &lc,
+                    fused_step ? mg->mask0_ptr() : nullptr, fused_step ? vx_accum.d : nullptr,
+                    fused_step ? vy_accum.d : nullptr);
   std::swap(ixf, ixb);
   std::swap(iyf, iyb);
+  return zeroed;
 }
 
 // sum over the interior of (f * flag)^2: the residual norm of p = 0, the
@@ -950,11 +1150,11 @@ void DeviceSim::step(float dt_) {
       fused_prestep();
       fused_borders(false, false);
       mark();
-      advect();
+      const bool acc_zeroed = advect_impl(true);
       mark();
       fused_borders(false, false);
       mark();
-      fused_divergence();
+      fused_divergence(!acc_zeroed);
     });
     project_sinks();
     run_part(graphs_b, false, graphable, [&]() {

@@ -60,9 +60,12 @@ struct AdvectPeers {
   const float *vx_lo, *vx_hi, *vy_lo, *vy_hi; // neighbours' vx / vy fronts (virtual row 0); null at the ends
   int *err;
 };
-void launch_advect(const Grid &vx, const Grid &vy, const Grid &vxb, const Grid &vyb, const Grid &flag,
+// mask != nullptr (binary flags): the merged packed-fp32 kernel k_advect_xy may be used; with
+// ax / ay it also zeroes the accumulator interiors of those rows and the call returns true.
+bool launch_advect(const Grid &vx, const Grid &vy, const Grid &vxb, const Grid &vyb, const Grid &flag,
                    float half, float full, int y_lo, int y_hi, const AdvectPeers *peers,
-                   cudaStream_t stream, LaunchCounter *lc);
+                   cudaStream_t stream, LaunchCounter *lc, const uint8_t *mask = nullptr,
+                   float *ax = nullptr, float *ay = nullptr);
 // sinks (sim.cu): 3x3 stamps restricted to rows [y_lo, y_hi)
 void launch_stamp_sinks(const Grid &f, const float *d_sinks, int n, int y_lo, int y_hi,
                         cudaStream_t stream, LaunchCounter *lc);
@@ -97,6 +100,7 @@ public:
   void apply_accum();
   void diffuse();
   void advect();
+  bool advect_impl(bool fused_step);
   void set_vbcs();
   void project();
   void save_current();
@@ -158,7 +162,7 @@ private:
   // sim_fused.cu
   void fused_prestep();
   void fused_borders(bool with_p, bool with_current);
-  void fused_divergence();
+  void fused_divergence(bool zero_accum);
   void fused_gradient_save();
   std::map<int, StepGraph> graphs_a, graphs_b; // key: buffer roles before the part
   template <class F> void run_part(std::map<int, StepGraph> &cache, bool dt_dependent, bool graphable, F &&enqueue);

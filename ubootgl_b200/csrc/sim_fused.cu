@@ -474,8 +474,10 @@ void DeviceSim::fused_borders(bool with_p, bool with_current) {
   launch_borders(g, stream, &lc);
 }
 
-void DeviceSim::fused_divergence() {
-  launch_divergence4(vxb[ixf], vyb[iyf], f, vx_accum, vy_accum, 1.0f / h, 1, H - 1, stream, &lc);
+void DeviceSim::fused_divergence(bool zero_accum) {
+  const Grid none{};
+  launch_divergence4(vxb[ixf], vyb[iyf], f, zero_accum ? vx_accum : none, zero_accum ? vy_accum : none,
+                     1.0f / h, 1, H - 1, stream, &lc);
 }
 
 void DeviceSim::fused_gradient_save() {
