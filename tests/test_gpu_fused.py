@@ -62,7 +62,7 @@ def test_nonbinary_flags_fall_back_to_plain(ubgl, port):
     assert cases.rel_l2(m.get_p(), o.get_p()) <= 1e-5
 
 
-@pytest.mark.parametrize("W,H", [(70, 40), (130, 97), (258, 131), (545, 218), (1090, 436)])
+@pytest.mark.parametrize("W,H", [(70, 40), (130, 97), (258, 131), (545, 218), (1090, 436), (700, 501), (1301, 300)])
 def test_step_fused_equals_plain(ubgl, W, H):
     from ubootgl_b200 import capi
     c = cases.sim_case(W, H, seed=W + H)

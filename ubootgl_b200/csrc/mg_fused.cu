@@ -44,6 +44,7 @@
 // (solveLevel).
 #include "mg.cuh"
 #include "stencils.cuh"
+#include "packed.cuh"
 #include <cstdlib>
 #include <type_traits>
 
@@ -73,6 +74,8 @@ struct TileArgs {
   int st_lo, st_hi, own_lo, own_hi;
   int c_lo, c_hi; // MODE_POST: rows of the coarse level stored here (single GPU: 0, hc)
   int pf_dist;    // k_mg_run: L2-prefetch the window this many CTAs ahead (0: off)
+  int pair_sync;  // k_mg_run: neighbour-warp named barriers between half-sweeps (0: block barriers)
+  int dbg;        // timing attribution only (UBGL_MG_DBG): 1 skips the sweeps, 2 the residual + restriction
 };
 
 constexpr int LW = 128;    // staged window width in cells
@@ -645,8 +648,8 @@ __global__ void __launch_bounds__(RUN_NT, RUN_NT <= 256 ? 2 : 1) k_mg_run(TileAr
     }
   }
 
-  auto lo = [](int origin, int k) { return max(1, origin + k); };
-  auto hi = [](int origin, int len, int n, int k) { return min(n - 1, origin + len - k); };
+  auto lo_ = [](int origin, int k) { return max(1, origin + k); };
+  auto hi_ = [](int origin, int len, int n, int k) { return min(n - 1, origin + len - k); };
 
   // W / E neighbours of the 4 cells of slot q, given the other colour's 4 cells A of
   // the same row: q == 0: W = (left lane's A.w, A.x, A.y, A.z), E = A;
@@ -657,13 +660,46 @@ __global__ void __launch_bounds__(RUN_NT, RUN_NT <= 256 ? 2 : 1) k_mg_run(TileAr
     return (tg == (q == 0 ? 0 : 15)) ? 0.0f : e;
   };
 
+  // Most threads (row chunks 2 .. NCH-3 of an interior window, no cell on a global W / E border
+  // column) have all four rows inside the exact region of every half-sweep: for them the
+  // half-sweep runs without per-row tests and with packed fp32 (two cells per FADD2 / FMUL2;
+  // lane for lane the additions and the multiply of upd() below, in its order).
+  // (uniform over the 16 lanes that share a row chunk and shuffle with each other)
+  const bool no_fz = (__ballot_sync(0xffffffffu, fzb != 0) & hmask) == 0;
+  const bool fast = no_fz && r0 >= 2 * S && r0 >= 1 - Y0 && r0 + R <= LH - 2 * S && r0 + R <= h - 1 - Y0;
+
   // one colour of one sweep over the rows of this thread's run that are still exact at time k
   auto half_sweep = [&](int k, auto cpar_tag) {
     constexpr int CPAR = decltype(cpar_tag)::value;
-    const int r_lo = lo(Y0, k) - Y0, r_hi = hi(Y0, LH, h, k) - Y0;
-    if (r0 + R <= r_lo || r0 >= r_hi) return;
     const float *po = P(CPAR ^ 1, r0 - 1) + ci;
     float *pd = P(CPAR, r0) + ci;
+    if (fast) {
+      float4 O[R + 2];
+#pragma unroll
+      for (int j = 0; j < R + 2; j++) O[j] = lds4(po + j * RS);
+      float ed[R];
+#pragma unroll
+      for (int i = 0; i < R; i++)
+        ed[i] = ((CPAR + i) & 1) == 0 ? __shfl_up_sync(hmask, O[i + 1].w, 1, 16) : __shfl_down_sync(hmask, O[i + 1].x, 1, 16);
+#pragma unroll
+      for (int i = 0; i < R; i++) {
+        const int q = (CPAR + i) & 1;
+        const float4 Sv = O[i], A = O[i + 1], Nv = O[i + 2];
+        const float4 Fv = q == 0 ? FE[i] : FO[i];
+        const float4 Wt = q == 0 ? WE[i] : WO[i];
+        // pw + pe of the four cells: q == 0: (ed, A.x, A.y, A.z) + A;  q == 1: A + (A.y, A.z, A.w, ed)
+        f2 a = q == 0 ? add2(pk(ed[i], A.x), pk(A.x, A.y)) : add2(pk(A.x, A.y), pk(A.y, A.z));
+        f2 b = q == 0 ? add2(pk(A.y, A.z), pk(A.z, A.w)) : add2(pk(A.z, A.w), pk(A.w, ed[i]));
+        a = add2(add2(a, pk(Sv.x, Sv.y)), pk(Nv.x, Nv.y));
+        b = add2(add2(b, pk(Sv.z, Sv.w)), pk(Nv.z, Nv.w));
+        a = mul2(add2(a, pk(Fv.x, Fv.y)), pk(Wt.x, Wt.y));
+        b = mul2(add2(b, pk(Fv.z, Fv.w)), pk(Wt.z, Wt.w));
+        *reinterpret_cast<float4 *>(pd + i * RS) = make_float4(lo(a), hi(a), lo(b), hi(b));
+      }
+      return;
+    }
+    const int r_lo = lo_(Y0, k) - Y0, r_hi = hi_(Y0, LH, h, k) - Y0;
+    if (r0 + R <= r_lo || r0 >= r_hi) return;
     // all R+2 rows of the other colour and the R lane-edge values first (independent loads
     // and shuffles in flight together), then the arithmetic
     float4 O[R + 2];
@@ -716,8 +752,8 @@ __global__ void __launch_bounds__(RUN_NT, RUN_NT <= 256 ? 2 : 1) k_mg_run(TileAr
   // setZeroGradientBC on the border cells whose interior neighbour is still exact at
   // time k (see k_mg_tile)
   auto zero_gradient = [&](int k) {
-    const int gx_lo = lo(X0, k), gx_hi = hi(X0, LW, w, k);
-    const int gy_lo = lo(Y0, k), gy_hi = hi(Y0, LH, h, k);
+    const int gx_lo = lo_(X0, k), gx_hi = hi_(X0, LW, w, k);
+    const int gy_lo = lo_(Y0, k), gy_hi = hi_(Y0, LH, h, k);
     const int t = threadIdx.x;
     if (X0 <= 0 && gx_lo == 1)
       for (int gy = gy_lo + t; gy < gy_hi; gy += NT) cell(0, gy) = sel0(mbyte(0, gy), MB_C, cell(1, gy));
@@ -731,24 +767,47 @@ __global__ void __launch_bounds__(RUN_NT, RUN_NT <= 256 ? 2 : 1) k_mg_run(TileAr
         cell(gx, h - 1) = sel0(mbyte(gx, h - 1), MB_C, cell(gx, h - 2));
   };
 
-  if (MODE == MODE_POST && a.zgbc) { // setZeroGradientBC after correct (pressure_solver.cpp:236-239)
+  // Synchronisation between half-sweeps.  A half-sweep reads, of other warps' cells, only the
+  // row directly below its lower row chunk and the row directly above its upper one: rows of
+  // warp - 1 and warp + 1.  So a warp does not wait for the whole CTA but meets its two
+  // neighbours at NAMED barriers (id = upper warp of the pair, 64 threads each, lower pair
+  // first: no cycle).  Warps of a CTA may then be a half-sweep apart, and one warp's
+  // shared-memory latency overlaps another's arithmetic -- with a block barrier all eight start
+  // every phase together and the 4 warps per scheduler stall together (ncu: no pipe above
+  // 65 %, barrier + short-scoreboard stalls).  Windows that hold border cells of a level-0
+  // zero-gradient solve run zero_gradient() between sweeps, a block-wide pattern: they keep the
+  // block barriers; every other window skips them.
+  const bool zg_here = a.zgbc && (X0 <= 0 || w - 1 < X0 + LW || Y0 <= 0 || h - 1 < Y0 + LH);
+  const bool g_pair_sync_off = a.pair_sync == 0;
+  auto pair_sync = [&]() {
+    if (g_pair_sync_off) {
+      __syncthreads();
+      return;
+    }
+    if (warp > 0) asm volatile("bar.sync %0, 64;" ::"r"(warp) : "memory");
+    if (warp < NW - 1) asm volatile("bar.sync %0, 64;" ::"r"(warp + 1) : "memory");
+  };
+
+  if (MODE == MODE_POST && zg_here) { // setZeroGradientBC after correct (pressure_solver.cpp:236-239)
     zero_gradient(0);
     __syncthreads();
   }
 
 #pragma unroll 1
-  for (int s = 0; s < S; s++) {
+  for (int s = 0; s < ((a.dbg & 1) ? 0 : S); s++) {
     half_sweep(2 * s + 1, std::integral_constant<int, 1>()); // "red":   (x+y) odd,  pressure_solver.cpp:35-40
-    __syncthreads();
+    if (zg_here) __syncthreads(); else pair_sync();
     half_sweep(2 * s + 2, std::integral_constant<int, 0>()); // "black": (x+y) even, pressure_solver.cpp:42-47
-    __syncthreads();
-    if (a.zgbc) {
+    if (zg_here) {
+      __syncthreads();
       zero_gradient(2 * s + 2);
       __syncthreads();
+    } else {
+      pair_sync();
     }
   }
 
-  if (MODE == MODE_PRE) {
+  if (MODE == MODE_PRE && !(a.dbg & 2)) {
     // residual (pressure_solver.cpp:101-111, binary flags) of the thread's own cells on
     // rows [HY-1, HY+TY+1), both colours, written over the raw f parked in the R planes
     const int rr_lo = HY - 1, rr_hi = HY + TY + 1;
@@ -1104,6 +1163,17 @@ static void launch_run(const TileArgs &a, cudaStream_t stream, LaunchCounter *lc
   dim3 grid(ceil_div(a.w, G::TX), ceil_div(a.own_hi - a.own_lo, G::TY));
   TileArgs b = a;
   b.pf_dist = g_prefetch_dist;
+  static const int pair = [] {
+    const char *e = getenv("UBGL_MG_PAIR_SYNC");
+    return (e && e[0] == '0') ? 0 : 1;
+  }();
+  b.pair_sync = pair;
+  static const int dbg = [] {
+    const char *e = getenv("UBGL_MG_DBG");
+    return e ? atoi(e) : 0;
+  }();
+  b.dbg = dbg;
+
   UBGL_LAUNCH(lc, kind, level, stream, k_mg_run<MODE><<<grid, RUN_NT, G::smem, stream>>>(b));
 }
 

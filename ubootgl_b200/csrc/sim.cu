@@ -2,6 +2,7 @@
 // simulation.hpp / interpolators.hpp of te42kyfo/ubootgl (file:line per kernel).
 #include "sim.cuh"
 #include "stencils.cuh"
+#include "packed.cuh"
 #include <cstdlib>
 #include <algorithm>
 #include <cmath>
@@ -454,39 +455,9 @@ __global__ void __launch_bounds__(256, 4) k_advect_pair(Grid vx, Grid vy, Grid o
 // (x+1) loads of the vy loop, rows 1..H-2 for both components) as k_advect_vx / vy;
 // binary flags only (the fused step's precondition).
 // ---------------------------------------------------------------------------
-struct f2 { // two fp32 in one 64-bit register pair
-  unsigned long long v;
-};
-__device__ __forceinline__ f2 pk(float lo, float hi) {
-  f2 r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ float lo(f2 a) {
-  float x, y;
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(a.v));
-  return x;
-}
-__device__ __forceinline__ float hi(f2 a) {
-  float x, y;
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(a.v));
-  return y;
-}
-__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
-  f2 r;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
-  return r;
-}
-__device__ __forceinline__ f2 mul2(f2 a, f2 b) {
-  f2 r;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
-  return r;
-}
-
 // cr_weights() of tx (low halves) and ty (high halves) at once: the same operations lane for
 // lane, constants as broadcast scalars (w3 = fma(.., t2, +0) instead of a multiply: equal up to
 // the sign of a zero weight)
-__device__ __forceinline__ f2 bc(float c) { return pk(c, c); }
 __device__ __forceinline__ void cr_weights_xy(float tx, float ty, f2 &w0, f2 &w1, f2 &w2, f2 &w3) {
   const f2 t = pk(tx, ty);
   const f2 t2 = mul2(t, t);
@@ -538,8 +509,8 @@ __device__ __forceinline__ float bicubic_pk(const float *__restrict__ g, int pit
 
 enum { AMB_C = 1, AMB_W = 2, AMB_E = 32, AMB_S = 64, AMB_N = 128 }; // stencil mask bits (mg_fused.cu)
 
-template <bool SLAB>
-__global__ void __launch_bounds__(256, 4) k_advect_xy(Grid vx, Grid vy, Grid vxb, Grid vyb,
+template <bool SLAB, int OCC>
+__global__ void __launch_bounds__(256, OCC) k_advect_xy(Grid vx, Grid vy, Grid vxb, Grid vyb,
                                                       const uint8_t *__restrict__ mask, float *ax, float *ay,
                                                       float half, float full, float4 lim /* vx.w-3, vx.h-3, vy.w-3, vy.h-3 */,
                                                       int y_lo, int y_hi, TapRows tr) {
@@ -552,9 +523,26 @@ __global__ void __launch_bounds__(256, 4) k_advect_xy(Grid vx, Grid vy, Grid vxb
   const bool octx = row_ok && (x0 < vx.w - 8), octy = row_ok && (x0 < vy.w - 8);
   const int pitch = vx.pitch; // shared by every level-0 grid
   const int o = y * pitch + xi;
+  // The stencil-mask byte and the eight RK2 start velocities -- vx / vy at (x, y), (x, y-1),
+  // (x+1, y), (x+1, y-1); the (x+1) loads of vx are flat (simulation.cpp:317-325: x+1 == vx.width
+  // wraps into the next row) -- are requested TOGETHER, before the octet test: the kernel is bound
+  // by the latency of its first-touch loads (ncu: long scoreboard on exactly these two groups),
+  // one round trip instead of two.  Faces in skipped octets load eight values for nothing.
   unsigned m = 0;
+  float ux00 = 0.f, uy00 = 0.f, ux0m = 0.f, uy0m = 0.f, uy10 = 0.f, uy1m = 0.f, ux10 = 0.f, ux1m = 0.f;
   if (row_ok && xi <= W - 2) {
     m = mask[o];
+    const float *px = vx.d + o, *py = vy.d + o;
+    ux00 = px[0]; uy00 = py[0];
+    ux0m = px[-pitch]; uy0m = py[-pitch];
+    uy10 = py[1]; uy1m = py[1 - pitch];
+    if (xi + 1 >= vx.w) {
+      ux10 = vx.d[(y + 1) * pitch + (xi + 1 - vx.w)];
+      ux1m = vx.d[y * pitch + (xi + 1 - vx.w)];
+    } else {
+      ux10 = px[1];
+      ux1m = px[1 - pitch];
+    }
     // accumulators: interiors 1..W-3 x 1..H-2 (vx) and 1..W-2 x 1..H-3 (vy), simulation.cpp:380-394
     if (ax) {
       if (xi <= W - 3) ax[o] = 0.0f;
@@ -569,20 +557,6 @@ __global__ void __launch_bounds__(256, 4) k_advect_xy(Grid vx, Grid vy, Grid vxb
   if (!actx && !acty) return;
 
   const float fC = (m & AMB_C) ? 1.0f : 0.0f, fE = (m & AMB_E) ? 1.0f : 0.0f, fN = (m & AMB_N) ? 1.0f : 0.0f;
-  // RK2 start velocities: vx / vy at (x, y), (x, y-1), (x+1, y), (x+1, y-1); the (x+1) loads of
-  // vx are flat (simulation.cpp:317-325: x+1 == vx.width wraps into the next row)
-  const float *px = vx.d + o, *py = vy.d + o;
-  const float ux00 = px[0], uy00 = py[0];
-  const float ux0m = px[-pitch], uy0m = py[-pitch];
-  const float uy10 = py[1], uy1m = py[1 - pitch];
-  float ux10, ux1m;
-  if (xi + 1 >= vx.w) {
-    ux10 = vx.d[(y + 1) * pitch + (xi + 1 - vx.w)];
-    ux1m = vx.d[y * pitch + (xi + 1 - vx.w)];
-  } else {
-    ux10 = px[1];
-    ux1m = px[1 - pitch];
-  }
   const float fx = (float)xi, fy = (float)y;
 
   if (actx) { // simulation.cpp:246-297
@@ -873,10 +847,29 @@ bool launch_advect(const Grid &vx, const Grid &vy, const Grid &vxbk, const Grid 
   }
   if (variant == 3 && mask) {
     const float4 lim = make_float4((float)vx.w - 3.0f, (float)vx.h - 3.0f, (float)vy.w - 3.0f, (float)vy.h - 3.0f);
-    if (peers)
-      UBGL_LAUNCH(lc, K_ADVECT, LVL, stream, (k_advect_xy<true><<<g, b, 0, stream>>>(vx, vy, vxbk, vybk, mask, ax, ay, half, full, lim, y_lo, y_hi, tr)));
-    else
-      UBGL_LAUNCH(lc, K_ADVECT, LVL, stream, (k_advect_xy<false><<<g, b, 0, stream>>>(vx, vy, vxbk, vybk, mask, ax, ay, half, full, lim, y_lo, y_hi, tr)));
+    // resident CTAs per SM the register budget is cut for.  Measured at 8192^2 (B200): 3: 1.64,
+    // 4: 1.28, 5: 1.28, 6: 1.23, 8: 1.24 ms -- the kernel is latency bound, occupancy wins
+    static const int occ = [] {
+      const char *e = getenv("UBGL_ADVECT_OCC");
+      return e ? atoi(e) : 6;
+    }();
+#define UBGL_ADV_XY(S_, O_) UBGL_LAUNCH(lc, K_ADVECT, LVL, stream, (k_advect_xy<S_, O_><<<g, b, 0, stream>>>(vx, vy, vxbk, vybk, mask, ax, ay, half, full, lim, y_lo, y_hi, tr)))
+    if (peers) {
+      UBGL_ADV_XY(true, 4);
+    } else if (occ == 3) {
+      UBGL_ADV_XY(false, 3);
+    } else if (occ == 5) {
+      UBGL_ADV_XY(false, 5);
+    } else if (occ == 6) {
+      UBGL_ADV_XY(false, 6);
+    } else if (occ == 7) {
+      UBGL_ADV_XY(false, 7);
+    } else if (occ == 8) {
+      UBGL_ADV_XY(false, 8);
+    } else {
+      UBGL_ADV_XY(false, 4);
+    }
+#undef UBGL_ADV_XY
     return ax != nullptr;
   }
   if (variant == 2) {

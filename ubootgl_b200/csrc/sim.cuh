@@ -30,6 +30,9 @@ struct PrestepArgs {
   int bcLo, bcHi;   // BC of the column sides (W, E)
   int bcS, bcN;
   int st_lo, st_hi, own_lo, own_hi; // row slab (cell-grid rows), see common.cuh Rows
+  // frame mode (sim_fused.cu): a 1-D grid over the tiles the register-run kernel does not take --
+  // tile rows by < f_byl and by >= f_byf whole, in between only bx == 0 and bx >= f_bxf
+  int frame, f_nbx, f_byl, f_byf, f_bxf;
 };
 
 

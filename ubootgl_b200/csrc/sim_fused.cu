@@ -18,6 +18,7 @@
 #include "sim.cuh"
 #include "stencils.cuh"
 #include <algorithm>
+#include <cstdlib>
 
 namespace ubgl {
 
@@ -54,7 +55,25 @@ template <int COMP> __global__ void __launch_bounds__(PNT) k_prestep(PrestepArgs
   PrestepSmem &sm = *reinterpret_cast<PrestepSmem *>(smem_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int NW = PNT / 32;
-  const int x0 = blockIdx.x * PTX, y0 = g.own_lo + blockIdx.y * PTY;
+  int tbx = blockIdx.x, tby = blockIdx.y;
+  if (g.frame) { // linear id -> frame tile (see PrestepArgs)
+    int id = blockIdx.x;
+    const int low = g.f_byl * g.f_nbx, cw = 1 + g.f_nbx - g.f_bxf, mid = (g.f_byf - g.f_byl) * cw;
+    if (id < low) {
+      tby = id / g.f_nbx;
+      tbx = id - tby * g.f_nbx;
+    } else if (id < low + mid) {
+      id -= low;
+      tby = g.f_byl + id / cw;
+      const int c = id % cw;
+      tbx = c == 0 ? 0 : g.f_bxf + c - 1;
+    } else {
+      id -= low + mid;
+      tby = g.f_byf + id / g.f_nbx;
+      tbx = id % g.f_nbx;
+    }
+  }
+  const int x0 = tbx * PTX, y0 = g.own_lo + tby * PTY;
   const int X0 = x0 - 4, Y0 = y0 - 2;
   const int gw = g.gw, gh = g.gh;
   const int s_hi = min(gh, g.st_hi), m_hi = min(g.H, g.st_hi), o_hi = min(gh, g.own_hi);
@@ -232,6 +251,131 @@ template <int COMP> __global__ void __launch_bounds__(PNT) k_prestep(PrestepArgs
 }
 
 // ---------------------------------------------------------------------------
+// k_prestep_run<COMP> -- the same two passes for the tiles whose windows touch no border
+// cell (all but a one-tile frame of the grid), entirely in REGISTERS.
+//
+// k_prestep above is bound by the shared-memory pipe (ncu, 8192^2: L1/shared 80 %, DRAM 42 %):
+// every 4-cell group re-reads three 128-bit rows, two scalars and five mask words per pass.
+// Here a warp owns a 128-column strip (lane = 4 consecutive cells, 120 useful) and walks RW rows
+// bottom to top: the rows of v0 = front + accumulator, of the pass-1 result and of the stencil
+// mask it needs are a rolling window of registers (a row is loaded from HBM once, as one
+// 128-bit load per array), the W / E neighbours outside a lane's four cells come from the
+// adjacent lanes by shuffle, and the pass-2 row trails the pass-1 row by one.  No shared
+// memory, no block barrier; the price is pass 1 on two extra rows per strip and 8 idle columns
+// per 128.  Away from the border no setVBCs intervenes between the passes, so there is no BC
+// logic here: the frame tiles keep running k_prestep (launch_prestep).  Per-cell arithmetic and
+// predicate tests are those of k_prestep's pass(): bit-identical results.
+// ---------------------------------------------------------------------------
+template <int COMP>
+__device__ __forceinline__ float4 prestep_row(const float4 &S4, const float4 &C4, const float4 &N4, float wv, float ev,
+                                              unsigned ms, unsigned mc, unsigned mn, unsigned mW, unsigned mE,
+                                              float a, float rden) {
+  const float cc[4] = {C4.x, C4.y, C4.z, C4.w};
+  const float nn[4] = {N4.x, N4.y, N4.z, N4.w};
+  const float ss[4] = {S4.x, S4.y, S4.z, S4.w};
+  const float ww[4] = {wv, C4.x, C4.y, C4.z};
+  const float ee[4] = {C4.y, C4.z, C4.w, ev};
+  float out[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const unsigned bC = (mc >> (8 * j)) & 255u;
+    const unsigned bE = j < 3 ? (mc >> (8 * j + 8)) & 255u : mE;
+    const unsigned bW = j > 0 ? (mc >> (8 * j - 8)) & 255u : mW;
+    const unsigned bN = (mn >> (8 * j)) & 255u, bS = (ms >> (8 * j)) & 255u;
+    auto both = [](unsigned b, unsigned bits) { return (b & bits) == bits; };
+    const float c0 = cc[j];
+    float val;
+    bool mC;
+    if (COMP == 0) { // simulation.cpp:117-127
+      val = both(bE, MB_C | MB_E) ? ee[j] : 0.0f;
+      val = __fadd_rn(both(bC, MB_C | MB_W) ? ww[j] : 0.0f, val);
+      val = __fadd_rn(val, both(bN, MB_C | MB_W) ? nn[j] : -c0);
+      val = __fadd_rn(val, both(bS, MB_C | MB_W) ? ss[j] : -c0);
+      mC = both(bC, MB_C | MB_E);
+    } else { // simulation.cpp:143-153
+      val = both(bC, MB_C | MB_S) ? ss[j] : 0.0f;
+      val = __fadd_rn(both(bN, MB_C | MB_N) ? nn[j] : 0.0f, val);
+      val = __fadd_rn(val, both(bE, MB_C | MB_N) ? ee[j] : -c0);
+      val = __fadd_rn(val, both(bW, MB_C | MB_N) ? ww[j] : -c0);
+      mC = both(bC, MB_C | MB_N);
+    }
+    out[j] = mC ? __fmul_rn(__fmaf_rn(a, val, c0), rden) : 0.0f;
+  }
+  return make_float4(out[0], out[1], out[2], out[3]);
+}
+
+constexpr int PRW = 64; // rows per warp strip
+struct PrestepRunGeom {
+  int bx0, bx1; // interior tile columns [bx0, bx1) of PTX cells
+  int ya, yb;   // interior rows [ya, yb)
+};
+
+// One WARP per block: the strip's row range depends on blockIdx only, so every loop bound and
+// row test below is provably warp-uniform (uniform registers, plain branches around the shuffles).
+template <int COMP>
+__global__ void __launch_bounds__(32) k_prestep_run(PrestepArgs g, PrestepRunGeom q) {
+  const int lane = threadIdx.x;
+  const int bx = q.bx0 + blockIdx.x;
+  const int c0 = q.ya + blockIdx.y * PRW; // first output row of this warp
+  const int c1 = min(c0 + PRW, q.yb);
+  const int gx = bx * PTX - 4 + 4 * lane; // first of this lane's four cells
+  const bool col_ok = gx >= 0 && gx < g.pitch;
+  const bool useful = lane >= 1 && lane <= 30;
+  const int s_hi = min(g.gh, g.st_hi), m_hi = min(g.H, g.st_hi);
+  const int pitch = g.pitch;
+
+  float4 v[4], d[4]; // rolling rows: slot = row & 3
+  unsigned m[4], mWn[4], mEn[4];
+  auto load_row = [&](int r, int k) {
+    float4 A = make_float4(0.f, 0.f, 0.f, 0.f);
+    unsigned mw = 0u;
+    if (col_ok && r >= g.st_lo) {
+      const size_t o = (size_t)r * pitch + gx;
+      if (r < s_hi) {
+        A = *reinterpret_cast<const float4 *>(g.A + o);
+        const float4 ac = *reinterpret_cast<const float4 *>(g.acc + o); // every row here is interior
+        A.x = __fadd_rn(A.x, ac.x);
+        A.y = __fadd_rn(A.y, ac.y);
+        A.z = __fadd_rn(A.z, ac.z);
+        A.w = __fadd_rn(A.w, ac.w);
+      }
+      if (r < m_hi) mw = __ldg(reinterpret_cast<const unsigned *>(g.mask + o));
+    }
+    v[k] = A;
+    m[k] = mw;
+    // mask bytes of the cells left and right of this lane's four
+    mWn[k] = __shfl_up_sync(0xffffffffu, mw, 1) >> 24;
+    mEn[k] = __shfl_down_sync(0xffffffffu, mw, 1) & 255u;
+  };
+  auto west = [&](const float4 &x) { return __shfl_up_sync(0xffffffffu, x.w, 1); };
+  auto east = [&](const float4 &x) { return __shfl_down_sync(0xffffffffu, x.x, 1); };
+
+  // Row r lives in slot r & 3.  The loop starts on a multiple of 4 so that inside the unrolled
+  // body every slot index is a compile-time constant (the arrays stay in registers); the up to
+  // three rows before the first needed one are skipped by uniform tests.
+  // Iteration r: load row r+1; pass 1 on row r (rows c0-1 .. c1); pass 2 on row r-1 (rows c0 .. c1-1).
+  for (int rb = (c0 - 3) & ~3; rb <= c1; rb += 4) {
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int r = rb + u;
+      const int kC = u, kS = (u + 3) & 3, kN = (u + 1) & 3, kS2 = (u + 2) & 3;
+      if (r + 1 >= c0 - 2 && r <= c1) load_row(r + 1, kN);
+      if (r >= c0 - 1 && r <= c1) {
+        const float4 D = prestep_row<COMP>(v[kS], v[kC], v[kN], west(v[kC]), east(v[kC]), m[kS], m[kC], m[kN],
+                                           mWn[kC], mEn[kC], g.a, g.rden);
+        d[kC] = D;
+        if (useful && r >= c0 && r < c1) *reinterpret_cast<float4 *>(g.B + (size_t)r * pitch + gx) = D;
+        if (r - 1 >= c0) { // pass 2 on row r-1: pass-1 rows r-2, r-1, r
+          const float4 O = prestep_row<COMP>(d[kS2], d[kS], D, west(d[kS]), east(d[kS]), m[kS2], m[kS], m[kC],
+                                             mWn[kS], mEn[kS], g.a, g.rden);
+          if (useful) *reinterpret_cast<float4 *>(g.Cout + (size_t)(r - 1) * pitch + gx) = O;
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // setVBCs / setPBC, parallel over the perimeter.  Column phase and row phase are
 // separate launches: the row phase reads the column results at x = 0 / w-1 and
 // wins at the corners, exactly as the reference's loop order.
@@ -379,13 +523,41 @@ __global__ void k_gradient_save(Grid vx, Grid vy, Grid p, const uint8_t *mask, G
 // ---------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------
-void launch_prestep(int comp, const PrestepArgs &g, cudaStream_t stream, LaunchCounter *lc) {
+// 0: k_prestep everywhere; 1 (default): register-run kernel inside, k_prestep on the frame
+static int prestep_variant() {
+  static const int v = [] {
+    const char *e = getenv("UBGL_PRESTEP_VARIANT");
+    return (e && e[0] == '0') ? 0 : 1;
+  }();
+  return v;
+}
+
+void launch_prestep(int comp, const PrestepArgs &g0, cudaStream_t stream, LaunchCounter *lc) {
   static std::atomic<unsigned long long> attr_done0{0}, attr_done1{0};
   ensure_dyn_smem(k_prestep<0>, sizeof(PrestepSmem), attr_done0);
   ensure_dyn_smem(k_prestep<1>, sizeof(PrestepSmem), attr_done1);
+  PrestepArgs g = g0;
   const int rows = std::min(g.gh, g.own_hi) - g.own_lo;
   if (rows <= 0) return;
-  dim3 grid(ceil_div(g.gw, PTX), ceil_div(rows, PTY));
+  const int nbx = ceil_div(g.gw, PTX), nby = ceil_div(rows, PTY);
+  dim3 grid(nbx, nby);
+  g.frame = 0;
+  // tiles whose 128 x 36 window holds no border cell: columns [1, bxf), tile rows [byl, byf)
+  const int bxf = g.gw >= 125 ? std::min(nbx, (g.gw - 125) / PTX + 1) : 0;
+  const int byl = g.own_lo <= 1 ? 1 : 0;
+  const int top = g.gh - 35 - g.own_lo;
+  const int byf = top >= 0 ? std::min(nby, top / PTY + 1) : 0;
+  PrestepRunGeom q{1, bxf, g.own_lo + PTY * byl, std::min(g.own_lo + PTY * byf, std::min(g.gh, g.own_hi))};
+  const bool split = prestep_variant() == 1 && bxf > 1 && byf > byl && q.yb - q.ya >= 2 * PTY;
+  if (split) {
+    g.frame = 1; g.f_nbx = nbx; g.f_byl = byl; g.f_byf = byf; g.f_bxf = bxf;
+    grid = dim3(nbx * nby - (bxf - 1) * (byf - byl), 1);
+    dim3 rg(q.bx1 - q.bx0, ceil_div(q.yb - q.ya, PRW));
+    if (comp == 0)
+      UBGL_LAUNCH(lc, K_PRESTEP, 0, stream, k_prestep_run<0><<<rg, 32, 0, stream>>>(g, q));
+    else
+      UBGL_LAUNCH(lc, K_PRESTEP, 0, stream, k_prestep_run<1><<<rg, 32, 0, stream>>>(g, q));
+  }
   if (comp == 0)
     UBGL_LAUNCH(lc, K_PRESTEP, 0, stream, k_prestep<0><<<grid, PNT, sizeof(PrestepSmem), stream>>>(g));
   else
