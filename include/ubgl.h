@@ -232,6 +232,12 @@ int ubgl_slab_download(ubgl_slab_t *s, int field, float *host);
 int ubgl_slab_set_option(ubgl_slab_t *s, int option, int value); /* UBGL_OPT_VCYCLES */
 int ubgl_slab_set_sinks(ubgl_slab_t *s, const float *xyz, int n);
 int ubgl_slab_step(ubgl_slab_t *s, float dt);
+/* ubgl_sim_step_host for one rank's slab (Simulation::step as sim_loop.cpp:29's caller sees it,
+ * each rank over its own PCIe link): vx_accum / vy_accum mirrors in (arrays over the STORED rows,
+ * ubgl_slab_field_rows; their own rows are cleared like simulation.cpp:384,392), then the OWN
+ * rows of vx, vy, p, vx_current, vy_current are written at their place inside arrays over the
+ * stored rows.  m->flag must be NULL. */
+int ubgl_slab_step_host(ubgl_slab_t *s, float dt, const ubgl_host_mirrors *m);
 int ubgl_slab_sync(ubgl_slab_t *s);
 /* sum of r^2 over the own rows (calculateResidualField); add the ranks, take sqrt */
 int ubgl_slab_residual_sumsq(ubgl_slab_t *s, double *sumsq);

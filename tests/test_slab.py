@@ -117,6 +117,34 @@ def test_one_rank_slab_equals_simulation(ubgl, W, H):
 
 
 @pytest.mark.gpu
+def test_one_rank_slab_step_host_equals_simulation_step_host(ubgl):
+    """ubgl_slab_step_host (accumulator mirrors in, vx / vy / p / *_current mirrors out, packed DMAs)
+    against ubgl_sim_step_host, bit for bit, incl. the clearing of the accumulator mirrors."""
+    from ubootgl_b200 import capi
+    W, H = 600, 333
+    c = cases.sim_case(W, H, seed=77)
+    S = ubgl.SlabSimulation(c["flag"], W, H, 0, 1, lambda b: [b], device=0)
+    G = ubgl.Simulation(c["flag"])
+    for s in (S, G):
+        put = s.set_from_global if s is S else s.set
+        put(capi.VX, c["vx"]); put(capi.VY, c["vy"]); put(capi.P, c["p"])
+    shapes = dict(vx_accum=(H, W - 1), vy_accum=(H - 1, W), vx=(H, W - 1), vy=(H - 1, W), p=(H, W),
+                  vx_current=(H, W - 1), vy_current=(H - 1, W))
+    for k in range(2):
+        bufs = []
+        for s in (S, G):
+            b = {n: np.full(sh, np.nan, np.float32) for n, sh in shapes.items()}
+            b["vx_accum"][:] = c["vx_accum"] * (k + 1)
+            b["vy_accum"][:] = c["vy_accum"] * (k + 1)
+            s.step_host(0.001, **b)
+            bufs.append(b)
+        for n in shapes:
+            assert bits_same(bufs[0][n], bufs[1][n]), (k, n)
+        assert not bufs[0]["vx_accum"][1:-1, 1:-1].any() and bufs[0]["vx_accum"][0].any()  # interior cleared, border kept
+        assert (bufs[0]["vx"] == bufs[0]["vx_current"]).all()
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("nranks,dt", [(2, "0.002"), (2, "0.02"), (4, "0.002"), (4, "0.02")])
 def test_slabs_equal_single_gpu(ubgl, nranks, dt):
     if ubgl.lib.ubgl_device_count() < nranks:

@@ -104,6 +104,7 @@ def _load():
         "ubgl_slab_set_option": (i, [v, i, i]),
         "ubgl_slab_set_sinks": (i, [v, FP, i]),
         "ubgl_slab_step": (i, [v, f]),
+        "ubgl_slab_step_host": (i, [v, f, C.POINTER(HostMirrors)]),
         "ubgl_slab_sync": (i, [v]),
         "ubgl_slab_residual_sumsq": (i, [v, C.POINTER(C.c_double)]),
         "ubgl_slab_launch_count": (ll, [v]),
@@ -580,6 +581,23 @@ class SlabSimulation:
 
     def step(self, dt):
         _ck(lib.ubgl_slab_step(self._h, dt))
+
+    def step_host(self, dt, vx_accum=None, vy_accum=None, vx=None, vy=None, p=None, vx_current=None,
+                  vy_current=None):
+        """One step as a host caller sees it; every array covers this rank's STORED rows of its field
+        (field_rows), inputs are read whole, outputs are written on the own rows."""
+        m = HostMirrors()
+        ids = dict(vx_accum=VX_ACCUM, vy_accum=VY_ACCUM, vx=VX, vy=VY, p=P, vx_current=VX_CURRENT,
+                   vy_current=VY_CURRENT)
+        for name, a in (("vx_accum", vx_accum), ("vy_accum", vy_accum), ("vx", vx), ("vy", vy), ("p", p),
+                        ("vx_current", vx_current), ("vy_current", vy_current)):
+            if a is not None:
+                r0, n, w = self.field_rows(ids[name])
+                if a.dtype != np.float32 or not a.flags["C_CONTIGUOUS"] or a.shape != (n, w):
+                    raise UbglError(f"{name}: need a C-contiguous float32 array of the stored rows {(n, w)}")
+            setattr(m, name, _fp(a) if a is not None else None)
+        m.flag = None
+        _ck(lib.ubgl_slab_step_host(self._h, dt, C.byref(m)))
 
     def sync(self):
         _ck(lib.ubgl_slab_sync(self._h))

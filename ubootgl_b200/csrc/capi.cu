@@ -5,6 +5,7 @@
 #include "sim.cuh"
 #include "slab.cuh"
 #include "capi_internal.cuh"
+#include "hostwork.cuh"
 #include <algorithm>
 #include <cstring>
 #include <memory>
@@ -197,65 +198,6 @@ int ubgl_sim_stage(ubgl_sim_t *sim, int stage, float dt) {
   UBGL_CATCH
 }
 
-// Host side of ubgl_sim_step_host.  Two jobs run on a few host threads while the
-// GPU steps and the DMA engines copy:
-//  * applyAccumulatedVelocity's "accum = 0" (simulation.cpp:384,392): interior rows
-//    1..H-2 x cols 1..W-3 of vx_accum ((W-1) x H) and rows 1..H-3 x cols 1..W-2 of
-//    vy_accum (W x (H-1)), as soon as the upload has consumed the mirrors;
-//  * saveCurrentVelocityFields (simulation.cpp:16-19) for the mirrors: vx_current /
-//    vy_current are byte copies of the final front vx / vy, so they are filled from
-//    the freshly downloaded vx / vy mirror band by band (a host memcpy behind the
-//    D->H copy) instead of crossing PCIe a second time.
-struct HostBand {
-  cudaEvent_t ready = nullptr; // the D->H copy of this band has landed
-  const float *src = nullptr;
-  float *dst = nullptr;
-  size_t bytes = 0;
-};
-
-static void host_side_work(int device, cudaEvent_t uploaded, float *ax, float *ay, int W, int H,
-                           std::vector<HostBand> &bands, cudaError_t *first_err) {
-  const size_t big = (size_t)(16 << 20);
-  size_t total = 0;
-  for (auto &b : bands) total += b.bytes;
-  if (uploaded) total += sizeof(float) * (size_t)W * H * ((ax ? 1 : 0) + (ay ? 1 : 0));
-  unsigned nt = std::thread::hardware_concurrency();
-  nt = std::min(nt ? nt : 1u, 8u);
-  if (total < big) nt = 1;
-  std::vector<cudaError_t> errs(nt, cudaSuccess);
-  auto work = [&](unsigned t) {
-    cudaSetDevice(device);
-    if (uploaded) {
-      cudaError_t e = cudaEventSynchronize(uploaded);
-      if (e != cudaSuccess) errs[t] = e;
-      const int y0 = (int)((long long)H * t / nt), y1 = (int)((long long)H * (t + 1) / nt);
-      if (ax)
-        for (int y = std::max(y0, 1); y < std::min(y1, H - 1); y++)
-          std::memset(ax + (size_t)y * (W - 1) + 1, 0, sizeof(float) * (W - 3));
-      if (ay)
-        for (int y = std::max(y0, 1); y < std::min(y1, H - 2); y++)
-          std::memset(ay + (size_t)y * W + 1, 0, sizeof(float) * (W - 2));
-    }
-    for (size_t b = t; b < bands.size(); b += nt) {
-      cudaError_t e = cudaEventSynchronize(bands[b].ready);
-      if (e != cudaSuccess) {
-        errs[t] = e;
-        continue;
-      }
-      std::memcpy(bands[b].dst, bands[b].src, bands[b].bytes);
-    }
-  };
-  if (nt < 2) {
-    work(0);
-  } else {
-    std::vector<std::thread> th;
-    for (unsigned t = 0; t < nt; t++) th.emplace_back(work, t);
-    for (auto &t : th) t.join();
-  }
-  for (auto e : errs)
-    if (e != cudaSuccess && *first_err == cudaSuccess) *first_err = e;
-}
-
 int ubgl_sim_step_host(ubgl_sim_t *sim, float dt, const ubgl_host_mirrors *m) {
   UBGL_TRY
   SIM(sim);
@@ -334,7 +276,7 @@ int ubgl_sim_step_host(ubgl_sim_t *sim, float dt, const ubgl_host_mirrors *m) {
     }
     cudaError_t herr = cudaSuccess;
     if (uploaded || !bands.empty())
-      host_side_work(S.device, uploaded, m->vx_accum, m->vy_accum, S.W, S.H, bands, &herr);
+      host_side_work(S.device, uploaded, m->vx_accum, m->vy_accum, S.W, S.H, 0, 0, S.H, bands, &herr);
     UBGL_CUDA(herr);
     S.sync();
   } catch (...) {
@@ -682,6 +624,15 @@ int ubgl_slab_download(ubgl_slab_t *s, int field, float *host) {
   UBGL_TRY
   SLAB(s);
   S.download(field, host);
+  UBGL_CATCH
+}
+
+int ubgl_slab_step_host(ubgl_slab_t *s, float dt, const ubgl_host_mirrors *m) {
+  UBGL_TRY
+  SLAB(s);
+  NEED(m, "mirrors");
+  UBGL_REQUIRE(m->flag == nullptr, "slab: a flag change is ubgl_slab_upload(UBGL_FLAG) + reconnect, not part of step_host");
+  S.step_host(dt, SlabSim::HostRows{m->vx_accum, m->vy_accum, m->vx, m->vy, m->p, m->vx_current, m->vy_current});
   UBGL_CATCH
 }
 

@@ -990,6 +990,13 @@ __global__ void k_pack_rows(const float *__restrict__ src, int pitch, int w, flo
   for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < w; x += gridDim.x * blockDim.x)
     dst[y * w + x] = src[y * pitch + x];
 }
+// rows [0, rows) of a pitched array (src = its first row) packed to w floats per row
+void launch_pack_rows(const float *src, int pitch, int w, int rows, float *dst, cudaStream_t stream,
+                      LaunchCounter *lc) {
+  if (rows <= 0) return;
+  dim3 grid(std::min(ceil_div(w, 256), 8), rows);
+  UBGL_LAUNCH(lc, K_OTHER, 0, stream, k_pack_rows<<<grid, 256, 0, stream>>>(src, pitch, w, dst));
+}
 float *DeviceSim::packed(const Grid &g) {
   const size_t n = (size_t)g.w * g.h;
   if (n > cap_pack) {

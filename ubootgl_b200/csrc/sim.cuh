@@ -73,6 +73,9 @@ bool launch_advect(const Grid &vx, const Grid &vy, const Grid &vxb, const Grid &
 void launch_stamp_sinks(const Grid &f, const float *d_sinks, int n, int y_lo, int y_hi,
                         cudaStream_t stream, LaunchCounter *lc);
 
+void launch_pack_rows(const float *src, int pitch, int w, int rows, float *dst, cudaStream_t stream,
+                      LaunchCounter *lc);
+
 struct Sink {
   float x, y, z;
 };

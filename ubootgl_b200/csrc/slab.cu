@@ -1,5 +1,6 @@
 // slab.cu -- row-slab decomposed Simulation::step (see slab.cuh).
 #include "slab.cuh"
+#include "hostwork.cuh"
 #include "stencils.cuh"
 #include <algorithm>
 #include <cmath>
@@ -292,6 +293,7 @@ SlabSim::~SlabSim() {
   for (int r = 0; r < SLAB_MAXRANKS; r++)
     if (peer_arena[r] && r != plan.rank) cudaIpcCloseMemHandle(peer_arena[r]);
   if (d_sinks) cudaFree(d_sinks);
+  if (d_pack) cudaFree(d_pack);
   if (arena) cudaFree(arena);
   if (stream) cudaStreamDestroy(stream);
 }
@@ -694,6 +696,79 @@ void SlabSim::step(float dt_) {
                        stream, &lc);
   borders(false, true);
   exchange({xf(vxb[ixf], 0), xf(vyb[iyf], 0)}, 4); // entry invariant of the next step
+}
+
+// The slab analogue of ubgl_sim_step_host (capi.cu), one rank's share: every rank drives its own
+// PCIe link.  H->D: the accumulator mirrors, stored rows (ghost rows straight from the caller's
+// arrays, no exchange).  D->H: the OWN rows of vx, vy, p, packed on the device to the
+// reference's unpadded rows and sent as contiguous DMAs (a pitched 2-D copy is slower,
+// tools/pcie_probe.py); vx_current / vy_current are byte copies of the final vx / vy
+// (saveCurrentVelocityFields is a memcpy, simulation.cpp:16-19): host threads fill those
+// mirrors from the vx / vy bands as they land instead of a second PCIe crossing, and clear the
+// accumulator mirrors (:384,392) while the GPU steps.
+void SlabSim::step_host(float dt_, const HostRows &m) {
+  const Rows R = plan.rows(0);
+  auto up = [&](const Grid &g, const float *host) {
+    const int n = std::min(R.st_hi, g.h) - R.st_lo;
+    UBGL_CUDA(cudaMemcpy2DAsync(&g.at(0, R.st_lo), sizeof(float) * g.pitch, host, sizeof(float) * g.w,
+                                sizeof(float) * g.w, n, cudaMemcpyHostToDevice, stream));
+  };
+  if (m.vx_accum) up(vx_accum, m.vx_accum);
+  if (m.vy_accum) up(vy_accum, m.vy_accum);
+  cudaEvent_t uploaded = nullptr;
+  std::vector<HostBand> bands;
+  auto cleanup = [&]() {
+    if (uploaded) cudaEventDestroy(uploaded);
+    for (auto &b : bands)
+      if (b.ready) cudaEventDestroy(b.ready);
+  };
+  try {
+    if (m.vx_accum || m.vy_accum) {
+      UBGL_CUDA(cudaEventCreateWithFlags(&uploaded, cudaEventDisableTiming));
+      UBGL_CUDA(cudaEventRecord(uploaded, stream));
+    }
+    step(dt_);
+    if (!d_pack && (m.vx || m.vy || m.p))
+      UBGL_CUDA(cudaMalloc(&d_pack, sizeof(float) * (size_t)W * (R.own_hi - R.own_lo)));
+    struct Out { const Grid *g; float *dst, *cur; };
+    const Out outs[3] = {{&vxb[ixf], m.vx, m.vx_current}, {&vyb[iyf], m.vy, m.vy_current}, {&p, m.p, nullptr}};
+    for (const Out &o : outs) {
+      if (!o.dst && !o.cur) continue;
+      const Grid &g = *o.g;
+      const int y_lo = R.own_lo, y_hi = std::min(R.own_hi, g.h), n = y_hi - y_lo;
+      if (n <= 0) continue;
+      // the packed buffer is reused field after field: stream order keeps pack k+1 behind copy k
+      launch_pack_rows(&g.at(0, y_lo), g.pitch, g.w, n, d_pack, stream, &lc);
+      float *dst = o.dst ? o.dst : o.cur; // only the *_current mirror wanted: it takes the DMA itself
+      const size_t off = (size_t)(y_lo - R.st_lo) * g.w, row = sizeof(float) * (size_t)g.w;
+      const int nb = (o.dst && o.cur) ? std::min(16, n) : 1;
+      for (int b = 0; b < nb; b++) {
+        const int r0 = (int)((long long)n * b / nb), r1 = (int)((long long)n * (b + 1) / nb);
+        UBGL_CUDA(cudaMemcpyAsync(dst + off + (size_t)r0 * g.w, d_pack + (size_t)r0 * g.w, row * (size_t)(r1 - r0),
+                                  cudaMemcpyDeviceToHost, stream));
+        if (o.dst && o.cur) {
+          HostBand hb;
+          UBGL_CUDA(cudaEventCreateWithFlags(&hb.ready, cudaEventDisableTiming));
+          bands.push_back(hb);
+          HostBand &k = bands.back();
+          UBGL_CUDA(cudaEventRecord(k.ready, stream));
+          k.src = o.dst + off + (size_t)r0 * g.w;
+          k.dst = o.cur + off + (size_t)r0 * g.w;
+          k.bytes = row * (size_t)(r1 - r0);
+        }
+      }
+    }
+    cudaError_t herr = cudaSuccess;
+    if (uploaded || !bands.empty())
+      host_side_work(device, uploaded, m.vx_accum, m.vy_accum, W, H, R.st_lo, R.own_lo, R.own_hi, bands, &herr);
+    UBGL_CUDA(herr);
+    UBGL_CUDA(cudaStreamSynchronize(stream));
+    check_err();
+  } catch (...) {
+    cleanup();
+    throw;
+  }
+  cleanup();
 }
 
 double SlabSim::residual_sumsq() {

@@ -82,6 +82,13 @@ public:
   void upload(int id, const float *host);   // host covers the stored rows, unpadded
   void download(int id, float *host);
   void step(float dt);
+  // Simulation::step as a host caller sees it: accumulator mirrors in (stored rows, then their
+  // own rows are cleared), vx, vy, p, vx_current, vy_current mirrors out (own rows, written at
+  // their place inside arrays that cover the stored rows); any pointer may be null
+  struct HostRows {
+    float *vx_accum, *vy_accum, *vx, *vy, *p, *vx_current, *vy_current;
+  };
+  void step_host(float dt, const HostRows &m);
   void sync();
   double residual_sumsq(); // sum of r^2 over the own rows (caller adds the ranks and takes sqrt)
 
@@ -148,6 +155,7 @@ private:
   float *d_sinks = nullptr;
   int cap_sinks = 0;
   double *d_partials = nullptr, *d_sum = nullptr;
+  float *d_pack = nullptr; // own rows of one field, unpadded: the source of contiguous D->H copies
 };
 
 // halo kernels (slab.cu)
