@@ -220,6 +220,12 @@ typedef struct ubgl_slab ubgl_slab_t;
 /* pure host arithmetic, no CUDA: the decomposition a (W,H,nranks) run uses */
 int ubgl_slab_plan(int W, int H, int nranks, int rank, int *dist_levels, int *ghost, int *own_lo,
                    int *own_hi, int *st_lo, int *st_hi);
+/* Load balance: relative cost of every level-0 row (H positive floats; NULL: equal rows) for the
+ * plans made from now on in this process -- ubgl_slab_plan and ubgl_slab_create place the cuts at
+ * equal weight per rank (still multiples of 2^dist_levels).  The reference's advect skips octets
+ * without fluid (simulation.cpp:254-256), so a caller weights a row by its fluid fraction.  Every
+ * rank must set the same weights. */
+int ubgl_slab_set_row_weights(const float *weights, int H);
 int ubgl_slab_create(const float *flag_stored_rows, int W, int H, float pwidth, float mu, int device,
                      int rank, int nranks, ubgl_slab_t **out);
 int ubgl_slab_destroy(ubgl_slab_t *s);

@@ -67,6 +67,23 @@ def channel_flag_rows(W, H, y0, y1, seed=1234, ndiscs=32, radius=None, closed_bo
     return rows
 
 
+def channel_row_fluid_fraction(W, H, seed=1234, ndiscs=32, radius=None):
+    """Fluid fraction of every row of channel_flag(W, H, ...) from the disc list alone (chords;
+    overlapping discs are counted twice, which is immaterial for load balancing)."""
+    g = LCG(seed)
+    r = (H / 32.0) if radius is None else radius
+    solid = np.zeros(H, np.float64)
+    y = np.arange(H, dtype=np.float64)
+    for _ in range(ndiscs):
+        cx = (0.1 + 0.8 * g.u()) * W
+        cy = (0.15 + 0.7 * g.u()) * H
+        d2 = r * r - (y - cy) ** 2
+        solid += np.where(d2 > 0, 2.0 * np.sqrt(np.maximum(d2, 0.0)), 0.0)
+    frac = 1.0 - np.minimum(solid, W) / W
+    frac[0] = frac[H - 1] = 0.0
+    return frac
+
+
 def dipole_rhs(flag, g, n=64, amp=1000.0):
     """Zero-sum dipoles f(x,y)=+amp, f(x+3,y)=-amp at LCG positions in fluid."""
     H, W = flag.shape

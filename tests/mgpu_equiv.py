@@ -21,7 +21,7 @@ FIELDS = (("vx", "VX", 0), ("vy", "VY", 1), ("p", "P", 0), ("vxc", "VX_CURRENT",
           ("vxb", "VXB", 0), ("f", "F", 0), ("ax", "VX_ACCUM", 0))
 
 
-def check(W, H, steps, dt, rank, world, dev, verbose=True):
+def check(W, H, steps, dt, rank, world, dev, verbose=True, skew=False):
     """Runs `steps` steps of the seeded W x H case as `world` row slabs (all ranks) and as ONE
     single-GPU Simulation (rank 0), and compares 8 fields bit for bit (up to the sign of zero)
     plus the residual norm.  Collective: every rank must call it.  Returns a dict (same on all
@@ -31,9 +31,15 @@ def check(W, H, steps, dt, rank, world, dev, verbose=True):
 
     c = cases.sim_case(W, H, seed=11, ndiscs=9, radius=H / 17.0)
     sinks = [[0.4, 0.4 * H / W, 120.0], [0.2, 0.7 * H / W, 60.0]]
-    plan = u.slab_plan(W, H, world, rank)
-    S = u.SlabSimulation(c["flag"][plan["st_lo"]:plan["st_hi"]], W, H, rank, world,
-                         slab_boot.blob_exchange(), device=dev)
+    if skew:  # unequal slab heights (ubgl_slab_set_row_weights): rows get cheaper towards the top
+        u.slab_set_row_weights(np.linspace(1.6, 0.6, H).astype(np.float32))
+    try:
+        plan = u.slab_plan(W, H, world, rank)
+        S = u.SlabSimulation(c["flag"][plan["st_lo"]:plan["st_hi"]], W, H, rank, world,
+                             slab_boot.blob_exchange(), device=dev)
+    finally:
+        if skew:
+            u.slab_set_row_weights(None)
     for fld, key in ((capi.VX, "vx"), (capi.VY, "vy"), (capi.VX_ACCUM, "vx_accum"),
                      (capi.VY_ACCUM, "vy_accum"), (capi.P, "p")):
         S.set_from_global(fld, c[key])
@@ -77,7 +83,7 @@ def check(W, H, steps, dt, rank, world, dev, verbose=True):
                 print(f"MISMATCH residual norm: slabs {resn} single {res1}", flush=True)
     nbad = int(slab_boot.allreduce_max(float(len(bad_fields))))
     return {"bitwise_ok": nbad == 0, "fields": len(FIELDS), "ranks": world, "grid": [W, H], "steps": steps,
-            "dt": dt, "mismatched_fields": bad_fields if rank == 0 else None, "exchanges": ex,
+            "dt": dt, "rows": plan["own_hi"] - plan["own_lo"], "mismatched_fields": bad_fields if rank == 0 else None, "exchanges": ex,
             "halo_mb": hb / 1e6, "dist_levels": plan["dist_levels"], "residual": resn}
 
 
@@ -93,7 +99,7 @@ def main():
     rank, world = slab_boot.init_distributed("gloo")
     dev = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(dev)
-    r = check(W, H, steps, dt, rank, world, dev)
+    r = check(W, H, steps, dt, rank, world, dev, skew=len(sys.argv) > 5 and sys.argv[5] == "skew")
     if rank == 0:
         print(f"MGPU_EQUIV {'OK' if r['bitwise_ok'] else 'FAIL'} {W}x{H} ranks={world} steps={steps} dt={dt} "
               f"dist_levels={r['dist_levels']} exchanges={r['exchanges']} halo_MB={r['halo_mb']:.1f} "

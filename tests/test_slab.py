@@ -53,6 +53,32 @@ def test_flag_rows_generator_matches_global():
         assert (rows == f[p["st_lo"]:p["st_hi"]]).all()
 
 
+def test_weighted_plan_balances_fluid_rows():
+    """ubgl_slab_set_row_weights: cuts at equal weight, still aligned, ordered, covering; reset restores."""
+    import ubootgl_b200 as u
+    W = H = 32768
+    base = [u.slab_plan(W, H, 8, r) for r in range(8)]
+    frac = cases.channel_row_fluid_fraction(W, H, seed=1234)
+    wgt = (0.73 + 0.27 * frac).astype(np.float32)
+    try:
+        u.slab_set_row_weights(wgt)
+        plans = [u.slab_plan(W, H, 8, r) for r in range(8)]
+    finally:
+        u.slab_set_row_weights(None)
+    assert [u.slab_plan(W, H, 8, r) for r in range(8)] == base
+    align = 1 << plans[0]["dist_levels"]
+    assert plans[0]["own_lo"] == 0 and plans[-1]["own_hi"] == H
+    for a, b in zip(plans, plans[1:]):
+        assert a["own_hi"] == b["own_lo"] and a["own_hi"] % align == 0
+    cost = [float(wgt[p["own_lo"]:p["own_hi"]].sum()) for p in plans]
+    cost0 = [float(wgt[p["own_lo"]:p["own_hi"]].sum()) for p in base]
+    assert max(cost) / min(cost) < max(cost0) / min(cost0)       # better balanced than equal heights
+    assert max(cost) / (sum(cost) / 8) < 1.0 + 1.5 * align * float(wgt.max()) / (sum(cost) / 8)
+    # the obstacle-free edge ranks got fewer rows than the middle ones
+    rows = [p["own_hi"] - p["own_lo"] for p in plans]
+    assert rows[0] < rows[3] and rows[7] < rows[4]
+
+
 _GLOO_WORKER = r"""
 import os, sys
 sys.path.insert(0, {root!r})
@@ -145,12 +171,12 @@ def test_one_rank_slab_step_host_equals_simulation_step_host(ubgl):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("nranks,dt", [(2, "0.002"), (2, "0.02"), (4, "0.002"), (4, "0.02")])
+@pytest.mark.parametrize("nranks,dt", [(2, "0.002"), (2, "0.02"), (4, "0.002"), (4, "0.02"), (2, "0.002 skew"), (4, "0.02 skew")])
 def test_slabs_equal_single_gpu(ubgl, nranks, dt):
     if ubgl.lib.ubgl_device_count() < nranks:
         pytest.skip(f"needs {nranks} GPUs (run under gpurun --gpus {nranks})")
     cmd = ["timeout", "600", sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
            f"--nproc-per-node={nranks}", "--master-addr", "127.0.0.1", "--master-port", str(29540 + nranks),
-           os.path.join(ROOT, "tests", "mgpu_equiv.py"), "1000", "1536", "3", dt]
+           os.path.join(ROOT, "tests", "mgpu_equiv.py"), "1000", "1536", "3"] + dt.split()
     out = subprocess.run(cmd, capture_output=True, text=True, cwd=ROOT)
     assert out.returncode == 0 and "MGPU_EQUIV OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]

@@ -104,6 +104,7 @@ def _load():
         "ubgl_slab_set_option": (i, [v, i, i]),
         "ubgl_slab_set_sinks": (i, [v, FP, i]),
         "ubgl_slab_step": (i, [v, f]),
+        "ubgl_slab_set_row_weights": (i, [FP, i]),
         "ubgl_slab_step_host": (i, [v, f, C.POINTER(HostMirrors)]),
         "ubgl_slab_sync": (i, [v]),
         "ubgl_slab_residual_sumsq": (i, [v, C.POINTER(C.c_double)]),
@@ -497,6 +498,15 @@ class MG:
 
     def launch_count(self):
         return lib.ubgl_mg_launch_count(self._h)
+
+
+def slab_set_row_weights(weights):
+    """Relative cost of every level-0 row for the plans made from now on (None: equal rows)."""
+    if weights is None:
+        _ck(lib.ubgl_slab_set_row_weights(None, 0))
+        return
+    w = _f32(weights)
+    _ck(lib.ubgl_slab_set_row_weights(_fp(w), len(w)))
 
 
 def slab_plan(W, H, nranks, rank):

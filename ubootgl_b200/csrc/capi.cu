@@ -566,6 +566,12 @@ int ubgl_slab_plan(int W, int H, int nranks, int rank, int *dist_levels, int *gh
   UBGL_CATCH
 }
 
+int ubgl_slab_set_row_weights(const float *weights, int H) {
+  UBGL_TRY
+  set_slab_row_weights(weights, H);
+  UBGL_CATCH
+}
+
 int ubgl_slab_create(const float *flag, int W, int H, float pwidth, float mu, int device, int rank,
                      int nranks, ubgl_slab_t **out) {
   UBGL_TRY

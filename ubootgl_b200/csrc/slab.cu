@@ -20,6 +20,21 @@ static int slab_min_rows() {
   return v >= 32 ? v : 32;
 }
 
+// Row weights of the next plans (ubgl_slab_set_row_weights): relative cost of a level-0 row.
+// The advect pass skips octets without fluid (simulation.cpp:254-256), so rows through obstacles
+// are cheaper than open-channel rows; with equal-height slabs the obstacle-free ranks are the
+// slowest and every halo exchange waits for them.  Process-wide, like the option env vars.
+static std::vector<double> g_row_weight_prefix; // prefix sums, H + 1 entries; empty: equal rows
+void set_slab_row_weights(const float *w, int H) {
+  g_row_weight_prefix.clear();
+  if (!w || H <= 0) return;
+  g_row_weight_prefix.resize((size_t)H + 1, 0.0);
+  for (int y = 0; y < H; y++) {
+    UBGL_REQUIRE(w[y] > 0.0f, "slab: row weights must be positive");
+    g_row_weight_prefix[y + 1] = g_row_weight_prefix[y] + (double)w[y];
+  }
+}
+
 SlabPlan make_slab_plan(int W, int H, int nranks, int rank) {
   UBGL_REQUIRE(nranks >= 1 && nranks <= SLAB_MAXRANKS, "slab: 1..8 ranks");
   UBGL_REQUIRE(rank >= 0 && rank < nranks, "slab: bad rank");
@@ -44,6 +59,18 @@ SlabPlan make_slab_plan(int W, int H, int nranks, int rank) {
   P.cuts.resize(nranks + 1);
   for (int r = 0; r < nranks; r++) P.cuts[r] = (int)((long long)H * r / nranks) / align * align;
   P.cuts[nranks] = H;
+  if ((int)g_row_weight_prefix.size() == H + 1 && nranks > 1) {
+    // equal WEIGHT per rank: cut r at the aligned row whose prefix weight is nearest r/nranks of the total
+    const std::vector<double> &pre = g_row_weight_prefix;
+    for (int r = 1; r < nranks; r++) {
+      const double target = pre[H] * r / nranks;
+      int y = (int)(std::lower_bound(pre.begin(), pre.end(), target) - pre.begin());
+      int c = (y + align / 2) / align * align;
+      c = std::max(c, P.cuts[r - 1] + align);
+      c = std::min(c, H - (nranks - r) * align);
+      P.cuts[r] = c;
+    }
+  }
   for (int r = 0; r < nranks; r++)
     UBGL_REQUIRE(((P.cuts[r + 1] - P.cuts[r]) >> (n - 1)) >= 2 * P.ghost,
                  "slab: slab thinner than two halos on the coarsest distributed level");

@@ -41,6 +41,8 @@ struct SlabPlan {
 // Pure host arithmetic (no CUDA): throws ArgError if the grid is too small to
 // give every rank a slab.
 SlabPlan make_slab_plan(int W, int H, int nranks, int rank);
+// relative cost of every level-0 row for the plans made from now on (nullptr: equal rows)
+void set_slab_row_weights(const float *w, int H);
 
 constexpr int SLAB_MAXSEG = 16;
 constexpr int SLAB_MAXRANKS = 8;

@@ -29,7 +29,8 @@ def run(args, name):
     # CFL ~ 1-3 (back-traces stay in the ghost rows) and CFL ~ 25-75 (taps served by NVLink
     # peer loads).  Every scaling number below rests on this equivalence; a mismatch aborts. ----
     from tests import mgpu_equiv
-    equiv_runs = [mgpu_equiv.check(1000, 1536, 2, dt_, rank, world, dev, verbose=(rank == 0)) for dt_ in (0.002, 0.02)]
+    equiv_runs = [mgpu_equiv.check(1000, 1536, 2, dt_, rank, world, dev, verbose=(rank == 0), skew=sk)
+                  for dt_, sk in ((0.002, False), (0.02, True))]  # the second with unequal (weighted) slab heights
     equiv = {"bitwise_ok": all(r["bitwise_ok"] for r in equiv_runs), "fields": equiv_runs[0]["fields"],
              "ranks": world, "grid": equiv_runs[0]["grid"], "steps": 2, "dt": [r["dt"] for r in equiv_runs],
              "dist_levels": equiv_runs[0]["dist_levels"], "exchanges": [r["exchanges"] for r in equiv_runs],
@@ -43,7 +44,14 @@ def run(args, name):
                               "equiv": equiv}), flush=True)
         raise SystemExit(3)
 
+    # load balance: the advect pass (27 % of a step) skips octets without fluid, every other pass
+    # costs the same per row; cuts at equal weight instead of equal height (identical on every
+    # rank: computed from the generator's disc list)
+    if os.environ.get("UBGL_SLAB_BALANCE", "1") != "0":
+        frac = cases.channel_row_fluid_fraction(W, H, seed=1234)
+        u.slab_set_row_weights((0.73 + 0.27 * frac).astype(np.float32))
     plan = u.slab_plan(W, H, world, rank)
+    all_rows = [u.slab_plan(W, H, world, r) for r in range(world)]
     dt = float(np.float32(bench.PWIDTH) / np.float32(W - 1))  # dt = h, CFL ~ 1
     # synthetic input, generated slab-wise: only the rows this rank stores
     flag = cases.channel_flag_rows(W, H, plan["st_lo"], plan["st_hi"], seed=1234)
@@ -141,6 +149,7 @@ def run(args, name):
         "config": bench.workload_config(name, parallelism=f"row slabs x{world}"),
         "run_info": {"residual_after": res_after, "decomposition": f"{plan['dist_levels']} distributed MG levels, "
                      f"coarser levels replicated, ghost {plan['ghost']} rows",
+                     "rows_per_rank": [r["own_hi"] - r["own_lo"] for r in all_rows],
                      "halo_mb_per_step_all_ranks": halo_mb, "exchanges_per_step": (x1 - x0) / K,
                      "scaling_note": "strong scaling is defined on this workload; its 1-GPU base is the "
                                      "strong_scaling_base object of the N = 1 line (bench.py --gpus 1)"},
