@@ -13,6 +13,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -214,6 +215,51 @@ __device__ __forceinline__ void bilinear_scatter(const Grid &g, float cx, float 
   atomicAdd(&g.at(ix, iy), ax * ay * v);
 }
 
+// ---- two-level bins (UBGL_ITEMS_VARIANT = 2, default) -----------------------------------
+// The reference tests an item against EVERY position of its x-bin (:167-181): O(N^2 / 100),
+// 10^10 pair tests for 10^6 items, 65 % of the round-1 explosion frame.  Only pairs closer than
+// sqrt(size.x size.y 0.4) of the testing item contribute, so the x-bins are cut into y-cells at
+// least as tall as the largest such radius: an item then needs the cells y-1, y, y+1 of its
+// x-bin only.  Sort key = (x-bin, y-cell); the stable sort keeps array order inside a cell, and
+// the three cells are walked as a 3-way MERGE by array index, so the contacts of an item are
+// still added in the reference's push_back order and the sums round as in the reference.
+constexpr int ITEMS_NY = 2048;
+// r2max = max over the items of size.x * size.y * 0.4 (positive floats order like their bits)
+__global__ void k_items_r2max(const Item *items, int n, unsigned *r2max_bits) {
+  float m = 0.0f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    m = fmaxf(m, items[i].size[0] * items[i].size[1] * 0.4f);
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(r2max_bits, __float_as_uint(m));
+}
+// height of a y-cell: the largest interaction radius, but no more than ITEMS_NY cells over the domain
+__device__ __forceinline__ float items_cell_height(unsigned r2max_bits, float yrange) {
+  return fmaxf(sqrtf(__uint_as_float(r2max_bits)) * 1.0001f, yrange / (float)ITEMS_NY);
+}
+__device__ __forceinline__ int items_ycell(float y, float cy) {
+  const float c = floorf(y / cy);
+  return (int)fminf(fmaxf(c, 0.0f), (float)(ITEMS_NY - 1)); // monotone in y: |dy| < cy  =>  cells differ by <= 1
+}
+__global__ void k_items_key2(const Item *items, int n, const unsigned *r2max_bits, float yrange, unsigned *key, int *idx) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float cy = items_cell_height(*r2max_bits, yrange);
+  const unsigned xb = (unsigned)((unsigned long long)(long long)(int)(items[i].pos[0] * 100.0f) % 100ull); // :157
+  key[i] = xb * ITEMS_NY + (unsigned)items_ycell(items[i].pos[1], cy);
+  idx[i] = i;
+}
+// off[q] = first sorted slot whose key is >= q, q = 0 .. nkeys (off[nkeys] = n)
+__global__ void k_items_offsets2(const unsigned *skey, int n, int nkeys, int *off) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q > nkeys) return;
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (skey[mid] < (unsigned)q) lo = mid + 1; else hi = mid;
+  }
+  off[q] = lo;
+}
+
 // One thread per SORTED slot, so the lanes of a warp share a bin: the repulsion
 // loop (:167-181) walks the bin's positions in array order (stable sort == the
 // reference's push_back order).  It is the O(N^2/100) part of the reference
@@ -222,26 +268,66 @@ __device__ __forceinline__ void bilinear_scatter(const Grid &g, float cx, float 
 // reads them as warp-uniform broadcasts; each thread still visits exactly its own
 // bin's entries, in order, so the sums round as before.
 constexpr int ITEMS_NT = 128, ITEMS_TILE = 512;
+template <int VARIANT>
 __global__ void __launch_bounds__(ITEMS_NT) k_items_advect(Item *items, const int *order, const unsigned char *sbin,
-                                                           const int *off, const float2 *spos, int n, float game_dt,
-                                                           Grid flag, Grid vx, Grid vy, Grid p, Grid ax, Grid ay,
-                                                           float pwidth, float h) {
-  __shared__ float2 tile[ITEMS_TILE];
+                                                           const unsigned *skey, const int *off, const float2 *spos,
+                                                           int n, float game_dt, Grid flag, Grid vx, Grid vy, Grid p,
+                                                           Grid ax, Grid ay, float pwidth, float h) {
+  __shared__ float2 tile[VARIANT == 1 ? ITEMS_TILE : 1];
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = k < n;
   Item it;
   int qs = 0, qe = 0;
   if (live) {
     it = items[order[k]];
-    const int b = sbin[k];
-    qs = off[b];
-    qe = off[b + 1];
+    if (VARIANT == 1) {
+      const int b = sbin[k];
+      qs = off[b];
+      qe = off[b + 1];
+    }
   }
   float rfx = 0.0f, rfy = 0.0f;
   int contacts = 0;
   const float r2 = live ? it.size[0] * it.size[1] * 0.4f : 0.0f, lmin = live ? 0.1f * it.size[0] : 0.0f;
   const float px0 = live ? it.pos[0] : 0.0f, py0 = live ? it.pos[1] : 0.0f;
-  {
+  if (VARIANT == 2) {
+    if (live) {
+      // cells (xb, yc-1), (xb, yc), (xb, yc+1): three runs of sorted slots, each in array order
+      const unsigned key = skey[k];
+      const int yc = (int)(key % ITEMS_NY), kb = (int)(key - yc);
+      int cur[3], end[3], val[3];
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        const int y = yc - 1 + c;
+        const bool ok = y >= 0 && y < ITEMS_NY;
+        cur[c] = ok ? off[kb + y] : 0;
+        end[c] = ok ? off[kb + y + 1] : 0;
+        val[c] = cur[c] < end[c] ? order[cur[c]] : 0x7fffffff;
+      }
+      while (true) {
+        const int m = min(val[0], min(val[1], val[2]));
+        if (m == 0x7fffffff) break;
+        const int c = val[0] == m ? 0 : (val[1] == m ? 1 : 2);
+        const int j = c == 0 ? cur[0] : (c == 1 ? cur[1] : cur[2]);
+        const float2 o = __ldg(&spos[j]);
+        const float dx = px0 - o.x, dy = py0 - o.y;
+        const float d2 = dx * dx + dy * dy;
+        if (d2 < r2) { // :170-180
+          const float len = fmaxf(lmin, sqrtf(d2));
+          rfx += 0.0001f * (dx / len / len);
+          rfy += 0.0001f * (dy / len / len);
+          contacts++;
+        }
+        const int nj = j + 1;
+#pragma unroll
+        for (int q = 0; q < 3; q++)
+          if (q == c) {
+            cur[q] = nj;
+            val[q] = nj < end[q] ? order[nj] : 0x7fffffff;
+          }
+      }
+    }
+  } else {
     const int kf = blockIdx.x * blockDim.x, kl = min(kf + (int)blockDim.x, n) - 1;
     const int qlo = off[sbin[kf]], qhi = off[sbin[kl] + 1]; // slots any thread of this block visits
     for (int base = qlo; base < qhi; base += ITEMS_TILE) {
@@ -609,12 +695,15 @@ struct ubgl_items {
   unsigned char *bin = nullptr, *sbin = nullptr;
   int *idx = nullptr, *order = nullptr, *off = nullptr;
   float2 *spos = nullptr;
+  unsigned *key = nullptr, *skey = nullptr, *r2max = nullptr; // two-level bins
+  int *off2 = nullptr;
   void *tmp = nullptr;
   size_t tmp_bytes = 0;
   void release() {
     cudaFree(items); cudaFree(bin); cudaFree(sbin); cudaFree(idx); cudaFree(order); cudaFree(off);
-    cudaFree(spos); cudaFree(tmp);
+    cudaFree(spos); cudaFree(tmp); cudaFree(key); cudaFree(skey); cudaFree(r2max); cudaFree(off2);
     items = nullptr; bin = sbin = nullptr; idx = order = off = nullptr; spos = nullptr; tmp = nullptr;
+    key = skey = r2max = nullptr; off2 = nullptr;
     tmp_bytes = 0; cap = 0;
   }
   ~ubgl_items() {
@@ -774,7 +863,14 @@ int ubgl_items_upload(ubgl_items_t *it, const ubgl_item *items, int n) {
     UBGL_CUDA(cudaMalloc(&it->order, sizeof(int) * n));
     UBGL_CUDA(cudaMalloc(&it->off, sizeof(int) * 101));
     UBGL_CUDA(cudaMalloc(&it->spos, sizeof(float2) * n));
-    UBGL_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, it->tmp_bytes, it->bin, it->sbin, it->idx, it->order, n, 0, 7));
+    UBGL_CUDA(cudaMalloc(&it->key, sizeof(unsigned) * n));
+    UBGL_CUDA(cudaMalloc(&it->skey, sizeof(unsigned) * n));
+    UBGL_CUDA(cudaMalloc(&it->r2max, sizeof(unsigned)));
+    UBGL_CUDA(cudaMalloc(&it->off2, sizeof(int) * (100 * ITEMS_NY + 1)));
+    size_t t1 = 0, t2 = 0;
+    UBGL_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, t1, it->bin, it->sbin, it->idx, it->order, n, 0, 7));
+    UBGL_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, t2, it->key, it->skey, it->idx, it->order, n, 0, 18));
+    it->tmp_bytes = std::max(t1, t2);
     UBGL_CUDA(cudaMalloc(&it->tmp, it->tmp_bytes));
   }
   it->n = n;
@@ -802,16 +898,40 @@ int ubgl_items_advect_simple(ubgl_items_t *it, ubgl_sim_t *sim, float game_dt) {
   if (n == 0) return UBGL_OK;
   cudaStream_t st = S.stream;
   const int g = ceil_div(n, 256);
+  static const int variant = [] { // 1: one level of x-bins, every pair of a bin tested; 2 (default): + y-cells
+    const char *e = getenv("UBGL_ITEMS_VARIANT");
+    return (e && e[0] == '1') ? 1 : 2;
+  }();
+  if (variant == 2) {
+    static_assert(100 * ITEMS_NY < (1 << 18), "sort key bits");
+    const int nkeys = 100 * ITEMS_NY;
+    const float yrange = S.pwidth * (float)S.H / (float)S.W;
+    size_t tb = it->tmp_bytes;
+    UBGL_CUDA(cudaMemsetAsync(it->r2max, 0, sizeof(unsigned), st));
+    UBGL_LAUNCH(&S.lc, K_ITEMS, 0, st, k_items_r2max<<<std::min(g, 1184), 256, 0, st>>>(it->items, n, it->r2max));
+    UBGL_LAUNCH(&S.lc, K_ITEMS, 0, st, k_items_key2<<<g, 256, 0, st>>>(it->items, n, it->r2max, yrange, it->key, it->idx));
+    S.lc.n += 1; // the radix sort below (library kernels, not counted one by one)
+    UBGL_CUDA(cub::DeviceRadixSort::SortPairs(it->tmp, tb, it->key, it->skey, it->idx, it->order, n, 0, 18, st));
+    UBGL_LAUNCH(&S.lc, K_ITEMS, 0, st, k_items_offsets2<<<ceil_div(nkeys + 1, 256), 256, 0, st>>>(it->skey, n, nkeys, it->off2));
+    UBGL_LAUNCH(&S.lc, K_ITEMS, 0, st, k_items_gather_pos<<<g, 256, 0, st>>>(it->items, it->order, n, it->spos));
+    UBGL_LAUNCH(&S.lc, K_ITEMS, 1, st,
+                (k_items_advect<2><<<ceil_div(n, 128), 128, 0, st>>>(it->items, it->order, nullptr, it->skey, it->off2,
+                                                                    it->spos, n, game_dt, S.field(F_FLAG), S.field(F_VX),
+                                                                    S.field(F_VY), S.field(F_P), S.field(F_VX_ACCUM),
+                                                                    S.field(F_VY_ACCUM), S.pwidth, S.h)));
+    return UBGL_OK;
+  }
+  size_t tb = it->tmp_bytes;
   UBGL_LAUNCH(&S.lc, K_ITEMS, 0, st, k_items_bin<<<g, 256, 0, st>>>(it->items, n, it->bin, it->idx));
   S.lc.n += 1; // the radix sort below (library kernels, not counted one by one)
-  UBGL_CUDA(cub::DeviceRadixSort::SortPairs(it->tmp, it->tmp_bytes, it->bin, it->sbin, it->idx, it->order, n, 0, 7, st));
+  UBGL_CUDA(cub::DeviceRadixSort::SortPairs(it->tmp, tb, it->bin, it->sbin, it->idx, it->order, n, 0, 7, st));
   UBGL_LAUNCH(&S.lc, K_ITEMS, 0, st, k_items_offsets<<<g, 256, 0, st>>>(it->sbin, n, it->off));
   UBGL_LAUNCH(&S.lc, K_ITEMS, 0, st, k_items_gather_pos<<<g, 256, 0, st>>>(it->items, it->order, n, it->spos));
   UBGL_LAUNCH(&S.lc, K_ITEMS, 1, st,
-              k_items_advect<<<ceil_div(n, 128), 128, 0, st>>>(it->items, it->order, it->sbin, it->off, it->spos, n,
-                                                               game_dt, S.field(F_FLAG), S.field(F_VX),
-                                                               S.field(F_VY), S.field(F_P), S.field(F_VX_ACCUM),
-                                                               S.field(F_VY_ACCUM), S.pwidth, S.h));
+              (k_items_advect<1><<<ceil_div(n, 128), 128, 0, st>>>(it->items, it->order, it->sbin, nullptr, it->off,
+                                                                  it->spos, n, game_dt, S.field(F_FLAG), S.field(F_VX),
+                                                                  S.field(F_VY), S.field(F_P), S.field(F_VX_ACCUM),
+                                                                  S.field(F_VY_ACCUM), S.pwidth, S.h)));
   UBGL_CATCH
 }
 

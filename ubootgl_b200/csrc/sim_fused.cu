@@ -304,7 +304,6 @@ __device__ __forceinline__ float4 prestep_row(const float4 &S4, const float4 &C4
   return make_float4(out[0], out[1], out[2], out[3]);
 }
 
-constexpr int PRW = 64; // rows per warp strip
 struct PrestepRunGeom {
   int bx0, bx1; // interior tile columns [bx0, bx1) of PTX cells
   int ya, yb;   // interior rows [ya, yb)
@@ -312,7 +311,9 @@ struct PrestepRunGeom {
 
 // One WARP per block: the strip's row range depends on blockIdx only, so every loop bound and
 // row test below is provably warp-uniform (uniform registers, plain branches around the shuffles).
-template <int COMP>
+// PRW = rows per warp strip: 64 on large grids (pass 1 runs on PRW + 2 rows), 16 where that would
+// leave the GPU short of warps.
+template <int COMP, int PRW>
 __global__ void __launch_bounds__(32) k_prestep_run(PrestepArgs g, PrestepRunGeom q) {
   const int lane = threadIdx.x;
   const int bx = q.bx0 + blockIdx.x;
@@ -386,40 +387,78 @@ __device__ __forceinline__ void put3(const Grid &a, const Grid &b, const Grid &c
   if (c.d) c.at(x, y) = v;
 }
 
-__global__ void k_vbc_cols(BorderArgs g) {
-  const int y = g.y_lo + blockIdx.x * blockDim.x + threadIdx.x;
-  if (y >= g.y_hi) return;
-  if (y < g.xf.h) {
-    const int w = g.xf.w;
-    put3(g.xf, g.xb, g.xc, 0, y, vbc_par(g.bcW, g.xf.at(1, y), g.xf.at(0, y)));
-    put3(g.xf, g.xb, g.xc, w - 1, y, vbc_par(g.bcE, g.xf.at(w - 2, y), g.xf.at(w - 1, y)));
-  }
-  if (y < g.yf.h) {
-    const int w = g.yf.w;
-    put3(g.yf, g.yb, g.yc, 0, y, vbc_per(g.bcW, g.yf.at(1, y), g.yf.at(0, y)));
-    put3(g.yf, g.yb, g.yc, w - 1, y, vbc_per(g.bcE, g.yf.at(w - 2, y), g.yf.at(w - 1, y)));
-  }
-  if (g.p.d && y < g.p.h) {
-    g.p.at(0, y) = single_pbc(g.bcW, g.p.at(1, y));
-    g.p.at(g.p.w - 1, y) = single_pbc(g.bcE, g.p.at(g.p.w - 2, y));
-  }
+// Columns and rows in ONE launch (the game level's step is ~25 launches of ~8 us; three setVBCs
+// of two launches each were a fifth of it).  The reference's row loops run after its column loops
+// and read the column results at x = 0 / w-1 (simulation.cpp:80-102); the only row cells that
+// depend on them are the four corners, whose interior neighbour (0, 1), (w-1, 1), (0, h-2),
+// (w-1, h-2) is itself a column-phase cell.  A corner thread therefore evaluates that column
+// value itself from the interior cell next to it: whether its read of the cell's own value
+// (only INFLOW uses it, and keeps it) sees the column thread's store or not, the value is the same.
+struct BcGrid {
+  Grid f, b, c; // front, back, optional third copy
+  int comp;     // 0: vx (columns parallel, rows perpendicular), 1: vy
+};
+__device__ __forceinline__ float bcv(int comp, bool col, int bc, float a, float own) {
+  return (comp == 0) == col ? vbc_par(bc, a, own) : vbc_per(bc, a, own);
+}
+__device__ __forceinline__ void vbc_col_cell(const BcGrid &q, const BorderArgs &g, int y) {
+  const int w = q.f.w;
+  put3(q.f, q.b, q.c, 0, y, bcv(q.comp, true, g.bcW, q.f.at(1, y), q.f.at(0, y)));
+  put3(q.f, q.b, q.c, w - 1, y, bcv(q.comp, true, g.bcE, q.f.at(w - 2, y), q.f.at(w - 1, y)));
+}
+__device__ __forceinline__ void vbc_row_cell(const BcGrid &q, const BorderArgs &g, int x) {
+  const int w = q.f.w, h = q.f.h;
+  // The corner threads also do their interior neighbour (x = 1 / w-2), whose thread does
+  // nothing: the corner value may depend on that cell's value BEFORE the row phase (its own
+  // column-phase value, kept when the row side is INFLOW), read here before anybody writes it.
+  if (x == 1 || x == w - 2) return;
+  const bool corner = x == 0 || x == w - 1;
+  const int xn = x == 0 ? 1 : w - 2, bcx = x == 0 ? g.bcW : g.bcE;
+  auto row = [&](int y, int yi, int bc) { // border row y, interior row yi next to it
+    if (!corner) {
+      put3(q.f, q.b, q.c, x, y, bcv(q.comp, false, bc, q.f.at(x, yi), q.f.at(x, y)));
+      return;
+    }
+    const float nb_old = q.f.at(xn, y);                                              // (xn, y) before the row phase
+    const float own_col = bcv(q.comp, true, bcx, nb_old, q.f.at(x, y));              // (x, y) after the column phase
+    const float in_col = bcv(q.comp, true, bcx, q.f.at(xn, yi), q.f.at(x, yi));      // (x, yi) after the column phase
+    const float nb_new = bcv(q.comp, false, bc, q.f.at(xn, yi), nb_old);
+    put3(q.f, q.b, q.c, x, y, bcv(q.comp, false, bc, in_col, own_col));
+    put3(q.f, q.b, q.c, xn, y, nb_new);
+  };
+  if (g.do_s) row(0, 1, g.bcS);
+  if (g.do_n) row(h - 1, h - 2, g.bcN);
 }
 
-__global__ void k_vbc_rows(BorderArgs g) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  if (x < g.xf.w) {
-    const int h = g.xf.h;
-    if (g.do_s) put3(g.xf, g.xb, g.xc, x, 0, vbc_per(g.bcS, g.xf.at(x, 1), g.xf.at(x, 0)));
-    if (g.do_n) put3(g.xf, g.xb, g.xc, x, h - 1, vbc_per(g.bcN, g.xf.at(x, h - 2), g.xf.at(x, h - 1)));
+// thread t < ncol: column cells of row y_lo + t; else row cells of column t - ncol
+__global__ void k_vbc_all(BorderArgs g, int ncol) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const BcGrid qx{g.xf, g.xb, g.xc, 0}, qy{g.yf, g.yb, g.yc, 1};
+  if (t < ncol) {
+    const int y = g.y_lo + t;
+    // rows 0 and h-1 of a grid belong to the row phase (it runs last in the reference); the
+    // column phase writes them too there, with values the row phase overwrites: skipped here
+    if (y >= 1 && y < g.xf.h - 1) vbc_col_cell(qx, g, y);
+    if (y >= 1 && y < g.yf.h - 1) vbc_col_cell(qy, g, y);
+    if (g.p.d && y >= 1 && y < g.p.h - 1) {
+      g.p.at(0, y) = single_pbc(g.bcW, g.p.at(1, y));
+      g.p.at(g.p.w - 1, y) = single_pbc(g.bcE, g.p.at(g.p.w - 2, y));
+    }
+    return;
   }
-  if (x < g.yf.w) {
-    const int h = g.yf.h;
-    if (g.do_s) put3(g.yf, g.yb, g.yc, x, 0, vbc_par(g.bcS, g.yf.at(x, 1), g.yf.at(x, 0)));
-    if (g.do_n) put3(g.yf, g.yb, g.yc, x, h - 1, vbc_par(g.bcN, g.yf.at(x, h - 2), g.yf.at(x, h - 1)));
-  }
+  const int x = t - ncol;
+  if (!(g.do_s || g.do_n)) return;
+  if (x < g.xf.w) vbc_row_cell(qx, g, x);
+  if (x < g.yf.w) vbc_row_cell(qy, g, x);
   if (g.p.d && x < g.p.w) {
-    if (g.do_s) g.p.at(x, 0) = single_pbc(g.bcS, g.p.at(x, 1));
-    if (g.do_n) g.p.at(x, g.p.h - 1) = single_pbc(g.bcN, g.p.at(x, g.p.h - 2));
+    const int w = g.p.w, h = g.p.h;
+    auto inner = [&](int yy) {
+      if (x == 0) return single_pbc(g.bcW, g.p.at(1, yy));
+      if (x == w - 1) return single_pbc(g.bcE, g.p.at(w - 2, yy));
+      return g.p.at(x, yy);
+    };
+    if (g.do_s) g.p.at(x, 0) = single_pbc(g.bcS, inner(1));
+    if (g.do_n) g.p.at(x, h - 1) = single_pbc(g.bcN, inner(h - 2));
   }
 }
 
@@ -548,15 +587,23 @@ void launch_prestep(int comp, const PrestepArgs &g0, cudaStream_t stream, Launch
   const int top = g.gh - 35 - g.own_lo;
   const int byf = top >= 0 ? std::min(nby, top / PTY + 1) : 0;
   PrestepRunGeom q{1, bxf, g.own_lo + PTY * byl, std::min(g.own_lo + PTY * byf, std::min(g.gh, g.own_hi))};
-  const bool split = prestep_variant() == 1 && bxf > 1 && byf > byl && q.yb - q.ya >= 2 * PTY;
-  if (split) {
+  // one warp per strip: worth it only where the strips fill the machine (8 warps on each of the
+  // 148 SMs at least); the game level (1090 x 436: 184 strips) stays with k_prestep alone
+  const bool can = prestep_variant() == 1 && bxf > 1 && byf > byl && q.yb - q.ya >= 2 * PTY;
+  const int nx = can ? q.bx1 - q.bx0 : 0;
+  const int prw = !can ? 0 : nx * ceil_div(q.yb - q.ya, 64) >= 2 * 1184 ? 64 : nx * ceil_div(q.yb - q.ya, 16) >= 1184 ? 16 : 0;
+  if (prw) {
     g.frame = 1; g.f_nbx = nbx; g.f_byl = byl; g.f_byf = byf; g.f_bxf = bxf;
     grid = dim3(nbx * nby - (bxf - 1) * (byf - byl), 1);
-    dim3 rg(q.bx1 - q.bx0, ceil_div(q.yb - q.ya, PRW));
-    if (comp == 0)
-      UBGL_LAUNCH(lc, K_PRESTEP, 0, stream, k_prestep_run<0><<<rg, 32, 0, stream>>>(g, q));
+    dim3 rg(nx, ceil_div(q.yb - q.ya, prw));
+    if (comp == 0 && prw == 64)
+      UBGL_LAUNCH(lc, K_PRESTEP, 0, stream, (k_prestep_run<0, 64><<<rg, 32, 0, stream>>>(g, q)));
+    else if (comp == 0)
+      UBGL_LAUNCH(lc, K_PRESTEP, 0, stream, (k_prestep_run<0, 16><<<rg, 32, 0, stream>>>(g, q)));
+    else if (prw == 64)
+      UBGL_LAUNCH(lc, K_PRESTEP, 0, stream, (k_prestep_run<1, 64><<<rg, 32, 0, stream>>>(g, q)));
     else
-      UBGL_LAUNCH(lc, K_PRESTEP, 0, stream, k_prestep_run<1><<<rg, 32, 0, stream>>>(g, q));
+      UBGL_LAUNCH(lc, K_PRESTEP, 0, stream, (k_prestep_run<1, 16><<<rg, 32, 0, stream>>>(g, q)));
   }
   if (comp == 0)
     UBGL_LAUNCH(lc, K_PRESTEP, 0, stream, k_prestep<0><<<grid, PNT, sizeof(PrestepSmem), stream>>>(g));
@@ -565,10 +612,9 @@ void launch_prestep(int comp, const PrestepArgs &g0, cudaStream_t stream, Launch
 }
 
 void launch_borders(const BorderArgs &g, cudaStream_t stream, LaunchCounter *lc) {
-  if (g.y_hi > g.y_lo)
-    UBGL_LAUNCH(lc, K_VBC, 0, stream, k_vbc_cols<<<ceil_div(g.y_hi - g.y_lo, 128), 128, 0, stream>>>(g));
-  if (g.do_s || g.do_n)
-    UBGL_LAUNCH(lc, K_VBC, 0, stream, k_vbc_rows<<<ceil_div(g.yf.w, 128), 128, 0, stream>>>(g));
+  const int ncol = std::max(0, g.y_hi - g.y_lo), nrow = (g.do_s || g.do_n) ? g.yf.w : 0;
+  if (ncol + nrow > 0)
+    UBGL_LAUNCH(lc, K_VBC, 0, stream, k_vbc_all<<<ceil_div(ncol + nrow, 128), 128, 0, stream>>>(g, ncol));
 }
 
 // setPBC alone (simulation.cpp:36-45) for the slab driver
