@@ -136,6 +136,14 @@ typedef struct ubgl_host_mirrors {
   float *vy_current;   /* out, optional */
 } ubgl_host_mirrors;
 int ubgl_sim_step_host(ubgl_sim_t *sim, float dt, const ubgl_host_mirrors *m);
+/* Optional pipelined form of the same call (m->flag must be NULL): the outputs of step n-1 cross
+ * PCIe downwards while the accumulators of step n cross it upwards and step n runs, so the
+ * mirrors written by call n are those of step n-1 -- ONE STEP LATE, otherwise bit-identical to
+ * ubgl_sim_step_host's.  This is the coherence the reference's render thread already has with its
+ * simulation thread (draw.cpp:101 reads sim.p while sim_loop.cpp:29 is inside step()).  The first
+ * call writes no mirrors; ubgl_sim_step_host_flush brings the last step's fields down. */
+int ubgl_sim_step_host_pipelined(ubgl_sim_t *sim, float dt, const ubgl_host_mirrors *m);
+int ubgl_sim_step_host_flush(ubgl_sim_t *sim, const ubgl_host_mirrors *m);
 /* Stop rule of the pressure solves inside step() / stage(PROJECT).  rel_tol <= 0
  * (default): the reference's fixed UBGL_OPT_VCYCLES warm-started V-cycles, no
  * convergence test (simulation.cpp:189-190).  rel_tol > 0: V-cycles until

@@ -62,8 +62,10 @@ def test_nonbinary_flags_fall_back_to_plain(ubgl, port):
     assert cases.rel_l2(m.get_p(), o.get_p()) <= 1e-5
 
 
-@pytest.mark.parametrize("W,H", [(70, 40), (130, 97), (258, 131), (545, 218), (1090, 436), (700, 501), (1301, 300)])
+@pytest.mark.parametrize("W,H", [(70, 40), (130, 97), (258, 131), (545, 218), (1090, 436), (700, 501), (1301, 300), (2048, 1536)])
 def test_step_fused_equals_plain(ubgl, W, H):
+    """(2048, 1536) is large enough for the register-run prestep strips of 16 rows (k_prestep_run<., 16>);
+    the 64-row strips run in tests/test_gpu_fullsize.py at 8192^2."""
     from ubootgl_b200 import capi
     c = cases.sim_case(W, H, seed=W + H)
     outs = []

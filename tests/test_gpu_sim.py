@@ -267,3 +267,45 @@ def test_graph_not_replayed_after_dt_change(ubgl):
         for a, b in zip(sa, sb):
             assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
     assert launches[0] == launches[1]
+
+
+def test_pipelined_host_step_is_the_synchronous_one_a_step_late(ubgl):
+    """ubgl_sim_step_host_pipelined: after call n the mirrors hold step n-1, bit for bit what
+    ubgl_sim_step_host returned for that step; flush brings the last one; accumulators are consumed
+    and cleared per call exactly as in the synchronous form."""
+    from ubootgl_b200 import capi
+    W, H = 700, 501
+    c = cases.sim_case(W, H, seed=31)
+    shapes = dict(vx_accum=(H, W - 1), vy_accum=(H - 1, W), vx=(H, W - 1), vy=(H - 1, W), p=(H, W),
+                  vx_current=(H, W - 1), vy_current=(H - 1, W))
+    sims = []
+    for _ in range(2):
+        s = ubgl.Simulation(c["flag"])
+        s.set(capi.VX, c["vx"]); s.set(capi.VY, c["vy"]); s.set(capi.P, c["p"])
+        sims.append(s)
+    A, B = sims
+    sync_out = []
+    steps = 4
+    for k in range(steps):
+        b = {n: np.full(sh, np.nan, np.float32) for n, sh in shapes.items()}
+        b["vx_accum"][:] = c["vx_accum"] * (k + 1)
+        b["vy_accum"][:] = c["vy_accum"] * (k + 1)
+        A.step_host(0.001, **b)
+        sync_out.append(b)
+    pb = {n: np.full(sh, np.nan, np.float32) for n, sh in shapes.items()}
+    for k in range(steps):
+        pb["vx_accum"][:] = c["vx_accum"] * (k + 1)
+        pb["vy_accum"][:] = c["vy_accum"] * (k + 1)
+        B.step_host_pipelined(0.001, **pb)
+        assert not pb["vx_accum"][1:-1, 1:-1].any()  # consumed and cleared
+        if k == 0:
+            assert np.isnan(pb["vx"]).all()  # nothing to bring down yet
+        else:
+            for n in ("vx", "vy", "p", "vx_current", "vy_current"):
+                assert np.array_equal(pb[n].view(np.uint32), sync_out[k - 1][n].view(np.uint32)), (k, n)
+    B.step_host_flush(**{n: pb[n] for n in ("vx", "vy", "p", "vx_current", "vy_current")})
+    for n in ("vx", "vy", "p", "vx_current", "vy_current"):
+        assert np.array_equal(pb[n].view(np.uint32), sync_out[-1][n].view(np.uint32)), n
+    # the device state is the same too
+    for f in (capi.VX, capi.VY, capi.P):
+        assert np.array_equal(A.get(f).view(np.uint32), B.get(f).view(np.uint32))

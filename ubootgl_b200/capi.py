@@ -63,6 +63,8 @@ def _load():
         "ubgl_sim_step": (i, [v, f]),
         "ubgl_sim_stage": (i, [v, i, f]),
         "ubgl_sim_step_host": (i, [v, f, C.POINTER(HostMirrors)]),
+        "ubgl_sim_step_host_pipelined": (i, [v, f, C.POINTER(HostMirrors)]),
+        "ubgl_sim_step_host_flush": (i, [v, C.POINTER(HostMirrors)]),
         "ubgl_sim_set_tolerance": (i, [v, f, i, f]),
         "ubgl_sim_solve_info": (i, [v, IP, FP, FP, i, IP]),
         "ubgl_sim_sync": (i, [v]),
@@ -257,6 +259,23 @@ class Simulation:
                         ("vy_current", vy_current)):
             setattr(m, name, _fp(a) if a is not None else None)
         _ck(lib.ubgl_sim_step_host(self._h, dt, C.byref(m)))
+
+    @staticmethod
+    def _mirrors(**kw):
+        m = HostMirrors()
+        for name in ("flag", "vx_accum", "vy_accum", "vx", "vy", "p", "vx_current", "vy_current"):
+            a = kw.get(name)
+            setattr(m, name, _fp(a) if a is not None else None)
+        return m
+
+    def step_host_pipelined(self, dt, **mirrors):
+        """ubgl_sim_step_host_pipelined: the mirrors written are those of the PREVIOUS step."""
+        m = self._mirrors(**mirrors)
+        _ck(lib.ubgl_sim_step_host_pipelined(self._h, dt, C.byref(m)))
+
+    def step_host_flush(self, **mirrors):
+        m = self._mirrors(**mirrors)
+        _ck(lib.ubgl_sim_step_host_flush(self._h, C.byref(m)))
 
     def sync(self):
         _ck(lib.ubgl_sim_sync(self._h))

@@ -287,6 +287,150 @@ int ubgl_sim_step_host(ubgl_sim_t *sim, float dt, const ubgl_host_mirrors *m) {
   UBGL_CATCH
 }
 
+// ---------------------------------------------------------------------------
+// Pipelined host-mirror step (optional mode).  ubgl_sim_step_host is PCIe-serial: accumulators
+// up (10.5 ms at 8192^2), the step (4.5 ms), fields down (18 ms).  Here the three overlap across
+// calls on PCIe's two directions: call n sends step n-1's staged outputs down on one copy stream
+// while step n's accumulators go up on another and step n runs; the mirrors a call returns are
+// therefore ONE STEP LATE (after call n they hold the fields of step n-1; the fields themselves
+// are those of the synchronous call, bit for bit).  That is the coherence the reference's render
+// thread already lives with: it reads sim.vx_current / sim.p while the simulation thread is
+// somewhere inside step() (draw.cpp:101 vs sim_loop.cpp:29).
+// ubgl_sim_step_host_flush brings the last step's fields down.
+// ---------------------------------------------------------------------------
+namespace {
+void pipe_setup(DeviceSim &S) {
+  if (S.s_in) return;
+  UBGL_CUDA(cudaStreamCreateWithFlags(&S.s_in, cudaStreamNonBlocking));
+  UBGL_CUDA(cudaStreamCreateWithFlags(&S.s_out, cudaStreamNonBlocking));
+  UBGL_CUDA(cudaEventCreateWithFlags(&S.ev_up, cudaEventDisableTiming));
+  UBGL_CUDA(cudaEventCreateWithFlags(&S.ev_pack, cudaEventDisableTiming));
+  UBGL_CUDA(cudaEventCreateWithFlags(&S.ev_down, cudaEventDisableTiming));
+  UBGL_CUDA(cudaEventCreateWithFlags(&S.ev_main, cudaEventDisableTiming));
+  const size_t n = (size_t)(S.W - 1) * S.H + (size_t)S.W * (S.H - 1) + (size_t)S.W * S.H;
+  UBGL_CUDA(cudaMalloc(&S.d_out, sizeof(float) * n));
+}
+
+// D->H of the staged outputs of the previous step into the caller's mirrors (copy stream s_out),
+// vx / vy in bands with events so that host threads can fill the *_current mirrors behind them
+void pipe_download(DeviceSim &S, const ubgl_host_mirrors *m, std::vector<HostBand> &bands) {
+  UBGL_CUDA(cudaStreamWaitEvent(S.s_out, S.ev_pack, 0));
+  const size_t nvx = (size_t)(S.W - 1) * S.H, nvy = (size_t)S.W * (S.H - 1), np = (size_t)S.W * S.H;
+  struct { const float *src; float *dst, *cur; int w, h; } out[3] = {
+      {S.d_out, m->vx, m->vx_current, S.W - 1, S.H},
+      {S.d_out + nvx, m->vy, m->vy_current, S.W, S.H - 1},
+      {S.d_out + nvx + nvy, m->p, nullptr, S.W, S.H}};
+  (void)np;
+  for (auto &o : out) {
+    float *dst = o.dst ? o.dst : o.cur;
+    if (!dst) continue;
+    const size_t row = sizeof(float) * (size_t)o.w;
+    const int nb = (o.dst && o.cur) ? std::min(32, o.h) : 1;
+    for (int b = 0; b < nb; b++) {
+      const int y0 = (int)((long long)o.h * b / nb), y1 = (int)((long long)o.h * (b + 1) / nb);
+      UBGL_CUDA(cudaMemcpyAsync(dst + (size_t)y0 * o.w, o.src + (size_t)y0 * o.w, row * (size_t)(y1 - y0),
+                                cudaMemcpyDeviceToHost, S.s_out));
+      if (o.dst && o.cur) {
+        HostBand hb;
+        UBGL_CUDA(cudaEventCreateWithFlags(&hb.ready, cudaEventDisableTiming));
+        bands.push_back(hb);
+        HostBand &k = bands.back();
+        UBGL_CUDA(cudaEventRecord(k.ready, S.s_out));
+        k.src = o.dst + (size_t)y0 * o.w;
+        k.dst = o.cur + (size_t)y0 * o.w;
+        k.bytes = row * (size_t)(y1 - y0);
+      }
+    }
+  }
+  UBGL_CUDA(cudaEventRecord(S.ev_down, S.s_out));
+}
+} // namespace
+
+int ubgl_sim_step_host_pipelined(ubgl_sim_t *sim, float dt, const ubgl_host_mirrors *m) {
+  UBGL_TRY
+  SIM(sim);
+  NEED(m, "mirrors");
+  UBGL_REQUIRE(m->flag == nullptr, "pipelined step: upload a new flag with ubgl_sim_update_flag between calls");
+  pipe_setup(S);
+  std::vector<HostBand> bands;
+  auto cleanup = [&]() {
+    for (auto &b : bands)
+      if (b.ready) cudaEventDestroy(b.ready);
+  };
+  try {
+    const bool had = S.pipe_pending;
+    if (had) pipe_download(S, m, bands); // step n-1 goes down ...
+    bool up = false;
+    // the accumulators may be overwritten only after everything queued so far (step n-1 reads and
+    // clears them) is through
+    UBGL_CUDA(cudaEventRecord(S.ev_main, S.stream));
+    UBGL_CUDA(cudaStreamWaitEvent(S.s_in, S.ev_main, 0));
+    if (m->vx_accum) { // ... while step n's accumulators come up on the other PCIe direction
+      Grid g = S.field(F_VX_ACCUM);
+      upload_grid(g, m->vx_accum, g.w, g.h, S.s_in);
+      up = true;
+    }
+    if (m->vy_accum) {
+      Grid g = S.field(F_VY_ACCUM);
+      upload_grid(g, m->vy_accum, g.w, g.h, S.s_in);
+      up = true;
+    }
+    if (up) {
+      UBGL_CUDA(cudaEventRecord(S.ev_up, S.s_in));
+      UBGL_CUDA(cudaStreamWaitEvent(S.stream, S.ev_up, 0));
+    }
+    S.step(dt);
+    // the staging buffer is free once the previous download has read it
+    if (had) UBGL_CUDA(cudaStreamWaitEvent(S.stream, S.ev_down, 0));
+    {
+      const size_t nvx = (size_t)(S.W - 1) * S.H, nvy = (size_t)S.W * (S.H - 1);
+      Grid gx = S.field(F_VX), gy = S.field(F_VY), gp = S.field(F_P);
+      launch_pack_rows(gx.d, gx.pitch, gx.w, gx.h, S.d_out, S.stream, &S.lc);
+      launch_pack_rows(gy.d, gy.pitch, gy.w, gy.h, S.d_out + nvx, S.stream, &S.lc);
+      launch_pack_rows(gp.d, gp.pitch, gp.w, gp.h, S.d_out + nvx + nvy, S.stream, &S.lc);
+      UBGL_CUDA(cudaEventRecord(S.ev_pack, S.stream));
+      S.pipe_pending = true;
+    }
+    cudaError_t herr = cudaSuccess;
+    if (up || !bands.empty())
+      host_side_work(S.device, up ? S.ev_up : nullptr, m->vx_accum, m->vy_accum, S.W, S.H, 0, 0, S.H, bands, &herr);
+    UBGL_CUDA(herr);
+    if (had) UBGL_CUDA(cudaEventSynchronize(S.ev_down)); // the mirrors now hold step n-1; step n keeps running
+    else if (up) UBGL_CUDA(cudaEventSynchronize(S.ev_up));
+  } catch (...) {
+    cleanup();
+    throw;
+  }
+  cleanup();
+  UBGL_CATCH
+}
+
+int ubgl_sim_step_host_flush(ubgl_sim_t *sim, const ubgl_host_mirrors *m) {
+  UBGL_TRY
+  SIM(sim);
+  NEED(m, "mirrors");
+  if (!S.pipe_pending) return UBGL_OK;
+  std::vector<HostBand> bands;
+  auto cleanup = [&]() {
+    for (auto &b : bands)
+      if (b.ready) cudaEventDestroy(b.ready);
+  };
+  try {
+    pipe_download(S, m, bands);
+    cudaError_t herr = cudaSuccess;
+    if (!bands.empty()) host_side_work(S.device, nullptr, nullptr, nullptr, S.W, S.H, 0, 0, 0, bands, &herr);
+    UBGL_CUDA(herr);
+    UBGL_CUDA(cudaEventSynchronize(S.ev_down));
+    S.pipe_pending = false;
+    S.sync();
+  } catch (...) {
+    cleanup();
+    throw;
+  }
+  cleanup();
+  UBGL_CATCH
+}
+
 int ubgl_sim_set_tolerance(ubgl_sim_t *sim, float rel_tol, int max_cycles, float stagnation) {
   UBGL_TRY
   SIM(sim);

@@ -691,6 +691,11 @@ DeviceSim::~DeviceSim() {
   if (d_fnorm) cudaFree(d_fnorm);
   if (h_stage) cudaFreeHost(h_stage);
   if (d_pack) cudaFree(d_pack);
+  if (d_out) cudaFree(d_out);
+  if (s_in) { cudaStreamSynchronize(s_in); cudaStreamDestroy(s_in); }
+  if (s_out) { cudaStreamSynchronize(s_out); cudaStreamDestroy(s_out); }
+  for (cudaEvent_t e : {ev_up, ev_pack, ev_down, ev_main})
+    if (e) cudaEventDestroy(e);
   if (ev_stage) cudaEventDestroy(ev_stage);
   if (d_vxy) cudaFree(d_vxy);
   if (d_mag) cudaFree(d_mag);

@@ -153,6 +153,12 @@ public:
   void drop_graphs();
   float *d_pack = nullptr;
   size_t cap_pack = 0;
+  // ubgl_sim_step_host_pipelined (capi.cu): copy streams, the staged (packed) outputs of the last
+  // step and the events that order upload -> step -> pack -> download across calls
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  cudaEvent_t ev_up = nullptr, ev_pack = nullptr, ev_down = nullptr, ev_main = nullptr;
+  float *d_out = nullptr;
+  bool pipe_pending = false;
 
 private:
   // Three buffers per velocity component in the roles front / back
