@@ -7,6 +7,9 @@
 #include "capi_internal.cuh"
 #include "hostwork.cuh"
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <new>
@@ -391,12 +394,23 @@ int ubgl_sim_step_host_pipelined(ubgl_sim_t *sim, float dt, const ubgl_host_mirr
       UBGL_CUDA(cudaEventRecord(S.ev_pack, S.stream));
       S.pipe_pending = true;
     }
+    static const bool dbg = getenv("UBGL_PIPE_DEBUG") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
+    auto ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
+    double t_up = 0, t_host = 0, t_down = 0;
+    if (dbg && up) {
+      cudaEventSynchronize(S.ev_up);
+      t_up = ms();
+    }
     cudaError_t herr = cudaSuccess;
     if (up || !bands.empty())
       host_side_work(S.device, up ? S.ev_up : nullptr, m->vx_accum, m->vy_accum, S.W, S.H, 0, 0, S.H, bands, &herr);
     UBGL_CUDA(herr);
+    t_host = ms();
     if (had) UBGL_CUDA(cudaEventSynchronize(S.ev_down)); // the mirrors now hold step n-1; step n keeps running
     else if (up) UBGL_CUDA(cudaEventSynchronize(S.ev_up));
+    t_down = ms();
+    if (dbg) fprintf(stderr, "[pipe] upload done %.2f ms, host work done %.2f ms, download done %.2f ms\n", t_up, t_host, t_down);
   } catch (...) {
     cleanup();
     throw;

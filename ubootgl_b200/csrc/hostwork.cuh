@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 #include <vector>
@@ -34,7 +35,11 @@ inline void host_side_work(int device, cudaEvent_t uploaded, float *ax, float *a
   for (auto &b : bands) total += b.bytes;
   if (uploaded) total += sizeof(float) * (size_t)W * (clr_hi - clr_lo) * ((ax ? 1 : 0) + (ay ? 1 : 0));
   unsigned nt = std::thread::hardware_concurrency();
-  nt = std::min(nt ? nt : 1u, 8u);
+  static const unsigned cap = [] { // UBGL_HOST_THREADS: host copy threads of the *_step_host calls
+    const char *e = getenv("UBGL_HOST_THREADS");
+    return e ? (unsigned)std::max(1, atoi(e)) : 16u;
+  }();
+  nt = std::min(nt ? nt : 1u, cap);
   if (total < big) nt = 1;
   std::vector<cudaError_t> errs(nt, cudaSuccess);
   auto work = [&](unsigned t) {

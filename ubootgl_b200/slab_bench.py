@@ -25,11 +25,12 @@ def run(args, name):
     N = W * H
 
     # ---- N-GPU == 1-GPU, bit for bit, BEFORE anything is timed: the slab decomposition of a
-    # seeded 1000 x 1536 case on all ranks against the single-GPU Simulation on rank 0, at
+    # seeded 1000 x 1536 (8 ranks: x 3072) case on all ranks against the single-GPU Simulation on rank 0, at
     # CFL ~ 1-3 (back-traces stay in the ghost rows) and CFL ~ 25-75 (taps served by NVLink
     # peer loads).  Every scaling number below rests on this equivalence; a mismatch aborts. ----
     from tests import mgpu_equiv
-    equiv_runs = [mgpu_equiv.check(1000, 1536, 2, dt_, rank, world, dev, verbose=(rank == 0), skew=sk)
+    eh = max(1536, 384 * world)  # >= 384 rows per rank: the CFL ~ 75 back-traces stay inside the neighbouring slab
+    equiv_runs = [mgpu_equiv.check(1000, eh, 2, dt_, rank, world, dev, verbose=(rank == 0), skew=sk)
                   for dt_, sk in ((0.002, False), (0.02, True))]  # the second with unequal (weighted) slab heights
     equiv = {"bitwise_ok": all(r["bitwise_ok"] for r in equiv_runs), "fields": equiv_runs[0]["fields"],
              "ranks": world, "grid": equiv_runs[0]["grid"], "steps": 2, "dt": [r["dt"] for r in equiv_runs],
