@@ -85,6 +85,11 @@ def test_items_match_oracle(ubgl, port, W, H, n, dt):
         assert rel_l2(G.get(f), O.get(f)) <= 3e-5
 
 
+# share of rigid bodies that must agree with the oracle record for record (the rest sit within
+# rounding of a terrain-probe threshold and take the other branch); see profiles/r02_parity_errors.md
+BODY_CLOSE = 0.99
+
+
 @pytest.mark.parametrize("W,H,n,dt", [(130, 97, 300, 0.004), (258, 131, 1000, 0.01), (545, 218, 400, 1.0 / 60.0)])
 def test_bodies_match_oracle(ubgl, port, W, H, n, dt):
     """ubgl_items_advect (Simulation::advectFloatingItems, rigid bodies) against the restatement
@@ -102,8 +107,11 @@ def test_bodies_match_oracle(ubgl, port, W, H, n, dt):
         port.items_advect(o, dt, flag, vx, vy, ax, ay)
         g = I.get()
         assert np.isfinite(g["pos"]).all()
-        assert close_fraction(g, o) >= 0.99, (k, close_fraction(g, o))
-        assert (g["bumpCount"] == o["bumpCount"]).mean() >= 0.99
+        cf, bf = close_fraction(g, o), float((g["bumpCount"] == o["bumpCount"]).mean())
+        cases.record_parity(f"rigid bodies frame {k}: share of {n} bodies within 2e-4 / equal bumpCount", (W, H),
+                            "restatement (= unmodified reference to 1e-7)", {"close": cf, "bump": bf})
+        assert cf >= BODY_CLOSE, (k, cf)
+        assert bf >= BODY_CLOSE
         assert (g["force"] == 0).all() and (g["angForce"] == 0).all()
     assert o["bumpCount"].sum() > 0
     assert np.abs(ax).sum() > 0

@@ -461,8 +461,13 @@ __global__ void __launch_bounds__(ITEMS_NT) k_items_advect(Item *items, const in
 // one thread per body; per sub-step five terrain probes (each up to six bilinear flag samples),
 // then drag sampled at max(2, side/h) points along each of the four sides with the reaction
 // scattered into the device accumulators by atomicAdd, like the simple items above.
+// glm::rotate(vec2, angle).  The reference's cos / sin are glibc's cosf / sinf, correctly rounded
+// for practically every argument; CUDA's cosf / sinf are good to 1-2 ulp, and a last-bit difference
+// in a probe position flips `psampleFlagLinear(...) < 0.5` for bodies that sit exactly on a
+// terrain edge.  There are only a few thousand rigid bodies, so the rotation takes the
+// double-precision functions and rounds once: the float the reference computes.
 __device__ __forceinline__ void rot2(float x, float y, float ang, float &ox, float &oy) {
-  const float c = cosf(ang), s = sinf(ang); // glm::rotate(vec2, angle)
+  const float c = (float)cos((double)ang), s = (float)sin((double)ang);
   ox = x * c - y * s;
   oy = x * s + y * c;
 }

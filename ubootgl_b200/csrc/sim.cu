@@ -860,7 +860,11 @@ bool launch_advect(const Grid &vx, const Grid &vy, const Grid &vxbk, const Grid 
     }();
 #define UBGL_ADV_XY(S_, O_) UBGL_LAUNCH(lc, K_ADVECT, LVL, stream, (k_advect_xy<S_, O_><<<g, b, 0, stream>>>(vx, vy, vxbk, vybk, mask, ax, ay, half, full, lim, y_lo, y_hi, tr)))
     if (peers) {
-      UBGL_ADV_XY(true, 4);
+      if (occ == 4) {
+        UBGL_ADV_XY(true, 4);
+      } else {
+        UBGL_ADV_XY(true, 6);
+      }
     } else if (occ == 3) {
       UBGL_ADV_XY(false, 3);
     } else if (occ == 5) {

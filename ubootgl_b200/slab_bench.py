@@ -48,7 +48,9 @@ def run(args, name):
     # load balance: the advect pass (27 % of a step) skips octets without fluid, every other pass
     # costs the same per row; cuts at equal weight instead of equal height (identical on every
     # rank: computed from the generator's disc list)
-    if os.environ.get("UBGL_SLAB_BALANCE", "1") != "0":
+    # (measured at 8 GPUs, m2: 11.46 ms weighted vs 11.29 ms equal heights -- no gain, the exchanges wait on
+    # jitter, not on a systematic imbalance; the API stays, the bench uses equal heights unless asked)
+    if os.environ.get("UBGL_SLAB_BALANCE", "0") == "1":
         frac = cases.channel_row_fluid_fraction(W, H, seed=1234)
         u.slab_set_row_weights((0.73 + 0.27 * frac).astype(np.float32))
     plan = u.slab_plan(W, H, world, rank)
