@@ -86,9 +86,9 @@ def test_registry_item_advection_matches_the_unmodified_reference(ubgl, port, re
         assert cases.rel_l2(ax, rax) <= 2e-5 and cases.rel_l2(ay, ray) <= 2e-5
         tol = 5e-5
     else:
-        assert close_fraction(g, o) >= 0.99
-        assert cases.rel_l2(ax, rax) <= 1e-3 and cases.rel_l2(ay, ray) <= 1e-3
-        tol = 1e-3
+        assert close_fraction(g, o) >= 0.999
+        assert cases.rel_l2(ax, rax) <= 1e-4 and cases.rel_l2(ay, ray) <= 1e-4
+        tol = 2.5e-4  # measured 1.12e-4 (vy) against the -Ofast reference after the scattered reactions
     R.step(step_dt)
     for name, fld, shape in (("vx", ob.VX, (H, W - 1)), ("vy", ob.VY, (H - 1, W)), ("p", ob.P, (H, W))):
         got = np.fromfile(pout + "." + name, np.float32).reshape(shape)

@@ -87,7 +87,7 @@ def test_items_match_oracle(ubgl, port, W, H, n, dt):
 
 # share of rigid bodies that must agree with the oracle record for record (the rest sit within
 # rounding of a terrain-probe threshold and take the other branch); see profiles/r02_parity_errors.md
-BODY_CLOSE = 0.99
+BODY_CLOSE = 0.999  # measured 1.0 in every frame since the rotation is correctly rounded (round 1: >= 0.99)
 
 
 @pytest.mark.parametrize("W,H,n,dt", [(130, 97, 300, 0.004), (258, 131, 1000, 0.01), (545, 218, 400, 1.0 / 60.0)])
@@ -115,12 +115,16 @@ def test_bodies_match_oracle(ubgl, port, W, H, n, dt):
         assert (g["force"] == 0).all() and (g["angForce"] == 0).all()
     assert o["bumpCount"].sum() > 0
     assert np.abs(ax).sum() > 0
-    assert rel_l2(G.get(ob.VX_ACCUM), ax) <= 1e-3 and rel_l2(G.get(ob.VY_ACCUM), ay) <= 1e-3
+    eax, eay = rel_l2(G.get(ob.VX_ACCUM), ax), rel_l2(G.get(ob.VY_ACCUM), ay)
     # the scattered reaction feeds the next fluid step like host-uploaded accumulators
     O.set(ob.VX_ACCUM, ax); O.set(ob.VY_ACCUM, ay)
     G.step(0.001); O.step(0.001)
-    for f in (ob.VX, ob.VY, ob.P):
-        assert rel_l2(G.get(f), O.get(f)) <= 1e-3
+    es = {n: rel_l2(G.get(f), O.get(f)) for n, f in (("vx", ob.VX), ("vy", ob.VY), ("p", ob.P))}
+    cases.record_parity(f"rigid bodies: accumulators after 3 frames, fields after the next step ({n} bodies)", (W, H),
+                        "restatement (= unmodified reference to 1e-7)", dict(vx_accum=eax, vy_accum=eay, **es))
+    assert eax <= 1e-4 and eay <= 1e-4, (eax, eay)  # atomicAdd order vs the serial +=
+    for k_, e in es.items():
+        assert e <= 1e-4, (k_, e)
 
 
 def test_items_empty_and_regrow(ubgl, port):

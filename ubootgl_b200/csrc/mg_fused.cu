@@ -455,13 +455,13 @@ __global__ void __launch_bounds__(NT, 2) k_mg_tile(TileArgs a) {
 // (order of additions, table weights) is unchanged: results are bit-identical to
 // k_mg_tile and to the plain path (tests/test_gpu_fused.py).
 // ---------------------------------------------------------------------------
-constexpr int RUN_R = 4;                 // rows per thread
-#ifndef UBGL_RUN_NCH
-#define UBGL_RUN_NCH 16
+// R = rows per thread (template parameter): 4 -> 16 row chunks, 256 threads, ~122 registers, 16 warps
+// per SM; 2 -> 32 chunks, 512 threads, 64 registers, 32 warps per SM (twice the warps to hide the
+// latencies this kernel is bound by, for 1.33x the other-colour loads per cell)
+#ifndef UBGL_MG_ROWS_DEFAULT
+#define UBGL_MG_ROWS_DEFAULT 4
 #endif
-constexpr int RUN_NCH = UBGL_RUN_NCH;    // row chunks per window
-constexpr int RUN_LH = RUN_R * RUN_NCH;  // 64 window rows
-constexpr int RUN_NT = 16 * RUN_NCH;     // 16 column groups x 16 chunks = 256 threads
+constexpr int RUN_LH = 64;               // window rows
 constexpr int RUN_HX = 8;                // x halo: whole 8-cell column groups
 
 template <int MODE> struct RunGeom {
@@ -476,10 +476,10 @@ template <int MODE> struct RunGeom {
 
 __device__ __forceinline__ float4 lds4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
 
-template <int MODE>
-__global__ void __launch_bounds__(RUN_NT, RUN_NT <= 256 ? 2 : 1) k_mg_run(TileArgs a) {
+template <int MODE, int R>
+__global__ void __launch_bounds__(16 * (RUN_LH / R), 2) k_mg_run(TileArgs a) {
   using G = RunGeom<MODE>;
-  constexpr int S = G::S, R = RUN_R, LH = RUN_LH, NT = RUN_NT, HX = RUN_HX, HY = G::HY;
+  constexpr int S = G::S, LH = RUN_LH, NT = 16 * (RUN_LH / R), HX = RUN_HX, HY = G::HY;
   constexpr int TX = G::TX, TY = G::TY, NW = NT / 32;
   static_assert(R % 2 == 0 && HY % 2 == 0 && TX % 8 == 0 && TY % 2 == 0, "run geometry");
 
@@ -1158,8 +1158,6 @@ int tile_variant() { return g_tile_variant; }
 template <int MODE>
 static void launch_run(const TileArgs &a, cudaStream_t stream, LaunchCounter *lc, int kind, int level) {
   using G = RunGeom<MODE>;
-  static std::atomic<unsigned long long> attr_done{0};
-  ensure_dyn_smem(k_mg_run<MODE>, G::smem, attr_done);
   dim3 grid(ceil_div(a.w, G::TX), ceil_div(a.own_hi - a.own_lo, G::TY));
   TileArgs b = a;
   b.pf_dist = g_prefetch_dist;
@@ -1173,8 +1171,19 @@ static void launch_run(const TileArgs &a, cudaStream_t stream, LaunchCounter *lc
     return e ? atoi(e) : 0;
   }();
   b.dbg = dbg;
-
-  UBGL_LAUNCH(lc, kind, level, stream, k_mg_run<MODE><<<grid, RUN_NT, G::smem, stream>>>(b));
+  static const int rows_per_thread = [] { // UBGL_MG_ROWS: 4 or 2 (see RUN_LH)
+    const char *e = getenv("UBGL_MG_ROWS");
+    return (e && e[0] == '4') ? 4 : ((e && e[0] == '2') ? 2 : UBGL_MG_ROWS_DEFAULT);
+  }();
+  if (rows_per_thread == 2) {
+    static std::atomic<unsigned long long> attr_done2{0};
+    ensure_dyn_smem(k_mg_run<MODE, 2>, G::smem, attr_done2);
+    UBGL_LAUNCH(lc, kind, level, stream, (k_mg_run<MODE, 2><<<grid, 16 * (RUN_LH / 2), G::smem, stream>>>(b)));
+  } else {
+    static std::atomic<unsigned long long> attr_done4{0};
+    ensure_dyn_smem(k_mg_run<MODE, 4>, G::smem, attr_done4);
+    UBGL_LAUNCH(lc, kind, level, stream, (k_mg_run<MODE, 4><<<grid, 16 * (RUN_LH / 4), G::smem, stream>>>(b)));
+  }
 }
 
 static void set_rows(TileArgs &a, const Rows *rows) {
