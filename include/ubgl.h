@@ -296,6 +296,23 @@ int ubgl_tracers_shift(ubgl_tracers_t *t, float shift); /* shift_tracers.cs (poi
  * (2H-1) x (2W-1); either host pointer may be NULL (device copy only) */
 int ubgl_sim_colocate_velocity(ubgl_sim_t *sim, float *vxy_host, float *mag_host);
 
+/* (4) Display without PCIe (CUDA -> OpenGL interop).  Replaces the per-frame texture uploads
+ * VelocityTextures::updateFromStaggered (velocity_textures.cpp:63-93: two glTexSubImage2D +
+ * interp_shader.cs) and Draw2DBuf::draw(sim.p.data(), ...) (draw.cpp:101 ->
+ * draw_2dbuf.cpp:181-209: glTexSubImage2D of p): the texels are written from the resident
+ * fields into CUDA arrays by surface stores.  Each argument is a cudaArray_t (NULL: skip) --
+ * for a GL texture: cudaGraphicsGLRegisterImage once, then per frame cudaGraphicsMapResources,
+ * cudaGraphicsSubResourceGetMappedArray(level 0), this call, cudaGraphicsUnmapResources
+ * (INTEGRATION.md).  vxy: (2W-1) x (2H-1) RG32F, mag: (2W-1) x (2H-1) R32F (tex_vxy / tex_mag,
+ * velocity_textures.cpp:38-52), p: W x H R32F; wrong sizes or formats are rejected.  Returns
+ * after the stores have completed. */
+int ubgl_sim_export_display(ubgl_sim_t *sim, void *vxy_array, void *mag_array, void *p_array);
+/* Headless stand-in for a mapped GL texture (tests, offscreen consumers): a CUDA array of
+ * w x h texels with `channels` (1 or 2) 32-bit floats, surface-writable. */
+int ubgl_display_array_create(int w, int h, int channels, int device, void **array_out);
+int ubgl_display_array_read(void *array, float *host); /* h x w x channels floats */
+int ubgl_display_array_destroy(void *array);
+
 /* (2) Floating items, Simulation::advectFloatingItemsSimple
  * (advect_floating_items.cpp:148-274).  One record = CoItem + CoKinematicsSimple
  * (components.hpp:6-43); array order = the order the reference's view visits. */

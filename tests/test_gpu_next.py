@@ -30,6 +30,36 @@ def test_colocate_bit_exact(ubgl, port, W, H):
     assert (mag.view(np.uint32) == omag.view(np.uint32)).all()
 
 
+@pytest.mark.parametrize("W,H", [(70, 40), (258, 131), (1090, 436)])
+def test_display_export_into_cuda_arrays(ubgl, port, W, H):
+    """8f rank 4: the texels the reference uploads per frame (velocity_textures.cpp:63-93 through
+    interp_shader.cs, p through draw_2dbuf.cpp:181-209) written into CUDA arrays -- the form a mapped
+    GL texture takes -- without leaving the device: bit-identical to the restated shader and to p."""
+    flag, O = next_cases.developed_flow(port, W, H, seed=W + 1)
+    G = gpu_twin(ubgl, O, flag)
+    tw, th = 2 * W - 1, 2 * H - 1
+    avxy, amag, ap = ubgl.DisplayArray(tw, th, 2), ubgl.DisplayArray(tw, th, 1), ubgl.DisplayArray(W, H, 1)
+    G.export_display(avxy, amag, ap)
+    ovxy, omag = port.colocate(O.get(ob.VX_CURRENT), O.get(ob.VY_CURRENT))
+    assert (avxy.read().view(np.uint32) == ovxy.view(np.uint32)).all()
+    assert (amag.read().view(np.uint32) == omag.view(np.uint32)).all()
+    assert (ap.read().view(np.uint32) == O.get(ob.P).view(np.uint32)).all()
+    # any subset; after a step the arrays follow the new fields
+    p_before = ap.read()
+    G.step(0.001)
+    G.export_display(None, amag, None)
+    _, omag2 = port.colocate(G.get(ob.VX_CURRENT), G.get(ob.VY_CURRENT))
+    assert (amag.read().view(np.uint32) == omag2.view(np.uint32)).all()
+    assert (ap.read().view(np.uint32) == p_before.view(np.uint32)).all()  # p was not exported this time
+    # wrong texel layout or size: rejected, nothing written
+    with pytest.raises(ubgl.UbglError):
+        G.export_display(amag, None, None)  # R32F where RG32F is expected
+    with pytest.raises(ubgl.UbglError):
+        G.export_display(None, None, amag)  # (2W-1) x (2H-1) where W x H is expected
+    for a in (avxy, amag, ap):
+        a.close()
+
+
 @pytest.mark.parametrize("W,H,nt,scale", [(130, 97, 1000, 1), (258, 131, 5000, 1), (130, 97, 2000, 2)])
 def test_tracers_bit_exact(ubgl, port, W, H, nt, scale):
     """60 frames incl. respawn, ring wrap-around, freezing in terrain: bit-exact

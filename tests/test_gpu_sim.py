@@ -309,3 +309,46 @@ def test_pipelined_host_step_is_the_synchronous_one_a_step_late(ubgl):
     # the device state is the same too
     for f in (capi.VX, capi.VY, capi.P):
         assert np.array_equal(A.get(f).view(np.uint32), B.get(f).view(np.uint32))
+
+
+def test_current_fields_alias_the_front_until_somebody_writes(ubgl, port):
+    """saveCurrentVelocityFields (simulation.cpp:16-19) without the second store: after a fused step
+    vx_current / vy_current resolve to the front buffers; a write to either side (upload, stage call,
+    setGrids, raw device pointer) first gives *_current its own copy, so the reference's semantics --
+    the snapshot keeps the end-of-step values -- hold bit for bit."""
+    G, O, c = make_pair(ubgl, port, 130, 97, seed=77)
+    dt = float(O.dx)
+    for _ in range(2):
+        G.step(dt); O.step(dt)
+    snap = {f: G.get(f) for f in (ob.VX_CURRENT, ob.VY_CURRENT)}
+    for f, g in ((ob.VX_CURRENT, ob.VX), (ob.VY_CURRENT, ob.VY)):
+        assert (snap[f].view(np.uint32) == G.get(g).view(np.uint32)).all()
+        assert rel_l2(snap[f], O.get(f)) <= 1e-4
+    same = lambda f: (G.get(f).view(np.uint32) == snap[f].view(np.uint32)).all()
+    # host write to the front buffers: the snapshot stays
+    junk = (c["vx"] * 0.5 + 0.25).astype(np.float32)
+    G.set(ob.VX, junk); O.set(ob.VX, junk)
+    assert same(ob.VX_CURRENT) and same(ob.VY_CURRENT)
+    assert (G.get(ob.VX) == junk).all()
+    # the next step consumes the written front and makes a new snapshot
+    G.step(dt); O.step(dt)
+    assert not same(ob.VX_CURRENT)
+    snap = {f: G.get(f) for f in (ob.VX_CURRENT, ob.VY_CURRENT)}
+    # write to the snapshot itself: the front stays
+    front = G.get(ob.VY)
+    G.set(ob.VY_CURRENT, np.zeros_like(snap[ob.VY_CURRENT]))
+    assert (G.get(ob.VY).view(np.uint32) == front.view(np.uint32)).all()
+    assert not G.get(ob.VY_CURRENT).any() and same(ob.VX_CURRENT)
+    # a stage call works on the front in place: the snapshot stays
+    G.step(dt)
+    snap = {f: G.get(f) for f in (ob.VX_CURRENT, ob.VY_CURRENT)}
+    G.stage(ob.ST_DIFFUSE, dt)
+    assert same(ob.VX_CURRENT) and same(ob.VY_CURRENT)
+    assert not (G.get(ob.VX).view(np.uint32) == snap[ob.VX_CURRENT].view(np.uint32)).all()
+    # setGrids on the device zeroes front velocities in new solids, not the snapshot
+    G.step(dt)
+    snap = {f: G.get(f) for f in (ob.VX_CURRENT, ob.VY_CURRENT)}
+    nf = c["flag"].copy()
+    nf[40:60, 30:70] = 0.0
+    G.set_grids_all(nf)
+    assert same(ob.VX_CURRENT) and same(ob.VY_CURRENT)

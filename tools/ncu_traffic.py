@@ -19,12 +19,12 @@ for r in rows[2:]:
     name = r[c["Kernel Name"]]
     b = val(r, "dram__bytes_read.sum") + val(r, "dram__bytes_write.sum")
     key = None
-    if "k_mg_run<0>" in name or "k_mg_run<(int)0>" in name or "k_mg_tile<3, 0" in name:
+    if "k_mg_run<0" in name or "k_mg_run<(int)0" in name or "k_mg_tile<3, 0" in name:
         if acc.get("_cycle_done"):
             continue
         key = f"mg_pre_fused:{n_pre}"
         n_pre += 1
-    elif "k_mg_run<1>" in name or "k_mg_run<(int)1>" in name or "k_mg_tile<3, 1" in name:
+    elif "k_mg_run<1" in name or "k_mg_run<(int)1" in name or "k_mg_tile<3, 1" in name:
         if acc.get("_cycle_done"):
             continue
         n_pre -= 1

@@ -7,4 +7,4 @@ ctypes face of that C ABI used by tests/ and bench.py; it contains no compute
 and no CPU fallback: importing ``capi`` without the built library raises.
 """
 from . import capi  # noqa: F401
-from .capi import MG, Items, Simulation, SlabSimulation, Tracers, UbglError, lib, slab_plan, slab_set_row_weights  # noqa: F401
+from .capi import MG, DisplayArray, Items, Simulation, SlabSimulation, Tracers, UbglError, lib, slab_plan, slab_set_row_weights  # noqa: F401

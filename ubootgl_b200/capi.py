@@ -123,6 +123,10 @@ def _load():
         "ubgl_tracers_advect": (i, [v, v, f, C.c_uint]),
         "ubgl_tracers_shift": (i, [v, f]),
         "ubgl_sim_colocate_velocity": (i, [v, FP, FP]),
+        "ubgl_sim_export_display": (i, [v, v, v, v]),
+        "ubgl_display_array_create": (i, [i, i, i, i, VP]),
+        "ubgl_display_array_read": (i, [v, FP]),
+        "ubgl_display_array_destroy": (i, [v]),
         "ubgl_items_create": (i, [i, VP]),
         "ubgl_items_destroy": (i, [v]),
         "ubgl_items_upload": (i, [v, v, i]),
@@ -350,6 +354,12 @@ class Simulation:
         _ck(lib.ubgl_sim_colocate_velocity(self._h, _fp(vxy), _fp(mag)))
         return vxy, mag
 
+    def export_display(self, vxy=None, mag=None, p=None):
+        """velocity_textures.cpp:63-93 + draw_2dbuf.cpp:181-209 without PCIe: texels into CUDA arrays
+        (mapped GL textures, or DisplayArray stand-ins)."""
+        h = lambda a: a._h if isinstance(a, DisplayArray) else a
+        _ck(lib.ubgl_sim_export_display(self._h, h(vxy), h(mag), h(p)))
+
     def draw_circles(self, xyd, val):
         """Terrain::drawCircle (terrain.cpp:213-234) x n + MG::updateFields, on the device."""
         xyd = _f32(np.asarray(xyd, np.float32).reshape(-1, 3))
@@ -363,6 +373,31 @@ class Simulation:
         if col.shape != (self.height,):
             raise UbglError("shift_map: the new column needs H values")
         _ck(lib.ubgl_sim_shift_map(self._h, _fp(col)))
+
+
+class DisplayArray:
+    """A w x h CUDA array of 1 or 2 float channels: what a mapped R32F / RG32F GL texture is to CUDA."""
+
+    def __init__(self, w, h, channels, device=0):
+        self.w, self.h, self.channels = w, h, channels
+        self._h = C.c_void_p()
+        _ck(lib.ubgl_display_array_create(w, h, channels, device, C.byref(self._h)))
+
+    def read(self):
+        out = np.empty((self.h, self.w, self.channels) if self.channels > 1 else (self.h, self.w), np.float32)
+        _ck(lib.ubgl_display_array_read(self._h, _fp(out)))
+        return out
+
+    def close(self):
+        if self._h:
+            lib.ubgl_display_array_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Tracers:

@@ -505,6 +505,7 @@ int ubgl_sim_device_ptr(ubgl_sim_t *sim, int field, void **dptr, int *pitch) {
   SIM(sim);
   NEED(dptr, "dptr");
   UBGL_REQUIRE(field >= 0 && field < UBGL_NUM_FIELDS, "bad field id");
+  S.will_write(field); // the caller may write through the pointer: front and *_current get their own buffers
   Grid g = S.field(field);
   *dptr = g.d;
   if (pitch) *pitch = g.pitch;

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstdint>
+#include <cstdlib>
 #include <string>
 #include <vector>
 #include <atomic>
@@ -124,6 +125,24 @@ struct LaunchCounter {
   }
   // call after a stream synchronize
   void collect() {
+    // UBGL_TIMELINE=<prefix>: start offset and duration of every profiled launch of this collect
+    // (<prefix>.<RANK>.csv, rewritten each time) -- where a rank idles between its kernels
+    if (const char *tl = getenv("UBGL_TIMELINE")) {
+      if (!recs.empty()) {
+        const char *rk = getenv("RANK");
+        std::string path = std::string(tl) + "." + (rk ? rk : "0") + ".csv";
+        if (FILE *fp = fopen(path.c_str(), "w")) {
+          fprintf(fp, "kind,level,start_ms,dur_ms\n");
+          for (auto &r : recs) {
+            float t0 = 0.f, t = 0.f;
+            if (cudaEventElapsedTime(&t0, recs[0].a, r.a) == cudaSuccess &&
+                cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess)
+              fprintf(fp, "%d,%d,%.4f,%.4f\n", r.kind, r.level, t0, t);
+          }
+          fclose(fp);
+        }
+      }
+    }
     for (auto &r : recs) {
       float t = 0.f;
       if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) {

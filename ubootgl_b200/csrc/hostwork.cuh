@@ -35,7 +35,7 @@ inline void host_side_work(int device, cudaEvent_t uploaded, float *ax, float *a
   for (auto &b : bands) total += b.bytes;
   if (uploaded) total += sizeof(float) * (size_t)W * (clr_hi - clr_lo) * ((ax ? 1 : 0) + (ay ? 1 : 0));
   unsigned nt = std::thread::hardware_concurrency();
-  static const unsigned cap = [] { // UBGL_HOST_THREADS: host copy threads of the *_step_host calls
+  const unsigned cap = [] { // UBGL_HOST_THREADS: host copy threads of the *_step_host calls (read per call)
     const char *e = getenv("UBGL_HOST_THREADS");
     return e ? (unsigned)std::max(1, atoi(e)) : 16u;
   }();

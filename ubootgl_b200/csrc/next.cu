@@ -91,6 +91,53 @@ __global__ void k_colocate(Grid vx, Grid vy, int nx, int ny, float2 *vxy, float 
   if (mag) mag[(size_t)gy * tw + gx] = sqrtf(v.x * v.x + v.y * v.y);
 }
 
+// ---------------------------------------------------------------------------
+// Display export.  The reference crosses PCIe three times per frame for the
+// display: vx_current / vy_current into two R32F textures that interp_shader.cs turns into the
+// RG32F velocity and R32F magnitude textures (velocity_textures.cpp:63-93), and p into a fresh
+// R32F texture (draw.cpp:101 -> draw_2dbuf.cpp:181-209).  Here the same texels are written from
+// the resident fields straight into CUDA arrays -- which is what a GL texture registered with
+// cudaGraphicsGLRegisterImage is once mapped (cudaGraphicsSubResourceGetMappedArray) -- by surface
+// stores; nothing leaves the device.  Mip levels stay the caller's glGenerateMipmap (GPU side).
+// ---------------------------------------------------------------------------
+__global__ void k_export_vxy(Grid vx, Grid vy, int nx, int ny, cudaSurfaceObject_t s_vxy, cudaSurfaceObject_t s_mag) {
+  const int gx = blockIdx.x * blockDim.x + threadIdx.x, gy = blockIdx.y * blockDim.y + threadIdx.y;
+  if (gx >= 2 * nx - 1 || gy >= 2 * ny - 1) return;
+  const float2 v = vxy_texel(vx, vy, nx, ny, gx, gy);
+  if (s_vxy) surf2Dwrite(v, s_vxy, gx * (int)sizeof(float2), gy);
+  if (s_mag) surf2Dwrite(sqrtf(v.x * v.x + v.y * v.y), s_mag, gx * (int)sizeof(float), gy);
+}
+__global__ void k_export_scalar(Grid g, cudaSurfaceObject_t s) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= g.w || y >= g.h) return;
+  surf2Dwrite(g.at(x, y), s, x * (int)sizeof(float), y);
+}
+
+namespace {
+struct Surface { // surface object over a caller-owned array, checked against the expected texel layout
+  cudaSurfaceObject_t obj = 0;
+  Surface(void *array, int w, int h, int channels, const char *what) {
+    if (!array) return;
+    cudaChannelFormatDesc d{};
+    cudaExtent e{};
+    unsigned flags = 0;
+    UBGL_CUDA(cudaArrayGetInfo(&d, &e, &flags, (cudaArray_t)array));
+    const bool fmt = d.f == cudaChannelFormatKindFloat && d.x == 32 && (channels == 2 ? d.y == 32 : d.y == 0) &&
+                     d.z == 0 && d.w == 0;
+    UBGL_REQUIRE(fmt && (int)e.width == w && (int)e.height == h, what);
+    cudaResourceDesc r{};
+    r.resType = cudaResourceTypeArray;
+    r.res.array.array = (cudaArray_t)array;
+    UBGL_CUDA(cudaCreateSurfaceObject(&obj, &r));
+  }
+  ~Surface() {
+    if (obj) cudaDestroySurfaceObject(obj);
+  }
+  Surface(const Surface &) = delete;
+  Surface &operator=(const Surface &) = delete;
+};
+} // namespace
+
 __device__ __forceinline__ unsigned wang_hash(unsigned seed) { // advect_tracer_points.cs:20-27
   seed = (seed ^ 61u) ^ (seed >> 16);
   seed *= 9u;
@@ -738,6 +785,57 @@ int ubgl_sim_colocate_velocity(ubgl_sim_t *sim, float *vxy_host, float *mag_host
   UBGL_CATCH
 }
 
+int ubgl_sim_export_display(ubgl_sim_t *sim, void *vxy_array, void *mag_array, void *p_array) {
+  UBGL_TRY
+  SIM(sim);
+  const int tw = 2 * S.W - 1, th = 2 * S.H - 1;
+  Surface sv(vxy_array, tw, th, 2, "export_display: vxy must be a (2W-1) x (2H-1) array of 2 x 32-bit float texels (RG32F)");
+  Surface sm(mag_array, tw, th, 1, "export_display: mag must be a (2W-1) x (2H-1) array of 32-bit float texels (R32F)");
+  Surface sp(p_array, S.W, S.H, 1, "export_display: p must be a W x H array of 32-bit float texels (R32F)");
+  if (sv.obj || sm.obj)
+    UBGL_LAUNCH(&S.lc, K_COLOCATE, 0, S.stream,
+                k_export_vxy<<<grd(tw, th), blk(), 0, S.stream>>>(S.field(F_VX_CURRENT), S.field(F_VY_CURRENT), S.W,
+                                                                 S.H, sv.obj, sm.obj));
+  if (sp.obj)
+    UBGL_LAUNCH(&S.lc, K_COLOCATE, 0, S.stream, k_export_scalar<<<grd(S.W, S.H), blk(), 0, S.stream>>>(S.field(F_P), sp.obj));
+  // the surface objects die with this call: the stores must have been issued against live handles
+  UBGL_CUDA(cudaStreamSynchronize(S.stream));
+  UBGL_CATCH
+}
+
+int ubgl_display_array_create(int w, int h, int channels, int device, void **array_out) {
+  UBGL_TRY
+  NEED(array_out, "array_out");
+  *array_out = nullptr;
+  UBGL_REQUIRE(w >= 1 && h >= 1 && (channels == 1 || channels == 2), "display_array: w, h >= 1, channels 1 or 2");
+  require_device(device);
+  UBGL_CUDA(cudaSetDevice(device));
+  const cudaChannelFormatDesc d = cudaCreateChannelDesc(32, channels == 2 ? 32 : 0, 0, 0, cudaChannelFormatKindFloat);
+  cudaArray_t a = nullptr;
+  UBGL_CUDA(cudaMallocArray(&a, &d, (size_t)w, (size_t)h, cudaArraySurfaceLoadStore));
+  *array_out = a;
+  UBGL_CATCH
+}
+
+int ubgl_display_array_read(void *array, float *host) {
+  UBGL_TRY
+  NEED(array, "array");
+  NEED(host, "host");
+  cudaChannelFormatDesc d{};
+  cudaExtent e{};
+  unsigned flags = 0;
+  UBGL_CUDA(cudaArrayGetInfo(&d, &e, &flags, (cudaArray_t)array));
+  const size_t row = e.width * (size_t)((d.x + d.y + d.z + d.w) / 8);
+  UBGL_CUDA(cudaMemcpy2DFromArray(host, row, (cudaArray_t)array, 0, 0, row, e.height, cudaMemcpyDeviceToHost));
+  UBGL_CATCH
+}
+
+int ubgl_display_array_destroy(void *array) {
+  UBGL_TRY
+  if (array) UBGL_CUDA(cudaFreeArray((cudaArray_t)array));
+  UBGL_CATCH
+}
+
 int ubgl_tracers_create(int ntracers, int npoints, int device, ubgl_tracers_t **out) {
   UBGL_TRY
   NEED(out, "out");
@@ -994,6 +1092,7 @@ int ubgl_sim_set_grids_all(ubgl_sim_t *sim, const float *newflag) {
     upload_grid(tmp, newflag, S.W, S.H, S.stream);
     nf = tmp.d;
   }
+  S.will_write(F_VX); // setGrids zeroes the front velocities in solids, not *_current
   UBGL_LAUNCH(&S.lc, K_TERRAIN, 0, S.stream,
               k_set_grids_all<<<grd(S.W, S.H), blk(), 0, S.stream>>>(fl, S.field(F_VX), S.field(F_VY), S.field(F_P), nf, nfp));
   if (newflag) {
@@ -1017,6 +1116,7 @@ int ubgl_sim_shift_map(ubgl_sim_t *sim, const float *new_last_column) {
   Grid none{};
   cudaStream_t st = S.stream;
   // velocities: front shifted, back receives the same values (ubootgl_app.cpp:254-266)
+  S.will_write(F_VX); // *_current keeps the unshifted field, like the reference's separate copy
   UBGL_LAUNCH(&S.lc, K_TERRAIN, 0, st, k_shift_rows<<<S.H, 256, 0, st>>>(S.field(F_VX), S.field(F_VXB), 2, nullptr));
   UBGL_LAUNCH(&S.lc, K_TERRAIN, 0, st, k_shift_rows<<<S.H - 1, 256, 0, st>>>(S.field(F_VY), S.field(F_VYB), 2, nullptr));
   UBGL_LAUNCH(&S.lc, K_TERRAIN, 0, st, k_shift_rows<<<S.H, 256, 0, st>>>(S.field(F_P), none, 1, nullptr)); // :268-272

@@ -134,6 +134,10 @@ struct TapRows {
   const float *x_lo = nullptr, *x_hi = nullptr; // vx front of the lower / upper neighbour (virtual row 0)
   const float *y_lo = nullptr, *y_hi = nullptr; // vy front likewise
   int *err = nullptr;
+  // k_advect_xy's one-compare form of "all four tap rows are stored locally":
+  // (unsigned)(icy - lo1) <= span, lo1 = lo + 1, span = min(hi, grid height) - 3 - lo1
+  int lo1 = 0;
+  unsigned span_x = 0, span_y = 0;
 };
 
 // The rare slab case -- a tap row that is not stored locally -- is kept out of line so that
@@ -479,14 +483,14 @@ __device__ __forceinline__ int floor_rz(float c, float &fl) {
 // them from the constant bank instead of converting w and h for every sample)
 template <bool SLAB>
 __device__ __forceinline__ float bicubic_pk(const float *__restrict__ g, int pitch, float wm3, float hm3, int h,
-                                            float cx, float cy, const TapRows &tr,
+                                            float cx, float cy, const TapRows &tr, unsigned span,
                                             const float *g_lo, const float *g_hi) {
   cx = fmaxf(fminf(cx, wm3), 3.0f);
   cy = fmaxf(fminf(cy, hm3), 3.0f);
   float flx, fly;
   const int icx = floor_rz(cx, flx), icy = floor_rz(cy, fly);
   const float stx = __fsub_rn(cx, flx), sty = __fsub_rn(cy, fly);
-  if (SLAB && (icy - 1 < tr.lo || icy + 2 >= min(tr.hi, h)))
+  if (SLAB && (unsigned)(icy - tr.lo1) > span) // icy - 1 < tr.lo || icy + 2 >= min(tr.hi, h)
     return bicubic_far(g, pitch, icx, icy, stx, sty, h, tr.lo, tr.hi, tr.plo, tr.phi, g_lo, g_hi, tr.err);
   f2 w0, w1, w2, w3; // (x weight, y weight) of tap 0..3
   cr_weights_xy(stx, sty, w0, w1, w2, w3);
@@ -564,10 +568,10 @@ __global__ void __launch_bounds__(256, OCC) k_advect_xy(Grid vx, Grid vy, Grid v
     const float vx1 = ux00;
     const float vy1 = __fmul_rn(__fadd_rn(__fadd_rn(uy00, uy0m), __fadd_rn(uy10, uy1m)), 0.25f);
     const float midx = __fmaf_rn(-vx1, half, posx), midy = __fmaf_rn(-vy1, half, posy);
-    const float vx2 = bicubic_pk<SLAB>(vx.d, pitch, lim.x, lim.y, vx.h, __fsub_rn(midx, 0.5f), midy, tr, tr.x_lo, tr.x_hi);
-    const float vy2 = bicubic_pk<SLAB>(vy.d, pitch, lim.z, lim.w, vy.h, midx, __fsub_rn(midy, 0.5f), tr, tr.y_lo, tr.y_hi);
+    const float vx2 = bicubic_pk<SLAB>(vx.d, pitch, lim.x, lim.y, vx.h, __fsub_rn(midx, 0.5f), midy, tr, tr.span_x, tr.x_lo, tr.x_hi);
+    const float vy2 = bicubic_pk<SLAB>(vy.d, pitch, lim.z, lim.w, vy.h, midx, __fsub_rn(midy, 0.5f), tr, tr.span_y, tr.y_lo, tr.y_hi);
     const float endx = __fmaf_rn(-vx2, full, posx), endy = __fmaf_rn(-vy2, full, posy);
-    const float xvel = bicubic_pk<SLAB>(vx.d, pitch, lim.x, lim.y, vx.h, __fsub_rn(endx, 0.5f), endy, tr, tr.x_lo, tr.x_hi);
+    const float xvel = bicubic_pk<SLAB>(vx.d, pitch, lim.x, lim.y, vx.h, __fsub_rn(endx, 0.5f), endy, tr, tr.span_x, tr.x_lo, tr.x_hi);
     vxb.d[o] = __fmul_rn(__fmul_rn(xvel, fC), fE);
   }
   if (acty) { // simulation.cpp:300-347
@@ -575,10 +579,10 @@ __global__ void __launch_bounds__(256, OCC) k_advect_xy(Grid vx, Grid vy, Grid v
     const float vy1 = uy00;
     const float vx1 = __fmul_rn(__fadd_rn(__fadd_rn(ux00, ux0m), __fadd_rn(ux10, ux1m)), 0.25f);
     const float midx = __fmaf_rn(-vx1, half, posx), midy = __fmaf_rn(-vy1, half, posy);
-    const float vx2 = bicubic_pk<SLAB>(vx.d, pitch, lim.x, lim.y, vx.h, __fsub_rn(midx, 0.5f), midy, tr, tr.x_lo, tr.x_hi);
-    const float vy2 = bicubic_pk<SLAB>(vy.d, pitch, lim.z, lim.w, vy.h, midx, __fsub_rn(midy, 0.5f), tr, tr.y_lo, tr.y_hi);
+    const float vx2 = bicubic_pk<SLAB>(vx.d, pitch, lim.x, lim.y, vx.h, __fsub_rn(midx, 0.5f), midy, tr, tr.span_x, tr.x_lo, tr.x_hi);
+    const float vy2 = bicubic_pk<SLAB>(vy.d, pitch, lim.z, lim.w, vy.h, midx, __fsub_rn(midy, 0.5f), tr, tr.span_y, tr.y_lo, tr.y_hi);
     const float endx = __fmaf_rn(-vx2, full, posx), endy = __fmaf_rn(-vy2, full, posy);
-    const float yvel = bicubic_pk<SLAB>(vy.d, pitch, lim.z, lim.w, vy.h, endx, __fsub_rn(endy, 0.5f), tr, tr.y_lo, tr.y_hi);
+    const float yvel = bicubic_pk<SLAB>(vy.d, pitch, lim.z, lim.w, vy.h, endx, __fsub_rn(endy, 0.5f), tr, tr.span_y, tr.y_lo, tr.y_hi);
     vyb.d[o] = __fmul_rn(__fmul_rn(yvel, fC), fN);
   }
 }
@@ -662,6 +666,7 @@ DeviceSim::DeviceSim(const float *host_flag, int W_, int H_, float pwidth_, floa
   // Simulation(flag,pwidth,mu) simulation.hpp:32-67
   bcS = 3; bcN = 3; bcW = 0; bcE = 2;
   h = pwidth / ((float)W - 1.0f);
+  if (const char *e = getenv("UBGL_LAZY_CURRENT")) lazy_current = e[0] != '0'; // A/B of the aliasing
   mg.reset(new DeviceMG(W, H, device, stream, &lc));
   upload_grid(flag, host_flag, W, H, stream);
   {
@@ -716,10 +721,17 @@ Grid DeviceSim::field(int id) {
   case F_R:
     if (!r.d) r = alloc_grid(W, H, pitch);
     return r;
-  case F_VX_CURRENT: return vxb[ixc];
-  case F_VY_CURRENT: return vyb[iyc];
+  case F_VX_CURRENT: return vxb[cur_alias ? ixf : ixc];
+  case F_VY_CURRENT: return vyb[cur_alias ? iyf : iyc];
   }
   throw ArgError{"unknown field id"};
+}
+
+void DeviceSim::will_write(int id) {
+  if (!cur_alias) return;
+  if (id != F_VX && id != F_VY && id != F_VX_CURRENT && id != F_VY_CURRENT) return;
+  cur_alias = false;
+  save_current(); // stream-ordered device copy front -> the spare third buffer
 }
 
 void DeviceSim::field_size(int id, int *w, int *hh) const {
@@ -732,6 +744,7 @@ void DeviceSim::field_size(int id, int *w, int *hh) const {
 
 void DeviceSim::upload(int id, const float *host) {
   UBGL_REQUIRE(host != nullptr, "upload: null host pointer");
+  will_write(id);
   Grid g = field(id);
   upload_grid(g, host, g.w, g.h, stream);
   UBGL_CUDA(cudaStreamSynchronize(stream)); // host buffer is only borrowed for the call
@@ -752,6 +765,7 @@ __global__ void k_add_packed(Grid dst, const float *__restrict__ src, int border
 void DeviceSim::upload_add(int id, const float *host) {
   UBGL_REQUIRE(host != nullptr, "upload_add: null host pointer");
   UBGL_REQUIRE(id != F_FLAG, "upload_add: not meaningful for the flag field");
+  will_write(id);
   Grid g = field(id);
   const size_t n = (size_t)g.w * g.h;
   if (n > cap_pack) {
@@ -849,6 +863,11 @@ bool launch_advect(const Grid &vx, const Grid &vy, const Grid &vxbk, const Grid 
     tr.lo = peers->st_lo; tr.hi = peers->st_hi; tr.plo = peers->peer_lo; tr.phi = peers->peer_hi;
     tr.x_lo = peers->vx_lo; tr.x_hi = peers->vx_hi; tr.y_lo = peers->vy_lo; tr.y_hi = peers->vy_hi;
     tr.err = peers->err;
+    tr.lo1 = tr.lo + 1;
+    // a slab thinner than 4 rows leaves no local sample at all: span wraps to "never"
+    const int sx = std::min(tr.hi, vx.h) - 3 - tr.lo1, sy = std::min(tr.hi, vy.h) - 3 - tr.lo1;
+    tr.span_x = sx >= 0 ? (unsigned)sx : 0u;
+    tr.span_y = sy >= 0 ? (unsigned)sy : 0u;
   }
   if (variant == 3 && mask) {
     const float4 lim = make_float4((float)vx.w - 3.0f, (float)vx.h - 3.0f, (float)vy.w - 3.0f, (float)vy.h - 3.0f);
@@ -858,8 +877,19 @@ bool launch_advect(const Grid &vx, const Grid &vy, const Grid &vxbk, const Grid 
       const char *e = getenv("UBGL_ADVECT_OCC");
       return e ? atoi(e) : 6;
     }();
+    // UBGL_ADVECT_FORCE_SLAB=1: the slab build of the kernel on a single GPU (every row is local),
+    // to measure what its per-sample row test costs
+    static const bool force_slab = [] {
+      const char *e = getenv("UBGL_ADVECT_FORCE_SLAB");
+      return e && e[0] == '1';
+    }();
+    if (force_slab && !peers) {
+      tr.lo = tr.plo = 0; tr.hi = tr.phi = vx.h;
+      tr.lo1 = 1;
+      tr.span_x = (unsigned)(vx.h - 4); tr.span_y = (unsigned)(vy.h - 4);
+    }
 #define UBGL_ADV_XY(S_, O_) UBGL_LAUNCH(lc, K_ADVECT, LVL, stream, (k_advect_xy<S_, O_><<<g, b, 0, stream>>>(vx, vy, vxbk, vybk, mask, ax, ay, half, full, lim, y_lo, y_hi, tr)))
-    if (peers) {
+    if (peers || force_slab) {
       if (occ == 4) {
         UBGL_ADV_XY(true, 4);
       } else {
@@ -1064,6 +1094,7 @@ void DeviceSim::save_current() {
 
 void DeviceSim::stage(int st, float dt_) {
   dt = dt_;
+  will_write(F_VX); // the stages work on the front buffers in place
   switch (st) {
   case ST_ACCUM: apply_accum(); break;
   case ST_DIFFUSE: diffuse(); break;
@@ -1151,7 +1182,9 @@ void DeviceSim::step(float dt_) {
   int k = 0;
   auto mark = [&]() { if (timing) UBGL_CUDA(cudaEventRecord(ev[k++], stream)); };
   mark();
+  if (!fz) will_write(F_VX);
   if (fz) {
+    cur_alias = false; // the third buffers are scratch during the fused step, as before
     // small grids replay CUDA graphs of the two launch sequences (see sim.cuh)
     const bool graphable = use_graph && !timing && !lc.prof && tol <= 0.0f && (size_t)W * H <= ((size_t)1 << 22);
     mark(); // applyAccumulatedVelocity is part of the fused diffuse pass
@@ -1170,12 +1203,13 @@ void DeviceSim::step(float dt_) {
       solve_cycles();
       fused_gradient_save(); // reads only interior p: independent of setPBC
       mark();
-      fused_borders(true, true); // setPBC + setVBCs, also into vx_current / vy_current
+      fused_borders(true, !lazy_current); // setPBC + setVBCs, also into vx_current / vy_current
     });
     if (graphable) { // what solve_cycles() records on the host
       cycles_done = vcycles;
       res_hist.clear();
     }
+    cur_alias = lazy_current;
     mark();
     mark();
   } else {

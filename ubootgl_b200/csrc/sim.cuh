@@ -88,6 +88,13 @@ public:
   DeviceSim &operator=(const DeviceSim &) = delete;
 
   Grid field(int id); // current device grid of a public member (front/back resolved)
+  // vx_current / vy_current are byte copies of the final front buffers
+  // (saveCurrentVelocityFields, simulation.cpp:16-19).  The fused step does not write them a
+  // second time (8 B/cell of HBM stores): after it the *_current role ALIASES the front buffer
+  // (cur_alias) and field() resolves it so; will_write(id) -- called by everything that is about
+  // to change a front or *_current buffer outside step() -- makes the real copy first.
+  void will_write(int id);
+  bool lazy_current = true, cur_alias = false;
   void field_size(int id, int *w, int *h) const;
   void upload(int id, const float *host);
   void upload_add(int id, const float *host); // field += host grid

@@ -327,26 +327,31 @@ __global__ void __launch_bounds__(32) k_prestep_run(PrestepArgs g, PrestepRunGeo
 
   float4 v[4], d[4]; // rolling rows: slot = row & 3
   unsigned m[4], mWn[4], mEn[4];
-  auto load_row = [&](int r, int k) {
-    float4 A = make_float4(0.f, 0.f, 0.f, 0.f);
-    unsigned mw = 0u;
+  // A row is fetched in two halves, one loop iteration apart: issue_row() starts the three
+  // 128-/32-bit loads of row r + 2 into nA / nC / nM, commit_row() of the NEXT iteration turns
+  // them into v0 = front + accumulator and the neighbour mask bytes.  Between the two sits one
+  // iteration of arithmetic (both passes of one row), so the warp no longer stalls on its own
+  // loads (ncu r02: long scoreboard was 72 % of this kernel's stall samples at 62 % DRAM).
+  float4 nA, nC;
+  unsigned nM;
+  auto issue_row = [&](int r) {
+    nA = nC = make_float4(0.f, 0.f, 0.f, 0.f);
+    nM = 0u;
     if (col_ok && r >= g.st_lo) {
       const size_t o = (size_t)r * pitch + gx;
       if (r < s_hi) {
-        A = *reinterpret_cast<const float4 *>(g.A + o);
-        const float4 ac = *reinterpret_cast<const float4 *>(g.acc + o); // every row here is interior
-        A.x = __fadd_rn(A.x, ac.x);
-        A.y = __fadd_rn(A.y, ac.y);
-        A.z = __fadd_rn(A.z, ac.z);
-        A.w = __fadd_rn(A.w, ac.w);
+        nA = *reinterpret_cast<const float4 *>(g.A + o);
+        nC = *reinterpret_cast<const float4 *>(g.acc + o); // every row here is interior
       }
-      if (r < m_hi) mw = __ldg(reinterpret_cast<const unsigned *>(g.mask + o));
+      if (r < m_hi) nM = __ldg(reinterpret_cast<const unsigned *>(g.mask + o));
     }
-    v[k] = A;
-    m[k] = mw;
+  };
+  auto commit_row = [&](int k) {
+    v[k] = make_float4(__fadd_rn(nA.x, nC.x), __fadd_rn(nA.y, nC.y), __fadd_rn(nA.z, nC.z), __fadd_rn(nA.w, nC.w));
+    m[k] = nM;
     // mask bytes of the cells left and right of this lane's four
-    mWn[k] = __shfl_up_sync(0xffffffffu, mw, 1) >> 24;
-    mEn[k] = __shfl_down_sync(0xffffffffu, mw, 1) & 255u;
+    mWn[k] = __shfl_up_sync(0xffffffffu, nM, 1) >> 24;
+    mEn[k] = __shfl_down_sync(0xffffffffu, nM, 1) & 255u;
   };
   auto west = [&](const float4 &x) { return __shfl_up_sync(0xffffffffu, x.w, 1); };
   auto east = [&](const float4 &x) { return __shfl_down_sync(0xffffffffu, x.x, 1); };
@@ -354,13 +359,16 @@ __global__ void __launch_bounds__(32) k_prestep_run(PrestepArgs g, PrestepRunGeo
   // Row r lives in slot r & 3.  The loop starts on a multiple of 4 so that inside the unrolled
   // body every slot index is a compile-time constant (the arrays stay in registers); the up to
   // three rows before the first needed one are skipped by uniform tests.
-  // Iteration r: load row r+1; pass 1 on row r (rows c0-1 .. c1); pass 2 on row r-1 (rows c0 .. c1-1).
+  // Iteration r: row r+1 arrives (its loads were issued one iteration earlier), the loads of row
+  // r+2 start; pass 1 on row r (rows c0-1 .. c1); pass 2 on row r-1 (rows c0 .. c1-1).
+  issue_row(c0 - 2);
   for (int rb = (c0 - 3) & ~3; rb <= c1; rb += 4) {
 #pragma unroll
     for (int u = 0; u < 4; u++) {
       const int r = rb + u;
       const int kC = u, kS = (u + 3) & 3, kN = (u + 1) & 3, kS2 = (u + 2) & 3;
-      if (r + 1 >= c0 - 2 && r <= c1) load_row(r + 1, kN);
+      if (r + 1 >= c0 - 2 && r <= c1) commit_row(kN);
+      if (r + 2 >= c0 - 1 && r + 2 <= c1 + 1) issue_row(r + 2);
       if (r >= c0 - 1 && r <= c1) {
         const float4 D = prestep_row<COMP>(v[kS], v[kC], v[kN], west(v[kC]), east(v[kC]), m[kS], m[kC], m[kN],
                                            mWn[kC], mEn[kC], g.a, g.rden);
@@ -539,8 +547,10 @@ __global__ void k_gradient_save(Grid vx, Grid vy, Grid p, const uint8_t *mask, G
   if (x >= 1 && x + 3 <= W - 3 && y <= H - 3) {
     *reinterpret_cast<float4 *>(vx.d + o) = ux;
     *reinterpret_cast<float4 *>(vy.d + o) = uy;
-    *reinterpret_cast<float4 *>(cx.d + o) = ux;
-    *reinterpret_cast<float4 *>(cy.d + o) = uy;
+    if (cx.d) { // null: the caller aliases *_current to the front buffers (DeviceSim::cur_alias)
+      *reinterpret_cast<float4 *>(cx.d + o) = ux;
+      *reinterpret_cast<float4 *>(cy.d + o) = uy;
+    }
   } else {
     const float ax[4] = {ux.x, ux.y, ux.z, ux.w}, ay[4] = {uy.x, uy.y, uy.z, uy.w};
 #pragma unroll
@@ -549,11 +559,11 @@ __global__ void k_gradient_save(Grid vx, Grid vy, Grid p, const uint8_t *mask, G
       if (xx < 1 || xx > W - 2) continue;
       if (xx <= W - 3) { // vx faces 1..W-3 x 1..H-2
         vx.d[o + j] = ax[j];
-        cx.d[o + j] = ax[j];
+        if (cx.d) cx.d[o + j] = ax[j];
       }
       if (y <= H - 3) { // vy faces 1..W-2 x 1..H-3
         vy.d[o + j] = ay[j];
-        cy.d[o + j] = ay[j];
+        if (cx.d) cy.d[o + j] = ay[j];
       }
     }
   }
@@ -699,8 +709,9 @@ void DeviceSim::fused_divergence(bool zero_accum) {
 }
 
 void DeviceSim::fused_gradient_save() {
-  launch_gradient_save(vxb[ixf], vyb[iyf], p, mg->mask0_ptr(), vxb[ixc], vyb[iyc], 1.0f / h, 1, H - 1,
-                       stream, &lc);
+  const Grid none{};
+  launch_gradient_save(vxb[ixf], vyb[iyf], p, mg->mask0_ptr(), lazy_current ? none : vxb[ixc],
+                       lazy_current ? none : vyb[iyc], 1.0f / h, 1, H - 1, stream, &lc);
 }
 
 } // namespace ubgl

@@ -245,6 +245,7 @@ SlabSim::SlabSim(const float *flag_slab, int W_, int H_, float pwidth_, float mu
   UBGL_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
   pitch = round_up(W, 32);
   h = pwidth / ((float)W - 1.0f);
+  if (const char *e = getenv("UBGL_LAZY_CURRENT")) lazy_current = e[0] != '0';
 
   // arena size: control block + 14 level-0 fp32 slabs + mask, the distributed
   // pyramid (4 fp32 + mask per level) and the replicated levels (same arrays, whole)
@@ -461,10 +462,25 @@ Grid SlabSim::field(int id) {
   case F_F: return f;
   case F_VX_ACCUM: return vx_accum;
   case F_VY_ACCUM: return vy_accum;
-  case F_VX_CURRENT: return vxb[ixc];
-  case F_VY_CURRENT: return vyb[iyc];
+  case F_VX_CURRENT: return vxb[cur_alias ? ixf : ixc];
+  case F_VY_CURRENT: return vyb[cur_alias ? iyf : iyc];
   }
   throw ArgError{"unknown / unsupported field id in slab mode"};
+}
+
+void SlabSim::will_write(int id) {
+  if (!cur_alias) return;
+  if (id != F_VX && id != F_VY && id != F_VX_CURRENT && id != F_VY_CURRENT) return;
+  cur_alias = false;
+  const Rows R = plan.rows(0);
+  auto copy = [&](const Grid &src, const Grid &dst) { // stored rows, whole pitch
+    const int n = std::min(R.st_hi, src.h) - R.st_lo;
+    if (n > 0)
+      UBGL_CUDA(cudaMemcpyAsync(&dst.at(0, R.st_lo), &src.at(0, R.st_lo), sizeof(float) * (size_t)src.pitch * n,
+                                cudaMemcpyDeviceToDevice, stream));
+  };
+  copy(vxb[ixf], vxb[ixc]);
+  copy(vyb[iyf], vyb[iyc]);
 }
 
 void SlabSim::field_rows(int id, int *row_lo, int *nrows, int *w) const {
@@ -482,6 +498,7 @@ void SlabSim::field_rows(int id, int *row_lo, int *nrows, int *w) const {
 
 void SlabSim::upload(int id, const float *host) {
   UBGL_REQUIRE(host != nullptr, "upload: null host pointer");
+  will_write(id);
   Grid g = field(id);
   int r0, n, w;
   field_rows(id, &r0, &n, &w);
@@ -626,6 +643,7 @@ void SlabSim::project_sinks() {
 // ---------------------------------------------------------------------------
 void SlabSim::step(float dt_) {
   dt = dt_;
+  cur_alias = false; // the third buffers are scratch during the step
   const Rows R = plan.rows(0);
   const bool first = plan.rank == 0, last = plan.rank == plan.nranks - 1;
   const float ih = 1.0f / h;
@@ -719,9 +737,11 @@ void SlabSim::step(float dt_) {
   // neighbours' ghost copies must hold the BC'd border columns
   launch_pbc(p, bcW, bcE, bcN, bcS, R.own_lo, R.own_hi, first, last, stream, &lc);
   if (vcycles > 0) exchange({xf(p, 0)}, 8);
-  launch_gradient_save(vxb[ixf], vyb[iyf], p, mask0, vxb[ixc], vyb[iyc], ih, R.own_lo, R.own_hi,
-                       stream, &lc);
-  borders(false, true);
+  const Grid none{};
+  launch_gradient_save(vxb[ixf], vyb[iyf], p, mask0, lazy_current ? none : vxb[ixc], lazy_current ? none : vyb[iyc],
+                       ih, R.own_lo, R.own_hi, stream, &lc);
+  borders(false, !lazy_current);
+  cur_alias = lazy_current;
   exchange({xf(vxb[ixf], 0), xf(vyb[iyf], 0)}, 4); // entry invariant of the next step
 }
 

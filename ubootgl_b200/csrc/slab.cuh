@@ -151,6 +151,9 @@ private:
   std::vector<Level> lv;
   Grid vxb[3], vyb[3];
   int ixf = 0, ixb = 1, ixc = 2, iyf = 0, iyb = 1, iyc = 2;
+  // *_current aliases the front buffers after a step until somebody writes either (DeviceSim::cur_alias)
+  bool lazy_current = true, cur_alias = false;
+  void will_write(int id);
   Grid vx_accum, vy_accum, p, scratch0, f, flag, r;
   uint8_t *mask0 = nullptr;
   int *d_nonbinary = nullptr;

@@ -53,9 +53,43 @@ def run(args, name):
     if os.environ.get("UBGL_SLAB_BALANCE", "0") == "1":
         frac = cases.channel_row_fluid_fraction(W, H, seed=1234)
         u.slab_set_row_weights((0.73 + 0.27 * frac).astype(np.float32))
+    dt = float(np.float32(bench.PWIDTH) / np.float32(W - 1))  # dt = h, CFL ~ 1
+    if os.environ.get("UBGL_SLAB_SWEEP_MIN_ROWS"):  # tuning run: distributed-level depth (slab.cu: slab_min_rows)
+        import sys
+        for mr in os.environ["UBGL_SLAB_SWEEP_MIN_ROWS"].split(","):
+            os.environ["UBGL_SLAB_MIN_ROWS"] = mr
+            pl = u.slab_plan(W, H, world, rank)
+            fl = cases.channel_flag_rows(W, H, pl["st_lo"], pl["st_hi"], seed=1234)
+            sm = u.SlabSimulation(fl, W, H, rank, world, slab_boot.blob_exchange(), bench.PWIDTH, bench.MU, device=dev)
+            v0 = (fl[:, :-1] * fl[:, 1:]).astype(np.float32)
+            v0[:, 0] = 1.0
+            sm.set(capi.VX, v0)
+            st = torch.cuda.ExternalStream(sm.stream(), device=dev)
+            for _ in range(3):
+                sm.step(dt)
+            sm.sync()
+            blocks = []
+            for _ in range(3):  # three timed blocks of 10 steps
+                slab_boot.barrier()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(st)
+                for _ in range(10):
+                    sm.step(dt)
+                b.record(st)
+                sm.sync()
+                blocks.append(round(slab_boot.allreduce_max(a.elapsed_time(b)) / 10, 3))
+            x_, _b = sm.stats()
+            res = float(np.sqrt(slab_boot.allreduce_sum(sm.residual_sumsq())))
+            if rank == 0:
+                print(f"[sweep] min_rows {mr}: dist levels {pl['dist_levels']}, ms/step per block {blocks}, "
+                      f"exchanges/step {x_ / 33:.1f}, residual {res:.6f}", file=sys.stderr, flush=True)
+            slab_boot.barrier()
+            sm.close()
+            del sm, st
+            slab_boot.barrier()
+        os.environ.pop("UBGL_SLAB_MIN_ROWS", None)
     plan = u.slab_plan(W, H, world, rank)
     all_rows = [u.slab_plan(W, H, world, r) for r in range(world)]
-    dt = float(np.float32(bench.PWIDTH) / np.float32(W - 1))  # dt = h, CFL ~ 1
     # synthetic input, generated slab-wise: only the rows this rank stores
     flag = cases.channel_flag_rows(W, H, plan["st_lo"], plan["st_hi"], seed=1234)
     sim = u.SlabSimulation(flag, W, H, rank, world, slab_boot.blob_exchange(), bench.PWIDTH, bench.MU,
@@ -133,6 +167,25 @@ def run(args, name):
     slab_boot.barrier()
     t_e2e = slab_boot.allreduce_max((time.perf_counter() - t0) / KE)
     h2d_all, d2h_all = slab_boot.allreduce_sum(h2d), slab_boot.allreduce_sum(d2h)
+    if os.environ.get("UBGL_SLAB_E2E_SWEEP"):  # diagnosis: host copy threads per rank, and without the *_current mirrors
+        sweep = {}
+        for nt in (16, 4, 2, 1):
+            os.environ["UBGL_HOST_THREADS"] = str(nt)
+            for tag, bb in (("all", bufs), ("no_current", {k: v for k, v in bufs.items() if "current" not in k}),
+                            ("no_accum", {k: v for k, v in bufs.items() if "accum" not in k})):
+                if nt != 16 and tag != "all":
+                    continue
+                sim.step_host(dt, **bb)
+                slab_boot.barrier()
+                t0 = time.perf_counter()
+                sim.step_host(dt, **bb)
+                mine = time.perf_counter() - t0
+                slab_boot.barrier()
+                sweep[f"{tag}_threads{nt}"] = (round(slab_boot.allreduce_max(mine) * 1e3, 1),
+                                               round(-slab_boot.allreduce_max(-mine) * 1e3, 1))
+        os.environ.pop("UBGL_HOST_THREADS", None)
+        if rank == 0:
+            print("e2e sweep, ms (max rank, min rank):", json.dumps(sweep), flush=True)
 
     clocks = clk.summary()
     if rank != 0:
