@@ -141,6 +141,13 @@ class ClockSampler:
                 pass
             time.sleep(0.05 if self.nvml else 0.1)
 
+    def sample_once(self):
+        """One sample from the calling thread (the multi-GPU runs: see slab_bench.py)."""
+        try:
+            self.sample_nvml() if self.nvml else self.sample_smi()
+        except Exception:
+            pass
+
     def __enter__(self):
         self.t.start()
         return self

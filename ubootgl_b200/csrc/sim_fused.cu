@@ -314,7 +314,7 @@ struct PrestepRunGeom {
 // PRW = rows per warp strip: 64 on large grids (pass 1 runs on PRW + 2 rows), 16 where that would
 // leave the GPU short of warps.
 template <int COMP, int PRW>
-__global__ void __launch_bounds__(32) k_prestep_run(PrestepArgs g, PrestepRunGeom q) {
+__global__ void __launch_bounds__(32, 32) k_prestep_run(PrestepArgs g, PrestepRunGeom q) {
   const int lane = threadIdx.x;
   const int bx = q.bx0 + blockIdx.x;
   const int c0 = q.ya + blockIdx.y * PRW; // first output row of this warp
@@ -332,6 +332,9 @@ __global__ void __launch_bounds__(32) k_prestep_run(PrestepArgs g, PrestepRunGeo
   // them into v0 = front + accumulator and the neighbour mask bytes.  Between the two sits one
   // iteration of arithmetic (both passes of one row), so the warp no longer stalls on its own
   // loads (ncu r02: long scoreboard was 72 % of this kernel's stall samples at 62 % DRAM).
+  // Measured at 8192^2, both components: 0.492 -> 0.460 ms with the register budget held at 64
+  // (__launch_bounds__(32, 32): 32 warps per SM; at 68 registers / 28 warps it LOST: 0.522 ms);
+  // an additional prefetch.global.L2 four rows ahead lost as well (0.524 ms) and was removed.
   float4 nA, nC;
   unsigned nM;
   auto issue_row = [&](int r) {

@@ -12,11 +12,15 @@ namespace ubgl {
 // ---------------------------------------------------------------------------
 // plan (pure host)
 // ---------------------------------------------------------------------------
-// own rows per rank on the coarsest distributed level; coarser levels are replicated
-// (an exchange costs ~20 us of NVLink latency, a replicated 512^2 level about as much)
-static int slab_min_rows() {
+// own rows per rank on the coarsest distributed level; coarser levels are replicated.
+// A distributed coarse level costs a ~14 us kernel + a ~20 us exchange per leg whatever its
+// size, a replicated one only the kernel (plus a larger all-gather, once): measured at 8 GPUs on
+// 32768^2 (tools/gpu_t.sh) 9.35 / 9.31 / 9.27 / 9.36 / 9.88 ms per step for 64 / 128 / 256 / 512 /
+// 1024 rows.  Tall slabs therefore stop distributing at 256 rows (which also aligns the cuts to 32
+// rows instead of 128: finer load balancing); short ones keep 64 so that small grids still split.
+static int slab_min_rows(int H, int nranks) {
   const char *e = getenv("UBGL_SLAB_MIN_ROWS");
-  const int v = e ? atoi(e) : 64;
+  const int v = e ? atoi(e) : (H / nranks >= 2048 ? 256 : 64);
   return v >= 32 ? v : 32;
 }
 
@@ -51,7 +55,7 @@ SlabPlan make_slab_plan(int W, int H, int nranks, int rank) {
   UBGL_REQUIRE(P.levels >= 3, "slab: grid too small for a multigrid pyramid");
   const int L = P.levels - 2; // coarsest used level (pressure_solver.cpp:203)
   int n = 0;
-  const int min_rows = slab_min_rows();
+  const int min_rows = slab_min_rows(H, nranks);
   while (n < L && ((H >> n) / nranks) >= min_rows) n++;
   UBGL_REQUIRE(n >= 1, "slab: fewer than 64 rows per GPU at level 0 -- use fewer GPUs");
   P.ndist = n;
@@ -105,8 +109,13 @@ int SlabPlan::max_stored_rows(int l) const {
 // halo kernels
 // ---------------------------------------------------------------------------
 // Copies every segment with 128-bit loads/stores (dst is peer memory mapped over
-// NVLink), then publishes: all threads fence their stores system-wide, the last
-// block to finish releases `seq` into the peers' signal slots.
+// NVLink), then publishes: every thread fences its stores system-wide, the last
+// block to finish releases `seq` into the peers' signal slots, one slot per thread.
+// The critical path of an exchange is launch -> stores -> fence -> (block count) -> release
+// -> the neighbour's spin; a step makes ~34 of them, so nothing else sits on it: a launch of a
+// single block (the small exchanges of the coarse levels) skips the block counter altogether, the counter is
+// re-armed AFTER the release, and no fence follows the release (nothing later in this kernel
+// depends on it; the peer polls its own memory).
 __global__ void __launch_bounds__(256) k_halo_push(HaloPush a) {
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t nthreads = (size_t)gridDim.x * blockDim.x;
@@ -116,24 +125,24 @@ __global__ void __launch_bounds__(256) k_halo_push(HaloPush a) {
     const size_t n = a.seg[s].n16;
     for (size_t i = tid; i < n; i += nthreads) dst[i] = src[i];
   }
-  __threadfence_system();
+  __threadfence_system(); // this thread's peer stores are performed before anything below
   __syncthreads();
   __shared__ int is_last;
-  if (threadIdx.x == 0) {
+  if (gridDim.x == 1) {
+    if (threadIdx.x == 0) is_last = 1;
+  } else if (threadIdx.x == 0) {
     const unsigned done = atomicAdd(a.counter, 1u);
     is_last = done == gridDim.x - 1;
-    if (is_last) {
-      *a.counter = 0; // ready for the next launch on this stream
-      __threadfence_system();
-      for (int i = 0; i < a.nsig; i++)
-        if (a.sig[i]) *reinterpret_cast<volatile unsigned *>(a.sig[i]) = a.seq;
-      __threadfence_system();
-    }
+    if (is_last) __threadfence_system(); // the other blocks' stores (fenced before their atomicAdd) before the release
   }
   __syncthreads();
+  if (!is_last) return;
+  if ((int)threadIdx.x < a.nsig && a.sig[threadIdx.x])
+    *reinterpret_cast<volatile unsigned *>(a.sig[threadIdx.x]) = a.seq;
+  if (threadIdx.x == 0 && gridDim.x > 1) *a.counter = 0; // ready for the next launch on this stream
   // the last block stays until the neighbours have released the same sequence number into
   // this rank's slots (bounded spin, see k_halo_wait); every rank releases before it waits
-  if (is_last && (int)threadIdx.x < a.nwait) {
+  if ((int)threadIdx.x < a.nwait) {
     volatile unsigned *s = a.wait[threadIdx.x];
     const long long t0 = clock64();
     while ((int)(*s - a.seq) < 0) {
@@ -141,9 +150,9 @@ __global__ void __launch_bounds__(256) k_halo_push(HaloPush a) {
         *a.err = 2;
         break;
       }
-      __nanosleep(100);
+      __nanosleep(40);
     }
-    __threadfence_system();
+    __threadfence_system(); // acquire: the ghost rows the neighbour stored before its release
   }
 }
 
@@ -168,7 +177,9 @@ __global__ void k_halo_wait(unsigned *s0, unsigned *s1, unsigned *s2, unsigned *
 }
 
 void launch_halo_push(const HaloPush &a, size_t total16, cudaStream_t stream, LaunchCounter *lc) {
-  int blocks = (int)std::min<size_t>(148 * 2, (total16 + 255) / 256);
+  // up to 4 K 16-byte words (64 KB, the coarse distributed levels): one block, 16 independent
+  // load/store pairs per thread, no block counter; larger: ~4 per thread over up to 2 blocks per SM
+  int blocks = total16 <= (size_t)(4 << 10) ? 1 : (int)std::min<size_t>(148 * 2, (total16 + 1023) / 1024);
   if (blocks < 1) blocks = 1;
   UBGL_LAUNCH(lc, K_HALO_PUSH, 0, stream, k_halo_push<<<blocks, 256, 0, stream>>>(a));
 }

@@ -52,7 +52,9 @@ def run(args, name):
     # jitter, not on a systematic imbalance; the API stays, the bench uses equal heights unless asked)
     if os.environ.get("UBGL_SLAB_BALANCE", "0") == "1":
         frac = cases.channel_row_fluid_fraction(W, H, seed=1234)
-        u.slab_set_row_weights((0.73 + 0.27 * frac).astype(np.float32))
+        # fit of the per-rank advect times of an 8-GPU profile (gpurun_out/s2_tl.*): t = 0.739 + 2.063 frac ms per
+        # 4096 rows, beside 6.4 ms per 4096 rows for everything else
+        u.slab_set_row_weights((0.776 + 0.224 * frac).astype(np.float32))
     dt = float(np.float32(bench.PWIDTH) / np.float32(W - 1))  # dt = h, CFL ~ 1
     if os.environ.get("UBGL_SLAB_SWEEP_MIN_ROWS"):  # tuning run: distributed-level depth (slab.cu: slab_min_rows)
         import sys
@@ -109,13 +111,25 @@ def run(args, name):
     l0 = sim.launch_count()
     x0, b0 = sim.stats()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with bench.ClockSampler(dev) as clk:
-        e0.record(stream)
-        for _ in range(K):
-            sim.step(dt)
-        e1.record(stream)
-        sim.sync()
-        torch.cuda.synchronize()
+    # Clocks and throttle reasons DURING the timed region, without a sampling thread: the ranks run in
+    # lockstep (34 neighbour exchanges per step), so an NVML query that holds up ONE rank's launches for a
+    # millisecond holds up all of them -- a 50 ms sampling thread per rank cost 0.65 ms per step at 8 GPUs
+    # (10.0 vs 9.35 ms, tools/gpu_t.sh).  The launches of the K steps are queued well ahead of the GPU; every
+    # rank then samples from this thread while its GPU is still working through them.
+    clk = bench.ClockSampler(dev)
+    e0.record(stream)
+    for _ in range(K):
+        sim.step(dt)
+    e1.record(stream)
+    for _ in range(3):
+        if e1.query():
+            break
+        clk.sample_once()
+        time.sleep(0.01)
+    sim.sync()
+    torch.cuda.synchronize()
+    if not clk.rows:  # a run too short to catch in flight: one sample right behind it
+        clk.sample_once()
     slab_boot.barrier()
     ms_total = slab_boot.allreduce_max(e0.elapsed_time(e1))
     launches = slab_boot.allreduce_sum(sim.launch_count() - l0)
@@ -188,6 +202,17 @@ def run(args, name):
             print("e2e sweep, ms (max rank, min rank):", json.dumps(sweep), flush=True)
 
     clocks = clk.summary()
+    # the slowest clock and the union of the throttle reasons over all ranks
+    bits = sum(1 << i for i, nm in enumerate(bench.ClockSampler.NAMES) if nm in clocks["reasons"])
+    allbits = 0
+    for i in range(len(bench.ClockSampler.NAMES)):
+        if slab_boot.allreduce_max(float((bits >> i) & 1)) > 0:
+            allbits |= 1 << i
+    clocks["reasons"] = [nm for i, nm in enumerate(bench.ClockSampler.NAMES) if allbits & (1 << i)]
+    lo = -slab_boot.allreduce_max(-(clocks["sm_mhz"] if clocks["sm_mhz"] is not None else 1e9))
+    clocks["sm_mhz"] = lo if lo < 1e9 else None
+    clocks["samples"] = int(slab_boot.allreduce_sum(float(clocks["samples"])))
+    clocks["source"] += " (every rank, from the launching thread after the steps were queued; min clock / union of reasons over ranks)"
     if rank != 0:
         return
     cpu = None
