@@ -1,6 +1,6 @@
 """Helper of tests/test_gpu_advect_variants.py: runs the advect stage and two whole steps on
-seeded inputs with whatever UBGL_ADVECT_VARIANT the environment selects (the variant is
-fixed per process) and dumps the velocity fields.
+seeded inputs with whatever UBGL_ADVECT_VARIANT / UBGL_ADVECT_DIV the environment selects (fixed
+per process) and dumps the velocity fields, p and f.
     python tests/advect_dump.py OUT.npz
 """
 import os
@@ -33,6 +33,7 @@ def main(out):
             res[f"{W}x{H}_{tag}_vx2"] = s.get(capi.VX)
             res[f"{W}x{H}_{tag}_vy2"] = s.get(capi.VY)
             res[f"{W}x{H}_{tag}_p2"] = s.get(capi.P)
+            res[f"{W}x{H}_{tag}_f2"] = s.get(capi.F)
     np.savez(out, **res)
 
 

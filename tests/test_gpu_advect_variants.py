@@ -26,3 +26,23 @@ def test_pair_kernels_equal_single_face_kernels(ubgl, tmp_path):
         x, y = a[k], b[k]
         same = (x.view(np.uint32) == y.view(np.uint32)) | ((x == 0) & (y == 0))
         assert same.all(), (k, float(np.abs(x - y).max()))
+
+
+def test_divergence_in_the_advect_epilogue_equals_the_separate_pass(ubgl, tmp_path):
+    """UBGL_ADVECT_DIV=1: k_advect_xy<DIV> writes f = -(1/h) div v of its cells from the freshly advected faces
+    (left lane by shuffle, lower row through shared memory), k_divergence_edges the CTA edges and the ring next to
+    the BC faces after setVBCs -- bit for bit the f, p and velocities of the default (k_divergence4 as its own pass)."""
+    outs = []
+    for div in ("0", "1"):
+        out = str(tmp_path / f"advect_div{div}.npz")
+        env = dict(os.environ, UBGL_ADVECT_DIV=div)
+        env.pop("UBGL_ADVECT_VARIANT", None)
+        subprocess.run([sys.executable, os.path.join(ROOT, "tests", "advect_dump.py"), out], check=True, env=env,
+                       timeout=300)
+        outs.append(np.load(out))
+    a, b = outs
+    assert sorted(a.files) == sorted(b.files) and any(k.endswith("_f2") for k in a.files)
+    for k in a.files:
+        x, y = a[k], b[k]
+        same = (x.view(np.uint32) == y.view(np.uint32)) | ((x == 0) & (y == 0))
+        assert same.all(), (k, float(np.abs(x - y).max()))

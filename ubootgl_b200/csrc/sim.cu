@@ -513,11 +513,18 @@ __device__ __forceinline__ float bicubic_pk(const float *__restrict__ g, int pit
 
 enum { AMB_C = 1, AMB_W = 2, AMB_E = 32, AMB_S = 64, AMB_N = 128 }; // stencil mask bits (mg_fused.cu)
 
-template <bool SLAB, int OCC>
+// DIV: the divergence of the advected field (simulation.cpp:166-171) in the epilogue, for the cells
+// whose four faces this CTA holds: f(x, y) needs vx(x-1, y) -- the left lane's face, by shuffle -- and
+// vy(x, y-1) -- the face of the thread one row down, through 1 KB of shared memory.  Faces this
+// launch does not advect (skipped octets, last columns) are read back from the buffer they stay in.
+// The CTA's first row and first column, and the ring of cells next to the border faces setVBCs
+// rewrites afterwards, are left to k_divergence_edges (after setVBCs).  Same operation order as
+// k_divergence: bit-identical f.
+template <bool SLAB, int OCC, bool DIV>
 __global__ void __launch_bounds__(256, OCC) k_advect_xy(Grid vx, Grid vy, Grid vxb, Grid vyb,
                                                       const uint8_t *__restrict__ mask, float *ax, float *ay,
                                                       float half, float full, float4 lim /* vx.w-3, vx.h-3, vy.w-3, vy.h-3 */,
-                                                      int y_lo, int y_hi, TapRows tr) {
+                                                      int y_lo, int y_hi, TapRows tr, float *fdiv, float nih) {
   const int lane = threadIdx.x;
   const int xi = 1 + blockIdx.x * 32 + lane;
   const int y = y_lo + blockIdx.y * blockDim.y + threadIdx.y; // y_lo >= 1, y_hi <= H-1
@@ -558,10 +565,11 @@ __global__ void __launch_bounds__(256, OCC) k_advect_xy(Grid vx, Grid vy, Grid v
   const unsigned bx = __ballot_sync(0xffffffffu, condx), by = __ballot_sync(0xffffffffu, condy);
   const bool actx = octx && ((bx >> (lane & ~7)) & 0xffu) != 0;
   const bool acty = octy && ((by >> (lane & ~7)) & 0xffu) != 0;
-  if (!actx && !acty) return;
+  if (!DIV && !actx && !acty) return;
 
   const float fC = (m & AMB_C) ? 1.0f : 0.0f, fE = (m & AMB_E) ? 1.0f : 0.0f, fN = (m & AMB_N) ? 1.0f : 0.0f;
   const float fx = (float)xi, fy = (float)y;
+  float nvx = 0.0f, nvy = 0.0f; // DIV: the faces (xi, y) of the advected field
 
   if (actx) { // simulation.cpp:246-297
     const float posx = __fadd_rn(fx, 0.5f), posy = fy;
@@ -572,7 +580,8 @@ __global__ void __launch_bounds__(256, OCC) k_advect_xy(Grid vx, Grid vy, Grid v
     const float vy2 = bicubic_pk<SLAB>(vy.d, pitch, lim.z, lim.w, vy.h, midx, __fsub_rn(midy, 0.5f), tr, tr.span_y, tr.y_lo, tr.y_hi);
     const float endx = __fmaf_rn(-vx2, full, posx), endy = __fmaf_rn(-vy2, full, posy);
     const float xvel = bicubic_pk<SLAB>(vx.d, pitch, lim.x, lim.y, vx.h, __fsub_rn(endx, 0.5f), endy, tr, tr.span_x, tr.x_lo, tr.x_hi);
-    vxb.d[o] = __fmul_rn(__fmul_rn(xvel, fC), fE);
+    nvx = __fmul_rn(__fmul_rn(xvel, fC), fE);
+    vxb.d[o] = nvx;
   }
   if (acty) { // simulation.cpp:300-347
     const float posy = __fadd_rn(fy, 0.5f), posx = fx;
@@ -583,8 +592,67 @@ __global__ void __launch_bounds__(256, OCC) k_advect_xy(Grid vx, Grid vy, Grid v
     const float vy2 = bicubic_pk<SLAB>(vy.d, pitch, lim.z, lim.w, vy.h, midx, __fsub_rn(midy, 0.5f), tr, tr.span_y, tr.y_lo, tr.y_hi);
     const float endx = __fmaf_rn(-vx2, full, posx), endy = __fmaf_rn(-vy2, full, posy);
     const float yvel = bicubic_pk<SLAB>(vy.d, pitch, lim.z, lim.w, vy.h, endx, __fsub_rn(endy, 0.5f), tr, tr.span_y, tr.y_lo, tr.y_hi);
-    vyb.d[o] = __fmul_rn(__fmul_rn(yvel, fC), fN);
+    nvy = __fmul_rn(__fmul_rn(yvel, fC), fN);
+    vyb.d[o] = nvy;
   }
+  if (DIV) {
+    __shared__ float south[8][32];
+    const bool in = row_ok && xi <= W - 2;
+    if (in && !actx) nvx = vxb.d[o];
+    if (in && !acty) nvy = vyb.d[o];
+    const float west = __shfl_up_sync(0xffffffffu, nvx, 1);
+    south[threadIdx.y][lane] = nvy;
+    __syncthreads();
+    if (in && lane > 0 && threadIdx.y > 0 && xi <= W - 3 && y <= H - 3)
+      fdiv[o] = __fmul_rn(nih, __fsub_rn(__fadd_rn(__fsub_rn(nvx, west), nvy), south[threadIdx.y - 1][lane]));
+  }
+}
+
+// The cells k_advect_xy<DIV> leaves out: x = 1 (mod 32) (a CTA's first column), rows y_lo + 8k (its
+// first row), and x = W-2, y = H-2, whose east / north faces setVBCs writes.  One launch, 256-thread
+// blocks: the first n_row_blocks take 256-cell segments of the edge rows, the rest 32 list columns
+// (1, 33, 65, ..., and W-2) x 8 rows each; cells on both lists are written twice with the same value.
+__global__ void k_divergence_edges(Grid vx, Grid vy, Grid f, float nih, int y_lo, int y_hi, int n_row_blocks,
+                                   int segs, int n_edge_rows, int col_blocks) {
+  const int W = f.w, H = f.h;
+  auto cell = [&](int x, int y) {
+    const float d = __fsub_rn(__fadd_rn(__fsub_rn(vx.at(x, y), vx.at(x - 1, y)), vy.at(x, y)), vy.at(x, y - 1));
+    f.at(x, y) = __fmul_rn(nih, d);
+  };
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  if ((int)blockIdx.x < n_row_blocks) {
+    const int er = blockIdx.x / segs, seg = blockIdx.x - er * segs;
+    const int y = er < n_edge_rows - 1 ? y_lo + 8 * er : H - 2; // the last entry of the list is row H-2
+    const int x = 1 + seg * 256 + tid;
+    if (y >= y_lo && y < y_hi && x <= W - 2) cell(x, y);
+    return;
+  }
+  const int b = blockIdx.x - n_row_blocks;
+  const int rb = b / col_blocks, cb = b - rb * col_blocks;
+  const int y = y_lo + 8 * rb + threadIdx.y;
+  const int c = cb * 32 + threadIdx.x;
+  const int ncol = (W - 2 + 31) / 32; // x = 1 + 32 c <= W-2
+  if (y >= y_hi) return;
+  if (c < ncol) cell(1 + 32 * c, y);
+  else if (c == ncol) cell(W - 2, y);
+}
+
+// y_lo / y_hi: the row range of the advect launch that computed the rest (after its clamps)
+void launch_divergence_edges(const Grid &vx, const Grid &vy, const Grid &f, float ih, int y_lo, int y_hi,
+                             cudaStream_t stream, LaunchCounter *lc) {
+  y_lo = std::max(y_lo, 1);
+  y_hi = std::min(y_hi, f.h - 1);
+  if (y_hi <= y_lo) return;
+  const int W = f.w;
+  const int segs = ceil_div(W - 2, 256);
+  const int n_edge_rows = ceil_div(y_hi - y_lo, 8) + 1; // rows y_lo + 8k, then H-2 (out of range on a slab that does not hold it)
+  const int ncol = (W - 2 + 31) / 32 + 1;
+  const int col_blocks = ceil_div(ncol, 32);
+  const int n_row_blocks = segs * n_edge_rows;
+  const int n_col_blocks = col_blocks * ceil_div(y_hi - y_lo, 8);
+  UBGL_LAUNCH(lc, K_DIVERGENCE, 0, stream,
+              (k_divergence_edges<<<n_row_blocks + n_col_blocks, dim3(32, 8), 0, stream>>>(vx, vy, f, -ih, y_lo, y_hi, n_row_blocks, segs,
+                                                                                          n_edge_rows, col_blocks)));
 }
 
 // project part 1 (simulation.cpp:166-171): f = -(1/h) div v on the interior
@@ -845,16 +913,18 @@ static int advect_variant() {
   return variant;
 }
 
-// Returns true when the launch also zeroed the accumulator interiors of rows [y_lo, y_hi)
-// (k_advect_xy, needs the stencil mask, i.e. binary flags); the caller then skips that part of
-// the divergence pass.
-bool launch_advect(const Grid &vx, const Grid &vy, const Grid &vxbk, const Grid &vybk,
-                   const Grid &flag, float half, float full, int y_lo, int y_hi, const AdvectPeers *peers,
-                   cudaStream_t stream, LaunchCounter *lc, const uint8_t *mask, float *ax, float *ay) {
+// Returns ADV_ZEROED when the launch also zeroed the accumulator interiors of rows [y_lo, y_hi)
+// (k_advect_xy, needs the stencil mask, i.e. binary flags), ADV_DIV when it also wrote the
+// divergence f = -ih div v of its cells except the edge set (fdiv != null; the caller then runs
+// launch_divergence_edges after setVBCs instead of the divergence pass).
+int launch_advect(const Grid &vx, const Grid &vy, const Grid &vxbk, const Grid &vybk,
+                  const Grid &flag, float half, float full, int y_lo, int y_hi, const AdvectPeers *peers,
+                  cudaStream_t stream, LaunchCounter *lc, const uint8_t *mask, float *ax, float *ay, float *fdiv,
+                  float ih) {
   const int W = flag.w, H = flag.h;
   y_lo = std::max(y_lo, 1);
   y_hi = std::min(y_hi, H - 1);
-  if (y_hi <= y_lo) return false;
+  if (y_hi <= y_lo) return 0;
   dim3 b(32, 8);
   dim3 g(ceil_div(W - 2, 32), ceil_div(y_hi - y_lo, 8));
   const int variant = advect_variant();
@@ -888,7 +958,28 @@ bool launch_advect(const Grid &vx, const Grid &vy, const Grid &vxbk, const Grid 
       tr.lo1 = 1;
       tr.span_x = (unsigned)(vx.h - 4); tr.span_y = (unsigned)(vy.h - 4);
     }
-#define UBGL_ADV_XY(S_, O_) UBGL_LAUNCH(lc, K_ADVECT, LVL, stream, (k_advect_xy<S_, O_><<<g, b, 0, stream>>>(vx, vy, vxbk, vybk, mask, ax, ay, half, full, lim, y_lo, y_hi, tr)))
+    // UBGL_ADVECT_DIV=1: the divergence in the advect epilogue (k_advect_xy<DIV> + k_divergence_edges)
+    // instead of its own pass.  Bit-identical (tests/test_gpu_advect_variants.py) and OFF by default:
+    // measured at 8192^2 it LOSES 0.12 ms per step -- the advect kernel goes from 1.230 to 1.319 ms (every
+    // thread stays to the end, a block barrier, the retained faces re-read) and the edge pass (the
+    // 1/32 of columns on CTA edges are sector-sized accesses) takes 0.153 ms against 0.121 ms for the
+    // whole k_divergence4, which runs at 85 % of the HBM peak.
+    static const bool div_on = [] {
+      const char *e = getenv("UBGL_ADVECT_DIV");
+      return e && e[0] == '1';
+    }();
+    const bool div = div_on && fdiv != nullptr && (occ == 6 || (peers && occ != 4));
+    const float nih = -ih;
+#define UBGL_ADV_XY(S_, O_) UBGL_LAUNCH(lc, K_ADVECT, LVL, stream, (k_advect_xy<S_, O_, false><<<g, b, 0, stream>>>(vx, vy, vxbk, vybk, mask, ax, ay, half, full, lim, y_lo, y_hi, tr, nullptr, 0.0f)))
+#define UBGL_ADV_XY_DIV(S_) UBGL_LAUNCH(lc, K_ADVECT, LVL, stream, (k_advect_xy<S_, 6, true><<<g, b, 0, stream>>>(vx, vy, vxbk, vybk, mask, ax, ay, half, full, lim, y_lo, y_hi, tr, fdiv, nih)))
+    if (div) {
+      if (peers || force_slab) {
+        UBGL_ADV_XY_DIV(true);
+      } else {
+        UBGL_ADV_XY_DIV(false);
+      }
+      return (ax != nullptr ? ADV_ZEROED : 0) | ADV_DIV;
+    }
     if (peers || force_slab) {
       if (occ == 4) {
         UBGL_ADV_XY(true, 4);
@@ -909,7 +1000,8 @@ bool launch_advect(const Grid &vx, const Grid &vy, const Grid &vxbk, const Grid 
       UBGL_ADV_XY(false, 4);
     }
 #undef UBGL_ADV_XY
-    return ax != nullptr;
+#undef UBGL_ADV_XY_DIV
+    return ax != nullptr ? ADV_ZEROED : 0;
   }
   if (variant == 2) {
     dim3 g2(g.x, ceil_div(y_hi - y_lo, 16));
@@ -920,32 +1012,32 @@ bool launch_advect(const Grid &vx, const Grid &vy, const Grid &vxbk, const Grid 
       UBGL_LAUNCH(lc, K_ADVECT, LVL, stream, (k_advect_pair<false, 0><<<g2, b, 0, stream>>>(vx, vy, vxbk, flag, half, full, y_lo, y_hi, tr)));
       UBGL_LAUNCH(lc, K_ADVECT, LVL, stream, (k_advect_pair<false, 1><<<g2, b, 0, stream>>>(vx, vy, vybk, flag, half, full, y_lo, y_hi, tr)));
     }
-    return false;
+    return 0;
   }
   if (!peers) {
     UBGL_LAUNCH(lc, K_ADVECT, LVL, stream, k_advect_vx<false><<<g, b, 0, stream>>>(vx, vy, vxbk, flag, half, full, y_lo, y_hi, tr));
     UBGL_LAUNCH(lc, K_ADVECT, LVL, stream, k_advect_vy<false><<<g, b, 0, stream>>>(vx, vy, vybk, flag, half, full, y_lo, y_hi, tr));
-    return false;
+    return 0;
   }
   UBGL_LAUNCH(lc, K_ADVECT, LVL, stream, k_advect_vx<true><<<g, b, 0, stream>>>(vx, vy, vxbk, flag, half, full, y_lo, y_hi, tr));
   UBGL_LAUNCH(lc, K_ADVECT, LVL, stream, k_advect_vy<true><<<g, b, 0, stream>>>(vx, vy, vybk, flag, half, full, y_lo, y_hi, tr));
-  return false;
+  return 0;
 }
 
 void DeviceSim::advect() { advect_impl(false); }
 
 // fused_step: the stencil mask is valid (binary flags) and the accumulators are consumed, so the
 // merged kernel may run and clear them; returns whether it did
-bool DeviceSim::advect_impl(bool fused_step) {
+int DeviceSim::advect_impl(bool fused_step) {
   float ih = 1.0f / h;
   float half = 0.5f * dt * ih, full = dt * ih; // simulation.cpp:276,286
-  const bool zeroed =
+  const int did =
       launch_advect(vxb[ixf], vyb[iyf], vxb[ixb], vyb[iyb], flag, half, full, 1, H - 1, nullptr, stream, &lc,
                     fused_step ? mg->mask0_ptr() : nullptr, fused_step ? vx_accum.d : nullptr,
-                    fused_step ? vy_accum.d : nullptr);
+                    fused_step ? vy_accum.d : nullptr, fused_step ? f.d : nullptr, ih);
   std::swap(ixf, ixb);
   std::swap(iyf, iyb);
-  return zeroed;
+  return did;
 }
 
 // sum over the interior of (f * flag)^2: the residual norm of p = 0, the
@@ -1192,11 +1284,14 @@ void DeviceSim::step(float dt_) {
       fused_prestep();
       fused_borders(false, false);
       mark();
-      const bool acc_zeroed = advect_impl(true);
+      const int adv = advect_impl(true);
       mark();
       fused_borders(false, false);
       mark();
-      fused_divergence(!acc_zeroed);
+      if (adv & ADV_DIV) // the advect epilogue wrote f except on CTA edges and next to the BC faces
+        launch_divergence_edges(vxb[ixf], vyb[iyf], f, 1.0f / h, 1, H - 1, stream, &lc);
+      else
+        fused_divergence(!(adv & ADV_ZEROED));
     });
     project_sinks();
     run_part(graphs_b, false, graphable, [&]() {

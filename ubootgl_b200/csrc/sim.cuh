@@ -65,10 +65,14 @@ struct AdvectPeers {
 };
 // mask != nullptr (binary flags): the merged packed-fp32 kernel k_advect_xy may be used; with
 // ax / ay it also zeroes the accumulator interiors of those rows and the call returns true.
-bool launch_advect(const Grid &vx, const Grid &vy, const Grid &vxb, const Grid &vyb, const Grid &flag,
-                   float half, float full, int y_lo, int y_hi, const AdvectPeers *peers,
-                   cudaStream_t stream, LaunchCounter *lc, const uint8_t *mask = nullptr,
-                   float *ax = nullptr, float *ay = nullptr);
+enum { ADV_ZEROED = 1, ADV_DIV = 2 };
+int launch_advect(const Grid &vx, const Grid &vy, const Grid &vxb, const Grid &vyb, const Grid &flag,
+                  float half, float full, int y_lo, int y_hi, const AdvectPeers *peers,
+                  cudaStream_t stream, LaunchCounter *lc, const uint8_t *mask = nullptr,
+                  float *ax = nullptr, float *ay = nullptr, float *fdiv = nullptr, float ih = 0.0f);
+// the cells the advect epilogue leaves out (CTA edges, the ring next to the BC faces), after setVBCs
+void launch_divergence_edges(const Grid &vx, const Grid &vy, const Grid &f, float ih, int y_lo, int y_hi,
+                             cudaStream_t stream, LaunchCounter *lc);
 // sinks (sim.cu): 3x3 stamps restricted to rows [y_lo, y_hi)
 void launch_stamp_sinks(const Grid &f, const float *d_sinks, int n, int y_lo, int y_hi,
                         cudaStream_t stream, LaunchCounter *lc);
@@ -113,7 +117,7 @@ public:
   void apply_accum();
   void diffuse();
   void advect();
-  bool advect_impl(bool fused_step);
+  int advect_impl(bool fused_step); // ADV_* flags of launch_advect
   void set_vbcs();
   void project();
   void save_current();

@@ -693,7 +693,7 @@ void SlabSim::step(float dt_) {
   exchange({xf(vxb[ixf], 0), xf(vyb[iyf], 0)}, plan.ghost);
 
   // advect (reads the fronts incl. ghost rows, writes own rows of the backs)
-  bool acc_zeroed = false;
+  int adv = 0;
   {
     AdvectPeers ap{};
     ap.st_lo = R.st_lo; ap.st_hi = R.st_hi; ap.peer_lo = R.st_lo; ap.peer_hi = R.st_hi;
@@ -709,9 +709,8 @@ void SlabSim::step(float dt_) {
       ap.vx_hi = peer_ptr(plan.rank + 1, vxb[ixf].d, 0, rb);
       ap.vy_hi = peer_ptr(plan.rank + 1, vyb[iyf].d, 0, rb);
     }
-    acc_zeroed = launch_advect(vxb[ixf], vyb[iyf], vxb[ixb], vyb[iyb], flag, 0.5f * dt * ih, dt * ih, R.own_lo,
-                               R.own_hi, plan.nranks > 1 ? &ap : nullptr, stream, &lc, mask0, vx_accum.d,
-                               vy_accum.d);
+    adv = launch_advect(vxb[ixf], vyb[iyf], vxb[ixb], vyb[iyb], flag, 0.5f * dt * ih, dt * ih, R.own_lo, R.own_hi,
+                        plan.nranks > 1 ? &ap : nullptr, stream, &lc, mask0, vx_accum.d, vy_accum.d, f.d, ih);
   }
   std::swap(ixf, ixb);
   std::swap(iyf, iyb);
@@ -723,8 +722,12 @@ void SlabSim::step(float dt_) {
     // the divergence pass also zeroes the accumulator interiors of the own rows
     // (simulation.cpp:384,392); the few ghost rows are cleared by memsets
     const Grid none{};
-    launch_divergence4(vxb[ixf], vyb[iyf], f, acc_zeroed ? none : vx_accum, acc_zeroed ? none : vy_accum, ih,
-                       R.own_lo, R.own_hi, stream, &lc);
+    const bool acc_zeroed = adv & ADV_ZEROED;
+    if (adv & ADV_DIV) // the advect epilogue wrote f except on CTA edges and next to the BC faces
+      launch_divergence_edges(vxb[ixf], vyb[iyf], f, ih, R.own_lo, R.own_hi, stream, &lc);
+    else
+      launch_divergence4(vxb[ixf], vyb[iyf], f, acc_zeroed ? none : vx_accum, acc_zeroed ? none : vy_accum, ih,
+                         R.own_lo, R.own_hi, stream, &lc);
     auto clear_rows = [&](int y0, int y1) {
       y0 = std::max(1, y0);
       const int yx = std::min(H - 1, y1), yy = std::min(H - 2, y1);
