@@ -561,6 +561,39 @@ def run_explosion(args, name):
     d2h = pcie_d2h_bytes(outs) + rec.nbytes
     h2d = CRATERS * 12 + len(sim.sinks()) * 12
 
+    # What bounds the item pass (the largest single item of this frame).  The reference tests an item against every
+    # position of its x-bin (advect_floating_items.cpp:167-181: N^2 / 100 pair tests); the kernel walks the y-cells
+    # y-1, y, y+1 of the x-bin only (next.cu).  Pair tests per frame are counted here on the host from the downloaded
+    # records with the kernel's own binning; the ceiling is the SM issue rate at ~12 instructions per test.
+    def items_roofline():
+        pos, size = rec["pos"].astype(np.float64), rec["size"].astype(np.float64)
+        r2max = float((size[:, 0] * size[:, 1] * 0.4).max())
+        yrange = PWIDTH * H / W
+        NY = 2048
+        cy = max(np.sqrt(r2max) * 1.0001, yrange / NY)
+        xb = (pos[:, 0] * 100.0).astype(np.int64) % 100
+        yc = np.clip(np.floor(pos[:, 1] / cy), 0, NY - 1).astype(np.int64)
+        occ = np.zeros((100, NY + 2), np.int64)
+        np.add.at(occ, (xb, yc + 1), 1)
+        near = occ[:, :-2] + occ[:, 1:-1] + occ[:, 2:]        # entries of cells y-1, y, y+1
+        pairs = int(near[xb, yc].sum())
+        ms = per.get("items", float("nan"))
+        props = torch.cuda.get_device_properties(dev)
+        issue = props.multi_processor_count * 4 * 32 * 1.965e9   # thread-instructions per second at 1965 MHz
+        ceil_pairs = issue / 12.0
+        rate = pairs / (ms * 1e-3)
+        return {"bound": "latency (dependent walk of three sorted y-cells per item, a handful of contacts each); neither HBM "
+                         "nor issue bound", "kernel": "items (r2max, keys, radix sort, offsets, k_items_advect)",
+                "ms_per_frame": ms, "pair_tests_per_frame": pairs, "pair_tests_reference_scheme": int((occ.sum(axis=1) ** 2).sum()),
+                "achieved": rate / 1e9, "peak": ceil_pairs / 1e9, "unit": "G pair tests/s", "frac": rate / ceil_pairs,
+                "peak_model": "SM issue rate (SMs x 4 schedulers x 32 lanes x 1.965 GHz) / 12 instructions per pair test",
+                "record_bytes_gbs": N_PARTICLES * 2 * capi.ITEM_DTYPE.itemsize / (ms * 1e-3) / 1e9,
+                "record_bytes_frac_of_hbm": N_PARTICLES * 2 * capi.ITEM_DTYPE.itemsize / (ms * 1e-3) / 1e9 / peak}
+    try:
+        roof_items = items_roofline()
+    except Exception as e:  # never lose the bench line over the diagnostic
+        roof_items = {"error": repr(e)}
+
     cpu = None
     if not args.no_cpu_baseline:  # in a child process, like cpu_reference_isolated
         try:
@@ -589,6 +622,7 @@ def run_explosion(args, name):
                       "fluid_step_ms": step_only,
                       "fluid_step_mlups": N / (step_only * 1e-3) / 1e6},
         "roofline": roof,
+        "roofline_items": roof_items,
         "roofline_step": {"bound": "hbm", "achieved": N * bpc / (step_only * 1e-3) / 1e9, "peak": peak,
                           "unit": "GB/s", "frac": N * bpc / (step_only * 1e-3) / 1e9 / peak, "bytes_per_cell": bpc,
                           "model": "fluid-step kernels only, 152 + 186.7*k B/cell, k=2", "peak_source": peak_src},
@@ -669,6 +703,19 @@ KERNEL_BYTES = {
 }
 
 
+# Kinds whose launch count per step depends on the schedule (advect: one merged launch for both
+# components or one per component; prestep: per component a register-run launch for the interior plus
+# a frame launch, which together cover the grid once): the figure is PER STEP, split over the launches.
+KERNEL_BYTES_PER_STEP = {"advect": 2 * 10.0, "prestep_fused": 32.0 + 48.0}
+
+
+def kernel_bytes_per_cell(kind, launches_per_step):
+    """Algorithmic B per cell of its level for ONE launch of this kind."""
+    if kind in KERNEL_BYTES_PER_STEP:
+        return KERNEL_BYTES_PER_STEP[kind] / max(launches_per_step, 1)
+    return KERNEL_BYTES.get(kind)
+
+
 def ncu_traffic(workload, kind, level):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel from the
     committed `ncu --set full` capture of the same workload (profiles/), else None."""
@@ -692,7 +739,7 @@ def dominant_roofline(kern, W, H, peak, peak_src, prof_ms_step, cells_scale=1.0,
         return None
     ms, n, k, l = kern[0]
     cells = (W >> l) * (H >> l) * cells_scale  # slab runs: one rank's rows
-    bpc = KERNEL_BYTES.get(k)
+    bpc = kernel_bytes_per_cell(k, n)
     if bpc is None:
         return {"bound": "hbm", "kernel": k, "level": l, "achieved": None, "peak": peak, "unit": "GB/s",
                 "frac": None, "traffic": None}
@@ -720,7 +767,7 @@ def roofline_by_kernel(kern, W, H, peak, prof_ms_step, workload=None):
         a = agg.setdefault(k, {"ms": 0.0, "launches": 0, "alg": 0.0, "traffic": 0.0, "have_traffic": True})
         a["ms"] += ms
         a["launches"] += n
-        bpc = KERNEL_BYTES.get(k)
+        bpc = kernel_bytes_per_cell(k, n)
         if bpc is not None:
             a["alg"] += (W >> l) * (H >> l) * bpc * n
         t = ncu_traffic(workload, k, l)

@@ -506,6 +506,10 @@ __global__ void __launch_bounds__(16 * (RUN_LH / R), 2) k_mg_run(TileArgs a) {
     rcpt[threadIdx.x] = rcp_count(threadIdx.x);
     prt[threadIdx.x] = prolong_rcp(threadIdx.x);
   }
+  // Programmatic dependent launch (UBGL_MG_PDL=1, launch_run): this grid may have been scheduled
+  // while the previous kernel of the stream was still draining; everything above touches no global
+  // memory.  Without the launch attribute the instruction is a no-op.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   // MODE_POST: the coarse error and coarse stencil mask under this thread's cells -- coarse
   // rows ycb .. ycb+2, columns xcb .. xcb+4 -- for prolongation + correction
@@ -879,6 +883,10 @@ __global__ void __launch_bounds__(16 * (RUN_LH / R), 2) k_mg_run(TileArgs a) {
     }
   }
 
+  // the next kernel of the stream may be scheduled from here on (it waits for this grid's
+  // completion before its first global access)
+  asm volatile("griddepcontrol.launch_dependents;");
+
   // ---- write the thread's own tile cells back (p ping-pong buffer), 128-bit stores ----
   if (tg >= HX / 8 && tg < (HX + TX) / 8) {
 #pragma unroll
@@ -1155,6 +1163,32 @@ static size_t g_tail_max_cells = env_tail_cells();
 void set_tile_variant(int v) { g_tile_variant = (v == 1) ? 1 : 2; }
 int tile_variant() { return g_tile_variant; }
 
+// <<<>>> or, with UBGL_MG_PDL=1, cudaLaunchKernelEx with programmatic stream serialization: the
+// grid is scheduled as soon as every CTA of the previous kernel has passed its
+// griddepcontrol.launch_dependents (or exited) and parks at griddepcontrol.wait
+template <typename K>
+static void launch_maybe_pdl(K kernel, dim3 grid, int threads, size_t smem, cudaStream_t stream, const TileArgs &b) {
+  static const bool pdl = [] {
+    const char *e = getenv("UBGL_MG_PDL");
+    return e && e[0] == '1';
+  }();
+  if (!pdl) {
+    kernel<<<grid, threads, smem, stream>>>(b);
+    return;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, b);
+}
+
 template <int MODE>
 static void launch_run(const TileArgs &a, cudaStream_t stream, LaunchCounter *lc, int kind, int level) {
   using G = RunGeom<MODE>;
@@ -1178,11 +1212,11 @@ static void launch_run(const TileArgs &a, cudaStream_t stream, LaunchCounter *lc
   if (rows_per_thread == 2) {
     static std::atomic<unsigned long long> attr_done2{0};
     ensure_dyn_smem(k_mg_run<MODE, 2>, G::smem, attr_done2);
-    UBGL_LAUNCH(lc, kind, level, stream, (k_mg_run<MODE, 2><<<grid, 16 * (RUN_LH / 2), G::smem, stream>>>(b)));
+    UBGL_LAUNCH(lc, kind, level, stream, (launch_maybe_pdl(k_mg_run<MODE, 2>, grid, 16 * (RUN_LH / 2), G::smem, stream, b)));
   } else {
     static std::atomic<unsigned long long> attr_done4{0};
     ensure_dyn_smem(k_mg_run<MODE, 4>, G::smem, attr_done4);
-    UBGL_LAUNCH(lc, kind, level, stream, (k_mg_run<MODE, 4><<<grid, 16 * (RUN_LH / 4), G::smem, stream>>>(b)));
+    UBGL_LAUNCH(lc, kind, level, stream, (launch_maybe_pdl(k_mg_run<MODE, 4>, grid, 16 * (RUN_LH / 4), G::smem, stream, b)));
   }
 }
 
