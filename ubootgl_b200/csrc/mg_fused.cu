@@ -506,10 +506,9 @@ __global__ void __launch_bounds__(16 * (RUN_LH / R), 2) k_mg_run(TileArgs a) {
     rcpt[threadIdx.x] = rcp_count(threadIdx.x);
     prt[threadIdx.x] = prolong_rcp(threadIdx.x);
   }
-  // Programmatic dependent launch (UBGL_MG_PDL=1, launch_run): this grid may have been scheduled
-  // while the previous kernel of the stream was still draining; everything above touches no global
-  // memory.  Without the launch attribute the instruction is a no-op.
-  asm volatile("griddepcontrol.wait;" ::: "memory");
+  // programmatic dependent launch (common.cuh): this grid may have been scheduled while the previous
+  // kernel of the stream was still draining; everything above touches no global memory
+  ubgl_pdl_prologue();
 
   // MODE_POST: the coarse error and coarse stencil mask under this thread's cells -- coarse
   // rows ycb .. ycb+2, columns xcb .. xcb+4 -- for prolongation + correction
@@ -883,10 +882,6 @@ __global__ void __launch_bounds__(16 * (RUN_LH / R), 2) k_mg_run(TileArgs a) {
     }
   }
 
-  // the next kernel of the stream may be scheduled from here on (it waits for this grid's
-  // completion before its first global access)
-  asm volatile("griddepcontrol.launch_dependents;");
-
   // ---- write the thread's own tile cells back (p ping-pong buffer), 128-bit stores ----
   if (tg >= HX / 8 && tg < (HX + TX) / 8) {
 #pragma unroll
@@ -951,6 +946,7 @@ struct TailArgs {
 };
 
 __global__ void __launch_bounds__(TAIL_NT, 1) k_mg_tail(TailArgs a) {
+  ubgl_pdl_prologue();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float *sPa = reinterpret_cast<float *>(smem_raw);
   float *sFa = sPa + a.cells;
@@ -1163,32 +1159,6 @@ static size_t g_tail_max_cells = env_tail_cells();
 void set_tile_variant(int v) { g_tile_variant = (v == 1) ? 1 : 2; }
 int tile_variant() { return g_tile_variant; }
 
-// <<<>>> or, with UBGL_MG_PDL=1, cudaLaunchKernelEx with programmatic stream serialization: the
-// grid is scheduled as soon as every CTA of the previous kernel has passed its
-// griddepcontrol.launch_dependents (or exited) and parks at griddepcontrol.wait
-template <typename K>
-static void launch_maybe_pdl(K kernel, dim3 grid, int threads, size_t smem, cudaStream_t stream, const TileArgs &b) {
-  static const bool pdl = [] {
-    const char *e = getenv("UBGL_MG_PDL");
-    return e && e[0] == '1';
-  }();
-  if (!pdl) {
-    kernel<<<grid, threads, smem, stream>>>(b);
-    return;
-  }
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = grid;
-  cfg.blockDim = dim3(threads);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = stream;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = 1;
-  cudaLaunchKernelEx(&cfg, kernel, b);
-}
-
 template <int MODE>
 static void launch_run(const TileArgs &a, cudaStream_t stream, LaunchCounter *lc, int kind, int level) {
   using G = RunGeom<MODE>;
@@ -1212,11 +1182,11 @@ static void launch_run(const TileArgs &a, cudaStream_t stream, LaunchCounter *lc
   if (rows_per_thread == 2) {
     static std::atomic<unsigned long long> attr_done2{0};
     ensure_dyn_smem(k_mg_run<MODE, 2>, G::smem, attr_done2);
-    UBGL_LAUNCH(lc, kind, level, stream, (launch_maybe_pdl(k_mg_run<MODE, 2>, grid, 16 * (RUN_LH / 2), G::smem, stream, b)));
+    UBGL_LAUNCH(lc, kind, level, stream, (launch_k(k_mg_run<MODE, 2>, grid, 16 * (RUN_LH / 2), G::smem, stream, b)));
   } else {
     static std::atomic<unsigned long long> attr_done4{0};
     ensure_dyn_smem(k_mg_run<MODE, 4>, G::smem, attr_done4);
-    UBGL_LAUNCH(lc, kind, level, stream, (launch_maybe_pdl(k_mg_run<MODE, 4>, grid, 16 * (RUN_LH / 4), G::smem, stream, b)));
+    UBGL_LAUNCH(lc, kind, level, stream, (launch_k(k_mg_run<MODE, 4>, grid, 16 * (RUN_LH / 4), G::smem, stream, b)));
   }
 }
 
@@ -1308,7 +1278,7 @@ void launch_mg_tail(const std::vector<TailLevel> &lv, int t, const float *hh, co
   const size_t smem = (size_t)cells * 9 + 16;
   static std::atomic<unsigned long long> attr_done{0};
   ensure_dyn_smem(k_mg_tail, TAIL_SMEM_MAX, attr_done);
-  UBGL_LAUNCH(lc, K_MG_COARSE, t, stream, k_mg_tail<<<1, TAIL_NT, smem, stream>>>(a));
+  UBGL_LAUNCH(lc, K_MG_COARSE, t, stream, launch_k(k_mg_tail, 1, TAIL_NT, smem, stream, a));
 }
 
 void launch_make_mask(const Grid &flag, uint8_t *mask, int *d_nonbinary, cudaStream_t stream,

@@ -614,6 +614,7 @@ __global__ void __launch_bounds__(256, OCC) k_advect_xy(Grid vx, Grid vy, Grid v
 // (1, 33, 65, ..., and W-2) x 8 rows each; cells on both lists are written twice with the same value.
 __global__ void k_divergence_edges(Grid vx, Grid vy, Grid f, float nih, int y_lo, int y_hi, int n_row_blocks,
                                    int segs, int n_edge_rows, int col_blocks) {
+  ubgl_pdl_prologue();
   const int W = f.w, H = f.h;
   auto cell = [&](int x, int y) {
     const float d = __fsub_rn(__fadd_rn(__fsub_rn(vx.at(x, y), vx.at(x - 1, y)), vy.at(x, y)), vy.at(x, y - 1));
@@ -651,7 +652,7 @@ void launch_divergence_edges(const Grid &vx, const Grid &vy, const Grid &f, floa
   const int n_row_blocks = segs * n_edge_rows;
   const int n_col_blocks = col_blocks * ceil_div(y_hi - y_lo, 8);
   UBGL_LAUNCH(lc, K_DIVERGENCE, 0, stream,
-              (k_divergence_edges<<<n_row_blocks + n_col_blocks, dim3(32, 8), 0, stream>>>(vx, vy, f, -ih, y_lo, y_hi, n_row_blocks, segs,
+              (launch_k(k_divergence_edges, n_row_blocks + n_col_blocks, dim3(32, 8), 0, stream, vx, vy, f, -ih, y_lo, y_hi, n_row_blocks, segs,
                                                                                           n_edge_rows, col_blocks)));
 }
 
@@ -667,6 +668,7 @@ __global__ void k_divergence(Grid vx, Grid vy, Grid f, float ih) {
 
 // sinks (simulation.cpp:173-182): 3x3 stamps, in list order (later sinks win)
 __global__ void k_stamp_sinks(Grid f, const float *sinks, int n, int y_lo, int y_hi) {
+  ubgl_pdl_prologue();
   int dx = (int)(threadIdx.x % 3) - 1, dy = (int)(threadIdx.x / 3) - 1;
   for (int k = 0; k < n; k++) {
     if (threadIdx.x < 9) {
@@ -679,7 +681,7 @@ __global__ void k_stamp_sinks(Grid f, const float *sinks, int n, int y_lo, int y
 
 void launch_stamp_sinks(const Grid &f, const float *d_sinks, int n, int y_lo, int y_hi,
                         cudaStream_t stream, LaunchCounter *lc) {
-  UBGL_LAUNCH(lc, K_SINKS, LVL, stream, k_stamp_sinks<<<1, 32, 0, stream>>>(f, d_sinks, n, y_lo, y_hi));
+  UBGL_LAUNCH(lc, K_SINKS, LVL, stream, launch_k(k_stamp_sinks, 1, 32, 0, stream, f, d_sinks, n, y_lo, y_hi));
 }
 
 // setPBC (simulation.cpp:36-45): columns for all y, then rows for all x.

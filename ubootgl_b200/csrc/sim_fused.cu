@@ -443,6 +443,7 @@ __device__ __forceinline__ void vbc_row_cell(const BcGrid &q, const BorderArgs &
 
 // thread t < ncol: column cells of row y_lo + t; else row cells of column t - ncol
 __global__ void k_vbc_all(BorderArgs g, int ncol) {
+  ubgl_pdl_prologue();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const BcGrid qx{g.xf, g.xb, g.xc, 0}, qy{g.yf, g.yb, g.yc, 1};
   if (t < ncol) {
@@ -627,17 +628,19 @@ void launch_prestep(int comp, const PrestepArgs &g0, cudaStream_t stream, Launch
 void launch_borders(const BorderArgs &g, cudaStream_t stream, LaunchCounter *lc) {
   const int ncol = std::max(0, g.y_hi - g.y_lo), nrow = (g.do_s || g.do_n) ? g.yf.w : 0;
   if (ncol + nrow > 0)
-    UBGL_LAUNCH(lc, K_VBC, 0, stream, k_vbc_all<<<ceil_div(ncol + nrow, 128), 128, 0, stream>>>(g, ncol));
+    UBGL_LAUNCH(lc, K_VBC, 0, stream, launch_k(k_vbc_all, ceil_div(ncol + nrow, 128), 128, 0, stream, g, ncol));
 }
 
 // setPBC alone (simulation.cpp:36-45) for the slab driver
 __global__ void k_pbc_cols(Grid p, int bcW, int bcE, int y_lo, int y_hi) {
+  ubgl_pdl_prologue();
   const int y = y_lo + blockIdx.x * blockDim.x + threadIdx.x;
   if (y >= y_hi || y >= p.h) return;
   p.at(0, y) = single_pbc(bcW, p.at(1, y));
   p.at(p.w - 1, y) = single_pbc(bcE, p.at(p.w - 2, y));
 }
 __global__ void k_pbc_rows(Grid p, int bcS, int bcN, int do_s, int do_n) {
+  ubgl_pdl_prologue();
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   if (x >= p.w) return;
   if (do_s) p.at(x, 0) = single_pbc(bcS, p.at(x, 1));
@@ -646,9 +649,9 @@ __global__ void k_pbc_rows(Grid p, int bcS, int bcN, int do_s, int do_n) {
 void launch_pbc(const Grid &p, int bcW, int bcE, int bcN, int bcS, int y_lo, int y_hi, bool do_s,
                 bool do_n, cudaStream_t stream, LaunchCounter *lc) {
   if (y_hi > y_lo)
-    UBGL_LAUNCH(lc, K_PBC, 0, stream, k_pbc_cols<<<ceil_div(y_hi - y_lo, 128), 128, 0, stream>>>(p, bcW, bcE, y_lo, y_hi));
+    UBGL_LAUNCH(lc, K_PBC, 0, stream, launch_k(k_pbc_cols, ceil_div(y_hi - y_lo, 128), 128, 0, stream, p, bcW, bcE, y_lo, y_hi));
   if (do_s || do_n)
-    UBGL_LAUNCH(lc, K_PBC, 0, stream, k_pbc_rows<<<ceil_div(p.w, 128), 128, 0, stream>>>(p, bcS, bcN, do_s, do_n));
+    UBGL_LAUNCH(lc, K_PBC, 0, stream, launch_k(k_pbc_rows, ceil_div(p.w, 128), 128, 0, stream, p, bcS, bcN, do_s, do_n));
 }
 
 void launch_divergence4(const Grid &vx, const Grid &vy, const Grid &f, const Grid &ax, const Grid &ay,

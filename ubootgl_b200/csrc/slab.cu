@@ -117,6 +117,7 @@ int SlabPlan::max_stored_rows(int l) const {
 // re-armed AFTER the release, and no fence follows the release (nothing later in this kernel
 // depends on it; the peer polls its own memory).
 __global__ void __launch_bounds__(256) k_halo_push(HaloPush a) {
+  ubgl_pdl_prologue();
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t nthreads = (size_t)gridDim.x * blockDim.x;
   for (int s = 0; s < a.nseg; s++) {
@@ -181,7 +182,7 @@ void launch_halo_push(const HaloPush &a, size_t total16, cudaStream_t stream, La
   // load/store pairs per thread, no block counter; larger: ~4 per thread over up to 2 blocks per SM
   int blocks = total16 <= (size_t)(4 << 10) ? 1 : (int)std::min<size_t>(148 * 2, (total16 + 1023) / 1024);
   if (blocks < 1) blocks = 1;
-  UBGL_LAUNCH(lc, K_HALO_PUSH, 0, stream, k_halo_push<<<blocks, 256, 0, stream>>>(a));
+  UBGL_LAUNCH(lc, K_HALO_PUSH, 0, stream, launch_k(k_halo_push, blocks, 256, 0, stream, a));
 }
 
 void launch_halo_wait(unsigned *const *slots, int n, unsigned seq, int *err, cudaStream_t stream,
