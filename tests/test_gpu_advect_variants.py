@@ -46,3 +46,21 @@ def test_divergence_in_the_advect_epilogue_equals_the_separate_pass(ubgl, tmp_pa
         x, y = a[k], b[k]
         same = (x.view(np.uint32) == y.view(np.uint32)) | ((x == 0) & (y == 0))
         assert same.all(), (k, float(np.abs(x - y).max()))
+
+
+def test_programmatic_dependent_launch_changes_nothing(ubgl, tmp_path):
+    """UBGL_PDL=0 (ordinary launches) vs the default (the multigrid passes, border kernels and sink stamps launched
+    with programmatic stream serialization, parked at griddepcontrol.wait): the same bits after the advect stage
+    and two whole steps at six sizes and two CFLs, graph replay included on the small grids."""
+    outs = []
+    for pdl in ("0", "1"):
+        out = str(tmp_path / f"pdl{pdl}.npz")
+        env = dict(os.environ, UBGL_PDL=pdl)
+        env.pop("UBGL_ADVECT_VARIANT", None)
+        subprocess.run([sys.executable, os.path.join(ROOT, "tests", "advect_dump.py"), out], check=True, env=env,
+                       timeout=300)
+        outs.append(np.load(out))
+    a, b = outs
+    assert sorted(a.files) == sorted(b.files) and len(a.files) > 0
+    for k in a.files:
+        assert (a[k].view(np.uint32) == b[k].view(np.uint32)).all(), k

@@ -36,11 +36,20 @@ def sync_from_oracle(G, O):
         G.set(f, O.get(f))
 
 
+FIELD_NAMES = {ob.VX: "vx", ob.VY: "vy", ob.VXB: "vx_back", ob.VYB: "vy_back", ob.P: "p", ob.F: "f",
+               ob.VX_ACCUM: "vx_accum", ob.VY_ACCUM: "vy_accum", ob.VX_CURRENT: "vx_current", ob.VY_CURRENT: "vy_current"}
+
+
 def check(G, O, fields, tol=TOL, what=""):
+    errs = {}
     for f in fields:
         a, b = G.get(f), O.get(f)
         assert a.shape == b.shape
-        assert rel_l2(a, b) <= tol, (what, f, rel_l2(a, b))
+        errs[FIELD_NAMES.get(f, str(f))] = rel_l2(a, b)
+    # measured errors go to gpurun_out/parity_errors.jsonl (profiles/r02_parity_errors.md: worst per stage)
+    cases.record_parity(f"test_gpu_sim: {what} (tol {tol:g})", O.get(ob.P).shape[::-1], "restatement", errs)
+    for k, e in errs.items():
+        assert e <= tol, (what, k, e)
 
 
 @pytest.mark.parametrize("W,H", SIZES)
@@ -53,10 +62,10 @@ def test_stages(ubgl, port, W, H):
     check(G, O, [ob.VX, ob.VY, ob.VX_ACCUM, ob.VY_ACCUM], 1e-7, "accum")
     sync_from_oracle(G, O)
     G.stage(ob.ST_DIFFUSE, dt); O.stage(ob.ST_DIFFUSE, dt)
-    check(G, O, [ob.VX, ob.VY, ob.VXB, ob.VYB], TOL, "diffuse")
+    check(G, O, [ob.VX, ob.VY, ob.VXB, ob.VYB], 2e-7, "diffuse")   # observed <= 7.1e-8 (profiles/r02_parity_errors.md)
     sync_from_oracle(G, O)
     G.stage(ob.ST_ADVECT, dt); O.stage(ob.ST_ADVECT, dt)
-    check(G, O, [ob.VX, ob.VY, ob.VXB, ob.VYB], TOL, "advect")
+    check(G, O, [ob.VX, ob.VY, ob.VXB, ob.VYB], 3e-6, "advect")    # observed <= 1.5e-6
     # untouched entries (skipped octets, last columns) are bit-identical copies
     gx, ox = G.get(ob.VX), O.get(ob.VX)
     stale = ox == c["vx"][::-1] if False else None
@@ -64,8 +73,8 @@ def test_stages(ubgl, port, W, H):
     G.stage(ob.ST_SETVBCS, dt); O.stage(ob.ST_SETVBCS, dt)
     check(G, O, [ob.VX, ob.VY, ob.VXB, ob.VYB], 0.0, "setVBCs2")
     G.stage(ob.ST_PROJECT, dt); O.stage(ob.ST_PROJECT, dt)
-    check(G, O, [ob.F], TOL, "divergence")
-    check(G, O, [ob.P, ob.VX, ob.VY], 2e-5, "project")
+    check(G, O, [ob.F], 1e-7, "divergence")                         # observed 0
+    check(G, O, [ob.P, ob.VX, ob.VY], 3e-6, "project")              # observed <= 1.5e-6
     sync_from_oracle(G, O)
     G.stage(ob.ST_SAVE, dt); O.stage(ob.ST_SAVE, dt)
     check(G, O, [ob.VX_CURRENT, ob.VY_CURRENT], 0.0, "save")
@@ -98,7 +107,7 @@ def test_boundary_condition_kinds(ubgl, port, bcs):
     G.stage(ob.ST_SETVBCS, dt); O.stage(ob.ST_SETVBCS, dt)
     check(G, O, [ob.VX, ob.VY, ob.VXB, ob.VYB], 0.0, "setVBCs")
     G.step(dt); O.step(dt)
-    check(G, O, [ob.VX, ob.VY, ob.P], 5e-5, "step")
+    check(G, O, [ob.VX, ob.VY, ob.P], 2e-6, "step")  # observed <= 8.7e-7
 
 
 @pytest.mark.parametrize("W,H", [(70, 40), (130, 97), (258, 131), (1090, 436)])
@@ -111,7 +120,7 @@ def test_steps_with_sinks(ubgl, port, W, H):
     dt = 0.001
     for k in range(3):
         G.step(dt); O.step(dt)
-        tol = 3e-5 * (k + 1)
+        tol = (7e-6, 1.3e-5, 3.2e-5)[k]  # observed <= 3.3e-6, 6.5e-6, 1.6e-5 (vy at 1090x436): twice that
         check(G, O, [ob.VX, ob.VY, ob.P, ob.VX_CURRENT, ob.VY_CURRENT], tol, f"step {k}")
         assert np.allclose(G.sinks(), O.sinks(), rtol=1e-6, atol=0)
         assert (G.get(ob.VX_ACCUM) == O.get(ob.VX_ACCUM)).all()
@@ -128,9 +137,9 @@ def test_step_host_mirrors(ubgl, port):
                 vy_current=(H - 1, W)).items()}
     G.step_host(dt, flag=c["flag"], vx_accum=ax, vy_accum=ay, **out)
     O.step(dt)
-    assert rel_l2(out["vx"], O.get(ob.VX)) <= 3e-5
-    assert rel_l2(out["vy"], O.get(ob.VY)) <= 3e-5
-    assert rel_l2(out["p"], O.get(ob.P)) <= 3e-5
+    assert rel_l2(out["vx"], O.get(ob.VX)) <= 5e-6  # one step at 130x97: observed <= 1.6e-6
+    assert rel_l2(out["vy"], O.get(ob.VY)) <= 5e-6
+    assert rel_l2(out["p"], O.get(ob.P)) <= 5e-6
     assert (out["vx_current"] == out["vx"]).all() and (out["vy_current"] == out["vy"]).all()
     assert (ax == O.get(ob.VX_ACCUM)).all() and (ay == O.get(ob.VY_ACCUM)).all()
 
@@ -170,7 +179,7 @@ def test_flag_update_rebuilds_pyramid(ubgl, port):
     for l in range(G.mg_levels()):
         assert (G.mg_flagc(l) == O.mg_flagc(l)).all()
     G.step(0.001); O.step(0.001)
-    check(G, O, [ob.VX, ob.VY, ob.P], 3e-5, "step after flag edit")
+    check(G, O, [ob.VX, ob.VY, ob.P], 3.5e-6, "step after flag edit")  # observed <= 1.6e-6
 
 
 def test_tolerance_mode_matches_fixed_count_and_oracle_history(ubgl, port):
