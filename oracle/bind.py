@@ -472,3 +472,40 @@ def have_ref_strict():
 
 def have_port():
     return os.path.exists(PORT_SO)
+
+
+GLSL_SO = os.path.join(HERE, "_ref", "libubgl_glsl.so")
+
+
+def have_glsl():
+    return os.path.exists(GLSL_SO)
+
+
+class Glsl:
+    """oracle/_ref/libubgl_glsl.so: the reference's UNMODIFIED GLSL compute shaders (interp_shader.cs,
+    advect_tracer_points.cs) compiled as C++ through oracle/shim/glsl_shim.hpp and dispatched as the
+    reference's host code does (oracle/glsl_run.cpp).  Same call signatures as Port.colocate /
+    Port.tracers_advect, which it pins."""
+
+    def __init__(self):
+        self.lib = C.CDLL(GLSL_SO)
+        self.lib.glsl_colocate.argtypes = [FP, FP, C.c_int, C.c_int, FP, FP]
+        self.lib.glsl_colocate.restype = None
+        self.lib.glsl_tracers_advect.argtypes = [FP, UP, UP, FP, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
+                                                 C.c_uint, FP, C.c_int, C.c_int, FP, C.c_int, C.c_int]
+        self.lib.glsl_tracers_advect.restype = None
+
+    def colocate(self, vx, vy):
+        ny, nx = vx.shape[0], vy.shape[1]
+        vxy = np.empty((2 * ny - 1, 2 * nx - 1, 2), np.float32)
+        mag = np.empty((2 * ny - 1, 2 * nx - 1), np.float32)
+        self.lib.glsl_colocate(fp(f32(vx)), fp(f32(vy)), nx, ny, fp(vxy), fp(mag))
+        return vxy, mag
+
+    def tracers_advect(self, st, dt, pdim, rand_seed, vxy, flagtex):
+        nt, npts = st["points"].shape[:2]
+        th, tw = vxy.shape[:2]
+        fh, fw = flagtex.shape
+        self.lib.glsl_tracers_advect(fp(st["points"]), st["start"].ctypes.data_as(UP), st["end"].ctypes.data_as(UP),
+                                     fp(st["ages"]), nt, npts, dt, pdim[0], pdim[1], rand_seed & 0xFFFFFFFF,
+                                     fp(f32(vxy)), tw, th, fp(f32(flagtex)), fw, fh)

@@ -3,9 +3,15 @@
  *
  *  1. co-located velocity texture + fluid tracer advection -- GLSL compute
  *     shaders in the reference (interp_shader.cs, advect_tracer_points.cs,
- *     shift_tracers.cs).  They cannot be executed here (no GL context in this
- *     image), so this part is PARITY UNPINNED: it restates the shaders plus
- *     the OpenGL 4.5 core texture-filtering rules they rely on (spec 8.14.2
+ *     shift_tracers.cs).  No GL implementation exists in this image, so the
+ *     shaders are executed as C++: oracle/Makefile compiles the UNMODIFIED .cs
+ *     sources where they lie through oracle/shim/glsl_shim.hpp into
+ *     oracle/_ref/libubgl_glsl.so, and tests/test_oracle_next.py pins this
+ *     restatement on them bit for bit (colocate at 4 sizes, 120 tracer frames
+ *     incl. respawn, ring wrap and freezing).  PINNED on the shader source;
+ *     what stays this project's reading is the texture FILTER arithmetic, which
+ *     the specification leaves open: the restatement and the shim both follow
+ *     the OpenGL 4.5 core texture-filtering rules (spec 8.14.2
  *     "coordinate wrapping and texel selection": u = s*w - 1/2, i0 = floor(u),
  *     alpha = frac(u), wrap = the texture-object default GL_REPEAT, LOD 0 in a
  *     compute shader => magnification filter, whose default is GL_LINEAR) in

@@ -53,3 +53,15 @@ def ref_strict():
         else:
             pytest.skip("oracle/_ref/libubgl_ref_strict.so not available on this box")
     return bind.RefStrict()
+
+
+@pytest.fixture(scope="session")
+def glsl():
+    """The reference's unmodified GLSL compute shaders compiled as C++ (oracle/_ref/libubgl_glsl.so)."""
+    from oracle import bind
+    if not bind.have_glsl():
+        if os.path.exists("/root/reference/advect_tracer_points.cs"):
+            bind.build(ref=True)
+        if not bind.have_glsl():
+            pytest.skip("oracle/_ref/libubgl_glsl.so not available on this box")
+    return bind.Glsl()

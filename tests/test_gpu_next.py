@@ -30,6 +30,32 @@ def test_colocate_bit_exact(ubgl, port, W, H):
     assert (mag.view(np.uint32) == omag.view(np.uint32)).all()
 
 
+@pytest.mark.parametrize("W,H,nt", [(130, 97, 2000), (1090, 436, 20000)])
+def test_tracers_and_texture_against_the_shader_source(ubgl, port, glsl, W, H, nt):
+    """The GPU directly against the reference's GLSL compute shaders (interp_shader.cs,
+    advect_tracer_points.cs: unmodified sources compiled through oracle/shim/glsl_shim.hpp): the co-located
+    velocity / magnitude texture and 60 tracer frames, bit for bit."""
+    flag, O = next_cases.developed_flow(port, W, H, seed=W + 7)
+    G = gpu_twin(ubgl, O, flag)
+    vxy, mag = G.colocate_velocity()
+    svxy, smag = glsl.colocate(O.get(ob.VX_CURRENT), O.get(ob.VY_CURRENT))
+    assert (vxy.view(np.uint32) == svxy.view(np.uint32)).all()
+    assert (mag.view(np.uint32) == smag.view(np.uint32)).all()
+    T = ubgl.Tracers(nt, 30)
+    st = next_cases.tracer_state(nt, 30)
+    pd = (np.float32(0.8), np.float32(0.8) * np.float32(H) / np.float32(W))
+    g = cases.LCG(3)
+    for k in range(60):
+        seed = int(g.u() * 2 ** 31)
+        T.advect(G, 0.02, seed)
+        glsl.tracers_advect(st, 0.02, pd, seed, svxy, flag)
+    gs = T.state()
+    for key in ("points", "ages"):
+        assert (gs[key].view(np.uint32) == st[key].view(np.uint32)).all(), key
+    for key in ("start", "end"):
+        assert (gs[key] == st[key]).all(), key
+
+
 @pytest.mark.parametrize("W,H", [(70, 40), (258, 131), (1090, 436)])
 def test_display_export_into_cuda_arrays(ubgl, port, W, H):
     """8f rank 4: the texels the reference uploads per frame (velocity_textures.cpp:63-93 through

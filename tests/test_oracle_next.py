@@ -167,3 +167,44 @@ def test_shift_map_and_set_grids():
     assert (p[:, :-1][new[:, :-1] == 1] == o["p"][:, 1:][new[:, :-1] == 1]).all()
     assert (p[new == 0] == 0).all()
     assert (vxc == vxf).all() and (vyc == vyf).all()
+
+
+# ---- the GLSL compute shaders themselves, unmodified, executed through oracle/shim/glsl_shim.hpp ----
+@pytest.mark.parametrize("W,H", [(24, 16), (70, 40), (130, 97), (258, 131)])
+def test_colocate_restatement_equals_the_shader_source(port, glsl, W, H):
+    """orc_colocate (and with it k_colocate / the on-the-fly texel evaluation of the tracer kernel, which are
+    bit-exact against it on the GPU) against interp_shader.cs compiled from the reference tree: same bits."""
+    flag, O = next_cases.developed_flow(port, W, H, seed=W)
+    vx, vy = O.get(ob.VX_CURRENT), O.get(ob.VY_CURRENT)
+    a_vxy, a_mag = port.colocate(vx, vy)
+    b_vxy, b_mag = glsl.colocate(vx, vy)
+    assert np.abs(a_vxy).sum() > 0
+    assert (a_vxy.view(np.uint32) == b_vxy.view(np.uint32)).all()
+    assert (a_mag.view(np.uint32) == b_mag.view(np.uint32)).all()
+
+
+@pytest.mark.parametrize("W,H,nt,scale", [(130, 97, 1000, 1), (258, 131, 3000, 1), (130, 97, 700, 2), (70, 40, 300, 3)])
+def test_tracer_restatement_equals_the_shader_source(port, glsl, W, H, nt, scale):
+    """orc_tracers_advect against advect_tracer_points.cs compiled from the reference tree, 120 frames from
+    GLTracers::init's state: every tracer respawns (wang hash + LCG, left-to-right randf() calls), rings wrap,
+    tracers freeze and age in terrain and outside the domain.  Points, ring pointers and ages: same bits."""
+    flag, O = next_cases.developed_flow(port, W, H, seed=H)
+    vxy, _ = glsl.colocate(O.get(ob.VX_CURRENT), O.get(ob.VY_CURRENT))
+    flagtex = np.kron(flag, np.ones((scale, scale), np.float32))  # terrain.flagFullRes at `scale`
+    a, b = next_cases.tracer_state(nt, 30), next_cases.tracer_state(nt, 30)
+    pd = (np.float32(0.8), np.float32(0.8) * np.float32(H) / np.float32(W))
+    g = cases.LCG(11)
+    respawned = frozen = 0
+    for k in range(120):
+        seed = int(g.u() * 2 ** 31)
+        ages_before = a["ages"].copy()
+        port.tracers_advect(a, 0.02, pd, seed, vxy, flagtex)
+        glsl.tracers_advect(b, 0.02, pd, seed, vxy, flagtex)
+        respawned += int((a["ages"] == 0).sum())
+        frozen += int((np.abs(a["ages"] - ages_before - np.float32(0.12)) < 1e-6).sum())
+        for key in ("points", "ages"):
+            assert (a[key].view(np.uint32) == b[key].view(np.uint32)).all(), (k, key)
+        for key in ("start", "end"):
+            assert (a[key] == b[key]).all(), (k, key)
+    assert respawned >= nt and frozen > 0, "respawn / freeze branches not exercised"
+    assert a["end"].max() == 29 or (a["start"] > 0).any(), "ring buffers never wrapped"
