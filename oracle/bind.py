@@ -494,6 +494,14 @@ class Glsl:
         self.lib.glsl_tracers_advect.argtypes = [FP, UP, UP, FP, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
                                                  C.c_uint, FP, C.c_int, C.c_int, FP, C.c_int, C.c_int]
         self.lib.glsl_tracers_advect.restype = None
+        self.lib.glsl_tracers_shift.argtypes = [FP, FP, C.c_int, C.c_int, C.c_float]
+        self.lib.glsl_tracers_shift.restype = None
+
+    def tracers_shift(self, st, shift):
+        """shift_tracers.cs; the ribbon vertices it also moves are rendering state (a scratch array here)."""
+        nt, npts = st["points"].shape[:2]
+        vertices = np.zeros((nt * npts * 2, 2), np.float32)
+        self.lib.glsl_tracers_shift(fp(st["points"]), fp(vertices), nt, npts, shift)
 
     def colocate(self, vx, vy):
         ny, nx = vx.shape[0], vy.shape[1]

@@ -32,7 +32,30 @@ extern uint rng_state;
 void glsl_main();
 } // namespace sh_advect
 
+namespace sh_shift {
+extern int npoints, ntracers;
+extern float shift;
+extern vec2_t *points, *vertices;
+void glsl_main();
+} // namespace sh_shift
+
 extern "C" {
+
+// DrawTracersCS::shiftTracers, draw_tracers_cs.cpp:272-283 (shift_tracers.cs over ntracers * npoints invocations);
+// vertices: 2 vec2 per point (the ribbon geometry, rendering state)
+void glsl_tracers_shift(float *points, float *vertices, int ntracers, int npoints, float shift) {
+  sh_shift::npoints = npoints;
+  sh_shift::ntracers = ntracers;
+  sh_shift::shift = shift;
+  sh_shift::points = reinterpret_cast<vec2_t *>(points);
+  sh_shift::vertices = reinterpret_cast<vec2_t *>(vertices);
+  const int groups = (ntracers * npoints - 1) / 256 + 1;
+  for (int g = 0; g < groups * 256; g++) {
+    gl_GlobalInvocationID.x = (uint)g;
+    gl_GlobalInvocationID.y = gl_GlobalInvocationID.z = 0;
+    sh_shift::glsl_main();
+  }
+}
 
 void glsl_colocate(const float *vx, const float *vy, int nx, int ny, float *vxy, float *mag) {
   using namespace sh_interp;

@@ -1,5 +1,5 @@
 // TEST INFRASTRUCTURE ONLY (oracle/): a GLSL 4.30 subset as C++, so that the reference's
-// UNMODIFIED compute-shader sources (interp_shader.cs, advect_tracer_points.cs) compile and
+// UNMODIFIED compute-shader sources (interp_shader.cs, advect_tracer_points.cs, shift_tracers.cs) compile and
 // run on the CPU, one call of main() per invocation.  This image has no GL implementation
 // (no libGL / libEGL / OSMesa), so this is how the C restatement of the shaders
 // (ubgl_oracle_next.c: orc_colocate, orc_tracers_advect) and the CUDA kernels are pinned to
@@ -88,6 +88,7 @@ typedef ivec2_t ivec2;
 typedef bvec4_t bvec4;
 
 inline vec2_t operator+(const vec2_t &a, const vec2_t &b) { return vec2_t{a.x + b.x, a.y + b.y}; }
+inline vec2_t &operator+=(vec2_t &a, const vec2_t &b) { a.x += b.x; a.y += b.y; return a; }
 inline vec2_t operator*(const vec2_t &a, float s) { return vec2_t{a.x * s, a.y * s}; }
 inline vec2_t operator*(const vec2_t &a, const vec2_t &b) { return vec2_t{a.x * b.x, a.y * b.y}; }
 inline vec2_t operator/(const vec2_t &a, const vec2_t &b) { return vec2_t{a.x / b.x, a.y / b.y}; }

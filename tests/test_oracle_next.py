@@ -206,5 +206,9 @@ def test_tracer_restatement_equals_the_shader_source(port, glsl, W, H, nt, scale
             assert (a[key].view(np.uint32) == b[key].view(np.uint32)).all(), (k, key)
         for key in ("start", "end"):
             assert (a[key] == b[key]).all(), (k, key)
+        if k % 40 == 39:  # the map scrolls: shift_tracers.cs
+            port.tracers_shift(a, np.float32(-0.0123))
+            glsl.tracers_shift(b, np.float32(-0.0123))
+            assert (a["points"].view(np.uint32) == b["points"].view(np.uint32)).all()
     assert respawned >= nt and frozen > 0, "respawn / freeze branches not exercised"
     assert a["end"].max() == 29 or (a["start"] > 0).any(), "ring buffers never wrapped"
