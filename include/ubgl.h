@@ -168,7 +168,11 @@ int ubgl_sim_mg_solve(ubgl_sim_t *sim, int cycles);
 int ubgl_sim_mg_solve_ex(ubgl_sim_t *sim, float h, int zero_gradient_bc, int cycles);
 /* device address + pitch (in floats) of a resident field, for zero-copy
  * producers/consumers (tracers, interop, benchmark input generation).  The
- * velocity buffers rotate roles inside step(): query again after every step. */
+ * velocity buffers rotate roles inside step(): query again after every step.
+ * After a fused step vx_current / vy_current alias the front buffers (they are byte
+ * copies of them, simulation.cpp:16-19, and the copy is not made until somebody is
+ * about to write either side); asking for the pointer of vx, vy, vx_current or
+ * vy_current makes that copy first, so writes through it behave as in the reference. */
 int ubgl_sim_device_ptr(ubgl_sim_t *sim, int field, void **dptr, int *pitch);
 /* per-stage device time of the last step when UBGL_OPT_TIMING=1 */
 int ubgl_sim_stage_ms(ubgl_sim_t *sim, int stage, float *ms);
