@@ -849,8 +849,11 @@ def main():
         if (args.workload or "").startswith("explosion"):
             return run_explosion(args, args.workload)
         return run_single_gpu(args, args.workload or "channel8192")
-    from ubootgl_b200 import slab_bench
-    return slab_bench.run(args, args.workload or "channel32768")
+    from ubootgl_b200 import slab_bench, slab_boot
+    try:
+        return slab_bench.run(args, args.workload or "channel32768")
+    finally:
+        slab_boot.shutdown(barrier=False)  # no collective here: rank 0 is still busy with the CPU baseline
 
 
 if __name__ == "__main__":

@@ -104,6 +104,7 @@ def main():
         print(f"MGPU_EQUIV {'OK' if r['bitwise_ok'] else 'FAIL'} {W}x{H} ranks={world} steps={steps} dt={dt} "
               f"dist_levels={r['dist_levels']} exchanges={r['exchanges']} halo_MB={r['halo_mb']:.1f} "
               f"residual={r['residual']:.6g}", flush=True)
+    slab_boot.shutdown()
     sys.exit(0 if r["bitwise_ok"] else 1)
 
 

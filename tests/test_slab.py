@@ -96,7 +96,8 @@ assert full.shape == (4096, 5) and (full[:2048] == 1).all() and (full[2048:] == 
 assert slab_boot.allreduce_max(rank) == world - 1
 assert slab_boot.allreduce_sum(rank + 1) == world * (world + 1) / 2
 slab_boot.barrier()
-print("GLOO_OK", rank)
+print("GLOO_OK", rank, flush=True)
+slab_boot.shutdown()
 """
 
 

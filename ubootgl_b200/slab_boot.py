@@ -25,6 +25,23 @@ def init_distributed(backend=None):
     return dist.get_rank(), dist.get_world_size()
 
 
+def shutdown(barrier=True):
+    """Tear the process group down before the interpreter exits: a gloo process that exits with the group
+    alive can die in a helper thread's destructor ("terminate called without an active exception"), and
+    NCCL warns about leaked resources."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        if barrier:
+            try:
+                dist.barrier()
+            except Exception:
+                pass
+        try:
+            dist.destroy_process_group()
+        except Exception:
+            pass
+
+
 def blob_exchange():
     """callable(bytes) -> list[bytes]: all-gather of one small blob per rank."""
     import torch
