@@ -354,6 +354,12 @@ def test_current_fields_alias_the_front_until_somebody_writes(ubgl, port):
     G.stage(ob.ST_DIFFUSE, dt)
     assert same(ob.VX_CURRENT) and same(ob.VY_CURRENT)
     assert not (G.get(ob.VX).view(np.uint32) == snap[ob.VX_CURRENT].view(np.uint32)).all()
+    # a raw device pointer may be written through: front and snapshot get buffers of their own first
+    G.step(dt)
+    snap = {f: G.get(f) for f in (ob.VX_CURRENT, ob.VY_CURRENT)}
+    pc, _ = G.device_ptr(ob.VX_CURRENT)
+    pf, _ = G.device_ptr(ob.VX)
+    assert pc != pf and same(ob.VX_CURRENT) and same(ob.VY_CURRENT)
     # setGrids on the device zeroes front velocities in new solids, not the snapshot
     G.step(dt)
     snap = {f: G.get(f) for f in (ob.VX_CURRENT, ob.VY_CURRENT)}
