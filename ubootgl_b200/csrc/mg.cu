@@ -170,6 +170,43 @@ __global__ void k_coarsen_flag(Grid fine, Grid fc, int r_lo, int r_hi) {
   fc.d[(size_t)y * fc.pitch + x] = v;
 }
 
+// ---------------------------------------------------------------------------
+// The same update restricted to the neighbourhoods of a list of edited discs (Terrain::drawCircle
+// craters, terrain.cpp:213-234; one (cx, cy, diam) triple each): a crater touches (2 diam + 1)^2
+// level-0 cells, the whole-field rebuild above reads and writes every level.  A level-l cell can
+// change only if its 3 x 3 fine stencil meets the dirty rectangle of level l-1, and a mask byte only
+// if the cell or one of its four neighbours changed: with the level-0 rectangle [lo, hi] per axis
+// both sets lie inside [(lo >> l) - 2, (hi >> l) + 3].  blockIdx.z = disc; cells outside the
+// rectangles keep their (unchanged) values, cells inside are recomputed to what k_coarsen_flag /
+// k_make_mask would write; overlapping rectangles write the same values twice.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ bool disc_rect_cell(const float *xyd, int level, int w, int h, int &x, int &y) {
+  const int c = blockIdx.z;
+  const int d = (int)xyd[3 * c + 2];
+  const int lox = (int)xyd[3 * c] - d - 1, loy = (int)xyd[3 * c + 1] - d - 1, side = ((2 * d + 3) >> level) + 7;
+  const int tx = blockIdx.x * blockDim.x + threadIdx.x, ty = blockIdx.y * blockDim.y + threadIdx.y;
+  x = (lox >> level) - 2 + tx;
+  y = (loy >> level) - 2 + ty;
+  return tx < side && ty < side && x >= 0 && y >= 0 && x < w && y < h;
+}
+// level 0: the caller's flag field into the solver's own copy (MG::updateFields' flagcs[0] = flag)
+__global__ void k_copy_flag_rects(Grid flag, Grid fc, const float *xyd) {
+  ubgl_pdl_prologue();
+  int x, y;
+  if (!disc_rect_cell(xyd, 0, fc.w, fc.h, x, y)) return;
+  fc.at(x, y) = flag.at(x, y);
+}
+__global__ void k_coarsen_flag_rects(Grid fine, Grid fc, const float *xyd, int level) {
+  ubgl_pdl_prologue();
+  int x, y;
+  if (!disc_rect_cell(xyd, level, fc.w, fc.h, x, y)) return;
+  if (x < 1 || y < 1 || x >= fc.w - 1 || y >= fc.h - 1) return; // border cells stay 1.0
+  const float *a = fine.d + (size_t)(2 * y - 1) * fine.pitch + 2 * x;
+  const float *b = a + fine.pitch, *c = b + fine.pitch;
+  const float s = fw9(a[-1], a[0], a[1], b[-1], b[0], b[1], c[-1], c[0], c[1]);
+  fc.d[(size_t)y * fc.pitch + x] = ((double)s > 0.2) ? 1.0f : 0.0f;
+}
+
 // prolongate (pressure_solver.cpp:134-172): e on the whole fine grid.
 __global__ void k_prolongate(Grid e, Grid ec, Grid flagc, Grid flag) {
   int x = blockIdx.x * blockDim.x + threadIdx.x;
@@ -280,6 +317,28 @@ void DeviceMG::update_fields(const Grid &flag0) {
     if (l + 1 < lv.size())
       launch_make_mask(lv[l].flagc, lv[l].mask, d_nonbinary, stream, lc, (int)l);
   }
+}
+
+// update_fields + the level-0 mask for an edit that wrote only 0.0 / 1.0 inside the boxes of n discs
+// (device list of (cx, cy, diam), diam <= max_diam) into a flag field whose masks are valid and
+// binary: ~2 small launches per level instead of a pass over every level.  Returns false (nothing
+// done) when the preconditions do not hold; the caller then rebuilds everything.
+bool DeviceMG::update_fields_discs(const Grid &flag0, const float *d_xyd, int n, int max_diam) {
+  if (n <= 0 || mask0_src != flag0.d || !mask0_binary) return false;
+  if (flag0.w != lv[0].w || flag0.h != lv[0].h || flag0.pitch != lv[0].pitch) return false;
+  auto grid = [&](int level) {
+    const int side = ((2 * max_diam + 3) >> level) + 7;
+    return dim3(ceil_div(side, 32), ceil_div(side, 8), n);
+  };
+  if (flag0.d != lv[0].flagc.d)
+    UBGL_LAUNCH(lc, K_COARSEN, 0, stream, launch_k(k_copy_flag_rects, grid(0), blk2d(), 0, stream, flag0, lv[0].flagc, d_xyd));
+  launch_make_mask_discs(flag0, mask0, d_xyd, grid(0), 0, stream, lc);
+  for (size_t l = 1; l < lv.size(); l++) {
+    UBGL_LAUNCH(lc, K_COARSEN, (int)l, stream,
+                launch_k(k_coarsen_flag_rects, grid((int)l), blk2d(), 0, stream, lv[l - 1].flagc, lv[l].flagc, d_xyd, (int)l));
+    if (l + 1 < lv.size()) launch_make_mask_discs(lv[l].flagc, lv[l].mask, d_xyd, grid((int)l), (int)l, stream, lc);
+  }
+  return true;
 }
 
 // (Re)build the level-0 stencil mask from the flag grid the caller solves with.

@@ -28,6 +28,7 @@ public:
 
   // MG::updateFields (pressure_solver.hpp:34-57); flag0 is a device grid.
   void update_fields(const Grid &flag0);
+  bool update_fields_discs(const Grid &flag0, const float *d_xyd, int n, int max_diam); // mg.cu
   // MG::solve -> solveLevel(.., level 0) (pressure_solver.cpp:201-248)
   void solve(const Grid &p, const Grid &f, const Grid &flag, float hh, bool zgbc);
 
@@ -96,6 +97,9 @@ void launch_make_mask(const Grid &flag, uint8_t *mask, int *d_nonbinary, cudaStr
                       LaunchCounter *lc, int level, const Rows *rows = nullptr,
                     const Rows *crows = nullptr);
 // MG::updateFields level step on coarse rows [r_lo, r_hi) (mg.cu)
+// the mask bytes in the neighbourhoods of edited discs only (mg.cu: update_fields_discs)
+void launch_make_mask_discs(const Grid &flag, uint8_t *mask, const float *d_xyd, dim3 grid, int level,
+                            cudaStream_t stream, LaunchCounter *lc);
 void launch_coarsen_flag(const Grid &fine, const Grid &fc, int r_lo, int r_hi, cudaStream_t stream,
                          LaunchCounter *lc, int level);
 

@@ -1121,6 +1121,28 @@ __global__ void k_make_mask(Grid flag, uint8_t *mask, int *nonbinary, int r_lo, 
   mask[(size_t)y * flag.pitch + x] = (uint8_t)m;
 }
 
+// k_make_mask for the cells around edited discs (see disc_rect_cell in mg.cu: same rectangle)
+__global__ void k_make_mask_discs(Grid flag, uint8_t *mask, const float *xyd, int level) {
+  ubgl_pdl_prologue();
+  const int c = blockIdx.z;
+  const int d = (int)xyd[3 * c + 2];
+  const int lox = (int)xyd[3 * c] - d - 1, loy = (int)xyd[3 * c + 1] - d - 1, side = ((2 * d + 3) >> level) + 7;
+  const int tx = blockIdx.x * blockDim.x + threadIdx.x, ty = blockIdx.y * blockDim.y + threadIdx.y;
+  const int x = (lox >> level) - 2 + tx, y = (loy >> level) - 2 + ty;
+  if (tx >= side || ty >= side || x < 0 || y < 0 || x >= flag.w || y >= flag.h) return;
+  auto bit = [&](int xx, int yy) -> unsigned {
+    if (xx < 0 || yy < 0 || xx >= flag.w || yy >= flag.h) return 0u;
+    return flag.at(xx, yy) != 0.0f ? 1u : 0u;
+  };
+  const unsigned bc = bit(x, y), bw = bit(x - 1, y), be = bit(x + 1, y), bs = bit(x, y - 1), bn = bit(x, y + 1);
+  const unsigned code = bc ? (bw + be + bs + bn) : 0u;
+  mask[(size_t)y * flag.pitch + x] = (uint8_t)(bc * MB_C | bw * MB_W | (code << 2) | be * MB_E | bs * MB_S | bn * MB_N);
+}
+void launch_make_mask_discs(const Grid &flag, uint8_t *mask, const float *d_xyd, dim3 grid, int level,
+                            cudaStream_t stream, LaunchCounter *lc) {
+  UBGL_LAUNCH(lc, K_COARSEN, level, stream, launch_k(k_make_mask_discs, grid, dim3(32, 8), 0, stream, flag, mask, d_xyd, level));
+}
+
 // ---------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------

@@ -1075,8 +1075,12 @@ int ubgl_sim_draw_circles(ubgl_sim_t *sim, const float *xyd, int n, float val) {
   UBGL_CUDA(cudaMemcpyAsync(d_xyd, hs, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, S.stream));
   S.stage_done();
   UBGL_LAUNCH(&S.lc, K_TERRAIN, 0, S.stream, k_draw_circles<<<n, 256, 0, S.stream>>>(S.field(F_FLAG), d_xyd, n, val));
+  // MG::updateFields + stencil masks (ubootgl_app.cpp:111-112).  The edit wrote 0.0 / 1.0 inside the discs'
+  // boxes only: every level is patched around them (UBGL_DISC_UPDATE=0, non-binary flags: rebuilt whole)
+  int max_d = 0;
+  for (int c = 0; c < n; c++) max_d = std::max(max_d, (int)xyd[3 * c + 2]);
+  S.flag_edited_discs(d_xyd, n, max_d);
   UBGL_CUDA(cudaFreeAsync(d_xyd, S.stream));
-  S.flag_changed(true, true); // MG::updateFields + stencil masks (ubootgl_app.cpp:111-112); cells get 0.0 / 1.0
   UBGL_CATCH
 }
 

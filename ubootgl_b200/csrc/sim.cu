@@ -865,6 +865,16 @@ void DeviceSim::flag_changed(bool pyramid, bool binary_edit) {
   mg->prepare_mask0(flag, keep);
 }
 
+void DeviceSim::flag_edited_discs(const float *d_xyd, int n, int max_diam) {
+  static const bool on = [] {
+    const char *e = getenv("UBGL_DISC_UPDATE");
+    return !(e && e[0] == '0');
+  }();
+  drop_graphs();
+  if (on && mg->update_fields_discs(flag, d_xyd, n, max_diam)) return;
+  flag_changed(true, true);
+}
+
 void DeviceSim::download(int id, float *host) {
   UBGL_REQUIRE(host != nullptr, "download: null host pointer");
   Grid g = field(id);

@@ -105,6 +105,9 @@ public:
   void download(int id, float *host);
   void update_flag(const float *host_flag);
   void flag_changed(bool pyramid, bool binary_edit = false);
+  // a device-side edit of 0.0 / 1.0 values inside the boxes of n discs (cx, cy, diam): patch the flag
+  // pyramid and the stencil masks around them instead of rebuilding every level
+  void flag_edited_discs(const float *d_xyd, int n, int max_diam);
 
   void stage(int st, float dt);
   void step(float dt);
